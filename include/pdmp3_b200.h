@@ -1,0 +1,142 @@
+/* pdmp3_b200.h -- inner C-ABI: host C (parser, batcher, streaming API) -> sm_100a CUDA kernels.
+ *
+ * Plain C types only.  Every entry point returns 0 on success or a negative P3_E* code; the
+ * library has NO CPU fallback: if no CUDA device / kernel image is available the calls fail.
+ *
+ * The batch path replaces, for a whole batch of frames at once, what the reference does per
+ * frame in  Read_Main_L3 -> Read_Huffman (pdmp3.c:1346-1442, 2051-2115)  and
+ * Decode_L3 (pdmp3.c:1024-1060: L3_Requantize 1829, L3_Reorder 1786, L3_Stereo 1911,
+ * L3_Antialias 1706, L3_Hybrid_Synthesis 1752, L3_Frequency_Inversion 1738,
+ * L3_Subband_Synthesis 1978) plus Convert_Frame_S16 (2307).
+ */
+#ifndef PDMP3_B200_H
+#define PDMP3_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P3_OK         0
+#define P3_EINVAL    -1
+#define P3_ENOMEM    -2
+#define P3_ECUDA     -3      /* CUDA runtime / launch failure (p3_last_error() has the text) */
+#define P3_ENODEV    -4      /* no usable sm_100 device: there is no CPU fallback */
+
+/* ---- host-side descriptors produced by the parser (replaces Read_Header 1252-1320,
+ *      Read_Audio_L3 1129-1200 and the bookkeeping of Get_Main_Data 1096-1122) ------------- */
+
+#define P3_FRAME_DECODE 1u   /* decode and emit PCM for this frame                             */
+#define P3_FRAME_NODATA 2u   /* main_data_begin exceeds the reservoir (pdmp3.c:1101): silence   */
+#define P3_FRAME_BAD    4u   /* side info fails validation: silence               */
+#define P3_FRAME_WARMUP 8u   /* decoded for filter state only (shard halo), no PCM emitted     */
+
+typedef struct {             /* 32 bytes, one per MP3 frame */
+  uint64_t main_off;         /* byte offset of this frame's main data inside the raw stream     */
+  uint64_t main_pos;         /* position of that data in the header-stripped main-data stream   */
+  uint16_t main_size;        /* bytes of main data carried by this frame (pdmp3.c:1146-1148)    */
+  uint16_t main_begin;       /* main_data_begin, bytes back into the reservoir (pdmp3.c:1157)   */
+  uint8_t  nch;              /* 1 or 2                                                          */
+  uint8_t  mode;             /* header mode (pdmp3.c:1287)                                      */
+  uint8_t  mode_ext;         /* header mode_extension (pdmp3.c:1288)                            */
+  uint8_t  sfreq;            /* 0: 44.1 kHz, 1: 48 kHz, 2: 32 kHz                                */
+  uint8_t  scfsi;            /* ch0 bands in bits 0-3, ch1 bands in bits 4-7 (pdmp3.c:1163)      */
+  uint8_t  flags;            /* P3_FRAME_*                                                       */
+  uint16_t bitrate_kbps;
+  uint32_t pcm_index;        /* output slot (units of 1152 sample-frames); unused for warm-up    */
+} p3_frame;
+
+typedef struct {             /* 16 bytes, one per granule-channel, order [frame][gr][ch(2)]      */
+  uint32_t w0;               /* part2_3_length:12 big_values:9 global_gain:8 preflag:1 scalefac_scale:1 count1table_select:1 */
+  uint32_t w1;               /* scalefac_compress:4 win_switch:1 block_type:2 mixed:1 table_select0:5 1:5 2:5 region0:4 region1:4 (implicit values reach 13) */
+  uint32_t w2;               /* subblock_gain0:3 1:3 2:3 | part2 start bit rel. to (main_pos-main_begin)*8 :14 */
+  uint32_t w3;               /* reserved, 0 */
+} p3_gc;
+
+#define P3_GC_P23L(g)   ((g).w0 & 0xfffu)
+#define P3_GC_BIGV(g)   (((g).w0 >> 12) & 0x1ffu)
+#define P3_GC_GAIN(g)   (((g).w0 >> 21) & 0xffu)
+#define P3_GC_PREF(g)   (((g).w0 >> 29) & 1u)
+#define P3_GC_SCALE(g)  (((g).w0 >> 30) & 1u)
+#define P3_GC_C1TAB(g)  (((g).w0 >> 31) & 1u)
+#define P3_GC_SFCOMP(g) ((g).w1 & 0xfu)
+#define P3_GC_WINSW(g)  (((g).w1 >> 4) & 1u)
+#define P3_GC_BTYPE(g)  (((g).w1 >> 5) & 3u)
+#define P3_GC_MIXED(g)  (((g).w1 >> 7) & 1u)
+#define P3_GC_TSEL(g,r) (((g).w1 >> (8 + 5 * (r))) & 0x1fu)
+#define P3_GC_REG0(g)   (((g).w1 >> 23) & 0xfu)
+#define P3_GC_REG1(g)   (((g).w1 >> 27) & 0xfu)
+#define P3_GC_SBG(g,w)  (((g).w2 >> (3 * (w))) & 7u)
+#define P3_GC_START(g)  (((g).w2 >> 9) & 0x3fffu)
+
+typedef struct {             /* parser state carried from one batch to the next (streaming)     */
+  uint64_t main_pos;         /* logical main-data bytes seen so far                              */
+  uint32_t top;              /* g_main_data_top of the reference (pdmp3.c:1109,1120)             */
+  uint32_t pcm_index;        /* next output slot                                                 */
+  int32_t  nch, sfreq;       /* format of the last parsed frame (-1 = none yet)                  */
+} p3_parse_state;
+
+typedef struct {
+  int64_t  max_frames;       /* <=0: no limit                                                    */
+  uint32_t lookahead;        /* a frame is read only if >= this many bytes are buffered at its
+                                sync position (reference: 1152, pdmp3.c:2445); 0 = every complete frame */
+  int32_t  nthreads;         /* side-info parse threads (<=0: pick)                              */
+  uint32_t warmup_frames;    /* first N frames flagged WARMUP (no PCM slot)                      */
+} p3_parse_opts;
+
+typedef struct {
+  int64_t  n_frames;
+  p3_frame *frames;          /* malloc'd [n_frames]   */
+  p3_gc    *gcs;             /* malloc'd [n_frames*4] */
+  uint64_t consumed;         /* bytes of `data` used up to the end of the last parsed frame      */
+  int64_t  n_pcm_frames;     /* frames holding a PCM slot                                        */
+  int32_t  stop;             /* 0: ran out of data, 1: max_frames, 2: no sync within 1152 bytes (pdmp3.c:1337) */
+} p3_parsed;
+
+int  p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *opts, p3_parse_state *state, p3_parsed *out);
+void p3_parsed_free(p3_parsed *p);
+
+/* ---- device context ------------------------------------------------------------------------ */
+typedef struct p3_ctx p3_ctx;
+
+#define P3_MODE_EXACT 0      /* direct-form transforms, reference summation order (bit-exact PCM) */
+#define P3_MODE_FAST  1      /* fast transforms (<= 1 LSB of int16 from the reference)            */
+
+int  p3_ctx_create(int device, p3_ctx **out);
+void p3_ctx_destroy(p3_ctx *c);
+int  p3_ctx_reset(p3_ctx *c);                 /* zero overlap / FIFO / reservoir state (pdmp3_open_feed, pdmp3.c:2377-2379) */
+int  p3_ctx_set_mode(p3_ctx *c, int mode);
+const char *p3_last_error(void);
+
+/* Tap buffers (device side, optional; for stage-level parity tests). NULL = not captured. */
+typedef struct {
+  int16_t *is_huff;   /* [n_frames][2][2][576] after Huffman                                    */
+  int32_t *count1;    /* [n_frames][2][2]                                                       */
+  uint8_t *scf;       /* [n_frames][2][2][64]: scalefac_l[21] | pad3 | scalefac_s[12][3] | pad4  */
+  float   *xr;        /* [n_frames][2][2][576] after requantize+reorder+stereo+antialias        */
+  float   *y;         /* [n_frames][2][2][576] after hybrid synthesis + frequency inversion, [sb][18] */
+} p3_taps;
+
+/* Decode a parsed batch.  `raw` is the raw MP3 byte stream the descriptors index into
+ * (host memory; copied to the device inside the call), `pcm` receives
+ * n_pcm_frames*1152*nch int16 (host memory).  State (IMDCT overlap, polyphase FIFO,
+ * reservoir tail) is carried inside the context from call to call.
+ * host_taps: optional host tap buffers (NULL entries skipped). */
+int p3_decode_batch(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *batch,
+                    int16_t *pcm, const p3_taps *host_taps);
+
+/* Device-resident variant used by the benchmark and the multi-GPU driver: upload once, run the
+ * kernels any number of times, download once.  Pointers returned are DEVICE pointers. */
+int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *batch);
+int p3_batch_run(p3_ctx *c);                          /* launches the kernel sequence on the ctx stream */
+int p3_batch_sync(p3_ctx *c);
+int p3_batch_download(p3_ctx *c, int16_t *pcm, const p3_taps *host_taps);
+void *p3_batch_pcm_device(p3_ctx *c, uint64_t *bytes);
+void *p3_ctx_stream(p3_ctx *c);                       /* cudaStream_t of the context */
+int  p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_stage /*[8]*/);  /* CUDA-event timing of p3_batch_run */
+int  p3_kernel_launch_count(p3_ctx *c);               /* kernels launched by the last p3_batch_run */
+
+#ifdef __cplusplus
+}
+#endif
+#endif
