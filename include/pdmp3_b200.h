@@ -50,7 +50,7 @@ typedef struct {             /* 16 bytes, one per granule-channel, order [frame]
   uint32_t w0;               /* part2_3_length:12 big_values:9 global_gain:8 preflag:1 scalefac_scale:1 count1table_select:1 */
   uint32_t w1;               /* scalefac_compress:4 win_switch:1 block_type:2 mixed:1 table_select0:5 1:5 2:5 region0:4 region1:4 (implicit values reach 13) */
   uint32_t w2;               /* subblock_gain0:3 1:3 2:3 | part2 start bit rel. to (main_pos-main_begin)*8 :14 */
-  uint32_t w3;               /* reserved, 0 */
+  uint32_t w3;               /* frames back to the last non-empty part of this [gr][ch] slot (0 = this one; Q6) */
 } p3_gc;
 
 #define P3_GC_P23L(g)   ((g).w0 & 0xfffu)
@@ -90,7 +90,7 @@ typedef struct {
   p3_gc    *gcs;             /* malloc'd [n_frames*4] */
   uint64_t consumed;         /* bytes of `data` used up to the end of the last parsed frame      */
   int64_t  n_pcm_frames;     /* frames holding a PCM slot                                        */
-  int32_t  stop;             /* 0: ran out of data, 1: max_frames, 2: no sync within 1152 bytes (pdmp3.c:1337) */
+  int32_t  stop;             /* 0: ran out of data, 1: max_frames, 2: no sync within 1152 bytes (pdmp3.c:1337), 3: channel count / sample rate changes at `consumed` */
 } p3_parsed;
 
 int  p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *opts, p3_parse_state *state, p3_parsed *out);

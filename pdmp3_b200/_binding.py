@@ -1,0 +1,261 @@
+"""ctypes binding to libpdmp3_b200.so (see include/pdmp3.h and include/pdmp3_b200.h)."""
+import ctypes as C
+import os
+import numpy as np
+
+PDMP3_OK, PDMP3_ERR, PDMP3_NEED_MORE, PDMP3_NEW_FORMAT, PDMP3_NO_SPACE = 0, -1, -10, -11, 7
+PDMP3_ENC_SIGNED_16 = 0x80 | 0x40 | 0x10
+MODE_EXACT, MODE_FAST = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libpdmp3_b200.so")
+
+
+class P3Error(RuntimeError):
+    pass
+
+
+class P3Frame(C.Structure):
+    _fields_ = [("main_off", C.c_uint64), ("main_pos", C.c_uint64), ("main_size", C.c_uint16), ("main_begin", C.c_uint16),
+                ("nch", C.c_uint8), ("mode", C.c_uint8), ("mode_ext", C.c_uint8), ("sfreq", C.c_uint8),
+                ("scfsi", C.c_uint8), ("flags", C.c_uint8), ("bitrate_kbps", C.c_uint16), ("pcm_index", C.c_uint32)]
+
+
+class P3Gc(C.Structure):
+    _fields_ = [("w0", C.c_uint32), ("w1", C.c_uint32), ("w2", C.c_uint32), ("w3", C.c_uint32)]
+
+
+class P3ParseState(C.Structure):
+    _fields_ = [("main_pos", C.c_uint64), ("top", C.c_uint32), ("pcm_index", C.c_uint32), ("nch", C.c_int32), ("sfreq", C.c_int32)]
+
+
+class P3ParseOpts(C.Structure):
+    _fields_ = [("max_frames", C.c_int64), ("lookahead", C.c_uint32), ("nthreads", C.c_int32), ("warmup_frames", C.c_uint32)]
+
+
+class P3Parsed(C.Structure):
+    _fields_ = [("n_frames", C.c_int64), ("frames", C.POINTER(P3Frame)), ("gcs", C.POINTER(P3Gc)),
+                ("consumed", C.c_uint64), ("n_pcm_frames", C.c_int64), ("stop", C.c_int32)]
+
+
+class P3Taps(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("is_huff", "count1", "scf", "xr", "y")]
+
+
+FRAME_DT = np.dtype([("main_off", "<u8"), ("main_pos", "<u8"), ("main_size", "<u2"), ("main_begin", "<u2"),
+                     ("nch", "u1"), ("mode", "u1"), ("mode_ext", "u1"), ("sfreq", "u1"), ("scfsi", "u1"),
+                     ("flags", "u1"), ("bitrate_kbps", "<u2"), ("pcm_index", "<u4")])
+
+_lib = None
+
+
+def lib():
+    """Load the product library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIBPATH):
+        raise P3Error("%s not found: build it with `python -m pdmp3_b200.build` (there is no CPU fallback)" % _LIBPATH)
+    L = C.CDLL(_LIBPATH)
+    L.p3_last_error.restype = C.c_char_p
+    L.p3_parse.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(P3ParseOpts), C.POINTER(P3ParseState), C.POINTER(P3Parsed)]
+    L.p3_parsed_free.argtypes = [C.POINTER(P3Parsed)]
+    L.p3_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.p3_ctx_destroy.argtypes = [C.c_void_p]
+    L.p3_ctx_reset.argtypes = [C.c_void_p]
+    L.p3_ctx_set_mode.argtypes = [C.c_void_p, C.c_int]
+    L.p3_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3Parsed), C.c_void_p, C.POINTER(P3Taps)]
+    L.p3_batch_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3Parsed)]
+    L.p3_batch_run.argtypes = [C.c_void_p]
+    L.p3_batch_sync.argtypes = [C.c_void_p]
+    L.p3_batch_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(P3Taps)]
+    L.p3_batch_pcm_device.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.p3_batch_pcm_device.restype = C.c_void_p
+    L.p3_ctx_stream.argtypes = [C.c_void_p]
+    L.p3_ctx_stream.restype = C.c_void_p
+    L.p3_batch_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.p3_kernel_launch_count.argtypes = [C.c_void_p]
+    for name in ("pdmp3_new", "pdmp3_delete", "pdmp3_open_feed", "pdmp3_feed", "pdmp3_read", "pdmp3_decode", "pdmp3_getformat"):
+        if not hasattr(L, name):
+            break
+    else:
+        L.pdmp3_new.restype = C.c_void_p
+        L.pdmp3_new.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+        L.pdmp3_delete.argtypes = [C.c_void_p]
+        L.pdmp3_open_feed.argtypes = [C.c_void_p]
+        L.pdmp3_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.pdmp3_read.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.pdmp3_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.pdmp3_getformat.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    _lib = L
+    return L
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise P3Error("%s failed (%d): %s" % (what, rc, lib().p3_last_error().decode(errors="replace")))
+
+
+class Parsed:
+    """Owns a p3_parsed (host descriptors of one batch)."""
+
+    def __init__(self, stream, lookahead=0, max_frames=0, warmup=0, nthreads=0, state=None):
+        self.stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        self.c = P3Parsed()
+        self.state = state if state is not None else P3ParseState(0, 0, 0, -1, -1)
+        o = P3ParseOpts(max_frames, lookahead, nthreads, warmup)
+        _check(lib().p3_parse(self.stream.ctypes.data, len(self.stream), C.byref(o), C.byref(self.state), C.byref(self.c)), "p3_parse")
+
+    n_frames = property(lambda s: s.c.n_frames)
+    n_pcm_frames = property(lambda s: s.c.n_pcm_frames)
+    consumed = property(lambda s: s.c.consumed)
+    stop = property(lambda s: s.c.stop)
+
+    @property
+    def nch(self):
+        return int(self.c.frames[0].nch) if self.c.n_frames else 2
+
+    def frames(self):
+        n = self.c.n_frames
+        return np.frombuffer(C.string_at(self.c.frames, 32 * n), dtype=FRAME_DT).copy() if n else np.zeros(0, FRAME_DT)
+
+    def gcs(self):
+        n = self.c.n_frames
+        return np.frombuffer(C.string_at(self.c.gcs, 64 * n), dtype=np.uint32).reshape(n, 4, 4).copy() if n else np.zeros((0, 4, 4), np.uint32)
+
+    def __del__(self):
+        try:
+            lib().p3_parsed_free(C.byref(self.c))
+        except Exception:
+            pass
+
+
+def parse_stream(stream, **kw):
+    return Parsed(stream, **kw)
+
+
+class Context:
+    """Device context of the batch C-ABI (p3_ctx)."""
+
+    def __init__(self, device=0, mode=MODE_EXACT):
+        self.h = C.c_void_p()
+        _check(lib().p3_ctx_create(device, C.byref(self.h)), "p3_ctx_create")
+        self.set_mode(mode)
+
+    def set_mode(self, mode):
+        _check(lib().p3_ctx_set_mode(self.h, mode), "p3_ctx_set_mode")
+
+    def reset(self):
+        _check(lib().p3_ctx_reset(self.h), "p3_ctx_reset")
+
+    def close(self):
+        if self.h:
+            lib().p3_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _taps(self, n):
+        arrs = dict(is_huff=np.zeros((n, 2, 2, 576), np.int16), count1=np.zeros((n, 2, 2), np.int32),
+                    scf=np.zeros((n, 2, 2, 64), np.uint8), xr=np.zeros((n, 2, 2, 576), np.float32),
+                    y=np.zeros((n, 2, 2, 576), np.float32))
+        return arrs, P3Taps(**{k: a.ctypes.data for k, a in arrs.items()})
+
+    def decode_parsed(self, parsed, taps=False):
+        """Host buffers in, host buffers out (copies inside). -> pcm [n_pcm_frames,1152,nch] (+ taps dict)."""
+        n = parsed.n_frames
+        pcm = np.zeros((parsed.n_pcm_frames, 1152, parsed.nch), np.int16)
+        arrs, t = self._taps(n) if taps else ({}, None)
+        _check(lib().p3_decode_batch(self.h, parsed.stream.ctypes.data, len(parsed.stream), C.byref(parsed.c),
+                                     pcm.ctypes.data, C.byref(t) if taps else None), "p3_decode_batch")
+        if taps:
+            # y is produced slot-major [18][32]; present it in the reference's [sb][18] layout
+            arrs["y"] = np.ascontiguousarray(arrs["y"].reshape(n, 2, 2, 18, 32).transpose(0, 1, 2, 4, 3)).reshape(n, 2, 2, 576)
+            arrs["scf_l"] = arrs["scf"][..., :21].copy()
+            arrs["scf_s"] = arrs["scf"][..., 24:60].reshape(n, 2, 2, 12, 3).copy()
+            return pcm, arrs
+        return pcm
+
+    def decode(self, stream, lookahead=0, taps=False, **kw):
+        return self.decode_parsed(Parsed(stream, lookahead=lookahead, **kw), taps=taps)
+
+    # device-resident path (bench)
+    def upload(self, parsed):
+        _check(lib().p3_batch_upload(self.h, parsed.stream.ctypes.data, len(parsed.stream), C.byref(parsed.c)), "p3_batch_upload")
+        self._up = parsed
+
+    def run(self):
+        _check(lib().p3_batch_run(self.h), "p3_batch_run")
+
+    def sync(self):
+        _check(lib().p3_batch_sync(self.h), "p3_batch_sync")
+
+    def download(self):
+        p = self._up
+        pcm = np.zeros((p.n_pcm_frames, 1152, p.nch), np.int16)
+        _check(lib().p3_batch_download(self.h, pcm.ctypes.data, None), "p3_batch_download")
+        return pcm
+
+    def time(self, iters=5):
+        tot = C.c_float(); st = (C.c_float * 8)()
+        _check(lib().p3_batch_time(self.h, iters, C.byref(tot), st), "p3_batch_time")
+        return tot.value, [st[i] for i in range(4)]
+
+    def launch_count(self):
+        return lib().p3_kernel_launch_count(self.h)
+
+
+class Decoder:
+    """The reference's streaming API, one method per function (pdmp3.c:2351-2535)."""
+
+    def __init__(self, options=None):
+        L = lib()
+        if not hasattr(L, "pdmp3_new"):
+            raise P3Error("libpdmp3_b200.so lacks the pdmp3_* streaming API")
+        err = C.c_int(0)
+        self.h = L.pdmp3_new(options.encode() if options else None, C.byref(err))
+        if not self.h:
+            raise P3Error("pdmp3_new failed: %s" % L.p3_last_error().decode(errors="replace"))
+
+    def open_feed(self):
+        return lib().pdmp3_open_feed(self.h)
+
+    def feed(self, data):
+        b = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data, dtype=np.uint8)
+        return lib().pdmp3_feed(self.h, b.ctypes.data if len(b) else None, len(b))
+
+    def read(self, outsize):
+        out = np.zeros(outsize, np.uint8); done = C.c_size_t(0)
+        rc = lib().pdmp3_read(self.h, out.ctypes.data if outsize else None, outsize, C.byref(done))
+        return rc, out[:done.value]
+
+    def read_into(self, out):
+        done = C.c_size_t(0)
+        rc = lib().pdmp3_read(self.h, out.ctypes.data, out.nbytes, C.byref(done))
+        return rc, done.value
+
+    def decode(self, data, outsize):
+        b = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data, dtype=np.uint8)
+        out = np.zeros(max(outsize, 1), np.uint8); done = C.c_size_t(0)
+        rc = lib().pdmp3_decode(self.h, b.ctypes.data, len(b), out.ctypes.data if outsize else None, outsize, C.byref(done))
+        return rc, out[:done.value]
+
+    def getformat(self):
+        rate = C.c_long(); ch = C.c_int(); enc = C.c_int()
+        rc = lib().pdmp3_getformat(self.h, C.byref(rate), C.byref(ch), C.byref(enc))
+        return rc, rate.value, ch.value, enc.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().pdmp3_delete(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

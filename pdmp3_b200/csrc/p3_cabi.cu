@@ -1,0 +1,262 @@
+/* p3_cabi.cu -- the thin C-ABI between the plain-C host side and the sm_100a kernels
+ * (include/pdmp3_b200.h).  Owns device memory, the stream, the carried decoder state and the
+ * kernel launch sequence K1..K4, which is the device-side Decode_L3 (pdmp3.c:1024-1060). */
+#include "p3_device.cuh"
+#include "p3_kernels.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+
+static thread_local char g_err[512];
+static int fail(int code, const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); return code; }
+extern "C" const char *p3_last_error(void) { return g_err; }
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(P3_ECUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct dbuf { void *p; size_t cap; };
+static int ensure(dbuf *b, size_t n)
+{
+  if (n <= b->cap) return P3_OK;
+  if (b->p) cudaFree(b->p);
+  b->p = NULL; b->cap = 0;
+  size_t want = n + n / 8 + 256;
+  cudaError_t e = cudaMalloc(&b->p, want);
+  if (e != cudaSuccess) return fail(P3_ENOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+  b->cap = want;
+  return P3_OK;
+}
+
+struct p3_ctx {
+  int device, mode;
+  cudaStream_t stream;
+  cudaEvent_t ev[10];
+  p3_tables *d_tables;
+  p3_state *d_state[2]; int cur;          /* double-buffered carried state: kernels read [cur], write [cur^1] */
+  uint8_t *d_tail; uint8_t h_tail[512];   /* last 512 main-data bytes before the current batch */
+  dbuf raw, frames, gcs, is16, count1, scf, xr, y, pcm;
+  /* current batch */
+  int64_t n_frames, n_pcm_frames; uint32_t nch; uint64_t raw_bytes;
+  uint32_t k1_smem_words; int64_t chunk_frames;
+  p3_frame *h_frames_last; /* unused */
+  int launches;
+  uint8_t next_tail[512]; int have_next_tail;
+};
+
+extern "C" int p3_ctx_create(int device, p3_ctx **out)
+{
+  int ndev = 0;
+  if (!out) return fail(P3_EINVAL, "null out");
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(P3_ENODEV, "no CUDA device (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(P3_ENODEV, "device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(P3_ENODEV, "device %d is sm_%d%d; kernels are built for sm_100a only", device, prop.major, prop.minor);
+  CK(cudaSetDevice(device));
+  p3_ctx *c = (p3_ctx *)calloc(1, sizeof *c);
+  if (!c) return fail(P3_ENOMEM, "calloc");
+  c->device = device; c->mode = P3_MODE_EXACT;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 10; i++) CK(cudaEventCreate(&c->ev[i]));
+  CK(cudaMalloc(&c->d_tables, sizeof(p3_tables)));
+  CK(cudaMemcpy(c->d_tables, p3_tables_get(), sizeof(p3_tables), cudaMemcpyHostToDevice));
+  for (int i = 0; i < 2; i++) { CK(cudaMalloc(&c->d_state[i], sizeof(p3_state))); CK(cudaMemset(c->d_state[i], 0, sizeof(p3_state))); }
+  CK(cudaMalloc(&c->d_tail, 512)); CK(cudaMemset(c->d_tail, 0, 512));
+  CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(k_polyphase, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  c->chunk_frames = 1 << 18;
+  *out = c;
+  return P3_OK;
+}
+
+extern "C" void p3_ctx_destroy(p3_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  dbuf *bs[] = {&c->raw, &c->frames, &c->gcs, &c->is16, &c->count1, &c->scf, &c->xr, &c->y, &c->pcm};
+  for (dbuf *b : bs) if (b->p) cudaFree(b->p);
+  cudaFree(c->d_tables); cudaFree(c->d_state[0]); cudaFree(c->d_state[1]); cudaFree(c->d_tail);
+  for (int i = 0; i < 10; i++) cudaEventDestroy(c->ev[i]);
+  cudaStreamDestroy(c->stream);
+  free(c);
+}
+
+extern "C" int p3_ctx_reset(p3_ctx *c)
+{
+  if (!c) return fail(P3_EINVAL, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 2; i++) CK(cudaMemset(c->d_state[i], 0, sizeof(p3_state)));
+  CK(cudaMemset(c->d_tail, 0, 512));
+  memset(c->h_tail, 0, 512); c->have_next_tail = 0;
+  return P3_OK;
+}
+
+extern "C" int p3_ctx_set_mode(p3_ctx *c, int mode) { if (!c || (mode != P3_MODE_EXACT && mode != P3_MODE_FAST)) return fail(P3_EINVAL, "bad mode"); c->mode = mode; return P3_OK; }
+extern "C" void *p3_ctx_stream(p3_ctx *c) { return c ? (void *)c->stream : NULL; }
+extern "C" int p3_kernel_launch_count(p3_ctx *c) { return c ? c->launches : 0; }
+
+/* last 512 bytes of the batch's header-stripped main-data stream (host side, tiny) */
+static void compute_tail(const uint8_t *raw, const p3_parsed *b, const uint8_t prev_tail[512], uint8_t out[512])
+{
+  int filled = 0;
+  for (int64_t f = b->n_frames - 1; f >= 0 && filled < 512; f--) {
+    int n = b->frames[f].main_size, take = n < 512 - filled ? n : 512 - filled;
+    memcpy(out + 512 - filled - take, raw + b->frames[f].main_off + n - take, (size_t)take);
+    filled += take;
+  }
+  if (filled < 512) memcpy(out, prev_tail + filled, (size_t)(512 - filled));
+}
+
+extern "C" int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *b)
+{
+  if (!c || !raw || !b) return fail(P3_EINVAL, "null argument");
+  CK(cudaSetDevice(c->device));
+  int64_t nf = b->n_frames;
+  c->n_frames = nf; c->n_pcm_frames = b->n_pcm_frames; c->raw_bytes = raw_bytes;
+  c->nch = nf ? b->frames[0].nch : 2;
+  if (nf == 0) return P3_OK;
+  for (int64_t f = 1; f < nf; f++)
+    if (b->frames[f].nch != c->nch) return fail(P3_EINVAL, "channel count changes inside a batch (frame %lld)", (long long)f);
+  int rc;
+  if ((rc = ensure(&c->raw, raw_bytes + 64))) return rc;
+  if ((rc = ensure(&c->frames, (size_t)nf * sizeof(p3_frame)))) return rc;
+  if ((rc = ensure(&c->gcs, (size_t)nf * 4 * sizeof(p3_gc)))) return rc;
+  if ((rc = ensure(&c->pcm, (size_t)(b->n_pcm_frames ? b->n_pcm_frames : 1) * 1152 * c->nch * sizeof(int16_t)))) return rc;
+  int64_t cf = nf < c->chunk_frames ? nf : c->chunk_frames;
+  if ((rc = ensure(&c->is16, (size_t)cf * 4 * 576 * 2))) return rc;
+  if ((rc = ensure(&c->count1, (size_t)cf * 4 * 4))) return rc;
+  if ((rc = ensure(&c->scf, (size_t)cf * 4 * P3_SCF_STRIDE))) return rc;
+  if ((rc = ensure(&c->xr, (size_t)cf * 4 * 576 * 4))) return rc;
+  if ((rc = ensure(&c->y, (size_t)cf * 4 * 576 * 4))) return rc;
+  /* K1 shared-memory window: 512 reservoir bytes + the largest group of K1_FPB frames */
+  uint64_t maxg = 0;
+  for (int64_t f0 = 0; f0 < nf; f0 += K1_FPB) {
+    int64_t f1 = f0 + K1_FPB < nf ? f0 + K1_FPB : nf;
+    uint64_t span = b->frames[f1 - 1].main_pos + b->frames[f1 - 1].main_size - b->frames[f0].main_pos;
+    if (span > maxg) maxg = span;
+  }
+  c->k1_smem_words = (uint32_t)((512 + maxg + 16 + 3) / 4);
+  if ((size_t)c->k1_smem_words * 4 + sizeof(((p3_tables *)0)->hlut) > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
+  CK(cudaMemcpyAsync(c->raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->frames.p, b->frames, (size_t)nf * sizeof(p3_frame), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->gcs.p, b->gcs, (size_t)nf * 4 * sizeof(p3_gc), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_tail, c->h_tail, 512, cudaMemcpyHostToDevice, c->stream));
+  compute_tail(raw, b, c->h_tail, c->next_tail); c->have_next_tail = 1;
+  return P3_OK;
+}
+
+/* Launch K1..K4 over frames [f0,f1) of the uploaded batch.  ev != NULL: record stage events. */
+static int run_chunk(p3_ctx *c, int64_t f0, int64_t f1, cudaEvent_t *ev)
+{
+  const p3_frame *fr = (const p3_frame *)c->frames.p; const p3_gc *gc = (const p3_gc *)c->gcs.p;
+  const int64_t nf = f1 - f0;
+  p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
+  CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));   /* fields a launch does not rewrite carry over */
+  if (ev) CK(cudaEventRecord(ev[0], c->stream));
+  size_t smem1 = (size_t)c->k1_smem_words * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
+  k_huffman<<<(unsigned)((nf + K1_FPB - 1) / K1_FPB), K1_THREADS, smem1, c->stream>>>(
+      (const uint8_t *)c->raw.p, fr, gc, c->d_tables, c->d_tail, f0, f1, c->k1_smem_words,
+      (int16_t *)c->is16.p, (int32_t *)c->count1.p, (uint8_t *)c->scf.p);
+  if (ev) CK(cudaEventRecord(ev[1], c->stream));
+  k_requant<<<(unsigned)(2 * nf), K2_THREADS, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, (const int16_t *)c->is16.p,
+      (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so, (float *)c->xr.p);
+  if (ev) CK(cudaEventRecord(ev[2], c->stream));
+  k_imdct<<<(unsigned)(4 * nf), K3_THREADS, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, (const float *)c->xr.p, si, so, (float *)c->y.p);
+  if (ev) CK(cudaEventRecord(ev[3], c->stream));
+  size_t smem4 = (size_t)(2048 + 512 + 2 * (15 + K4_SLOTS) * 96) * 4;
+  k_polyphase<<<(unsigned)((2 * nf + K4_GRAN - 1) / K4_GRAN), K4_THREADS, smem4, c->stream>>>(fr, c->d_tables, f0, f1,
+      (const float *)c->y.p, si, so, (int16_t *)c->pcm.p);
+  if (ev) CK(cudaEventRecord(ev[4], c->stream));
+  CK(cudaGetLastError());
+  c->cur ^= 1;
+  c->launches += 4;
+  return P3_OK;
+}
+
+extern "C" int p3_batch_run(p3_ctx *c)
+{
+  if (!c) return fail(P3_EINVAL, "null ctx");
+  CK(cudaSetDevice(c->device));
+  c->launches = 0;
+  for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames) {
+    int64_t f1 = f0 + c->chunk_frames < c->n_frames ? f0 + c->chunk_frames : c->n_frames;
+    int rc = run_chunk(c, f0, f1, NULL);
+    if (rc) return rc;
+  }
+  return P3_OK;
+}
+
+extern "C" int p3_batch_sync(p3_ctx *c)
+{
+  if (!c) return fail(P3_EINVAL, "null ctx");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return P3_OK;
+}
+
+extern "C" void *p3_batch_pcm_device(p3_ctx *c, uint64_t *bytes)
+{
+  if (bytes) *bytes = (uint64_t)c->n_pcm_frames * 1152 * c->nch * sizeof(int16_t);
+  return c->pcm.p;
+}
+
+extern "C" int p3_batch_download(p3_ctx *c, int16_t *pcm, const p3_taps *t)
+{
+  if (!c) return fail(P3_EINVAL, "null ctx");
+  CK(cudaSetDevice(c->device));
+  if (pcm && c->n_pcm_frames)
+    CK(cudaMemcpyAsync(pcm, c->pcm.p, (size_t)c->n_pcm_frames * 1152 * c->nch * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
+  if (t) {
+    if (c->n_frames > c->chunk_frames) return fail(P3_EINVAL, "taps need the batch to fit one chunk (%lld frames)", (long long)c->chunk_frames);
+    size_t ngc = (size_t)c->n_frames * 4;
+    if (t->is_huff) CK(cudaMemcpyAsync(t->is_huff, c->is16.p, ngc * 576 * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (t->count1)  CK(cudaMemcpyAsync(t->count1, c->count1.p, ngc * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (t->scf)     CK(cudaMemcpyAsync(t->scf, c->scf.p, ngc * P3_SCF_STRIDE, cudaMemcpyDeviceToHost, c->stream));
+    if (t->xr)      CK(cudaMemcpyAsync(t->xr, c->xr.p, ngc * 576 * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (t->y)       CK(cudaMemcpyAsync(t->y, c->y.p, ngc * 576 * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return P3_OK;
+}
+
+extern "C" int p3_decode_batch(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *b, int16_t *pcm, const p3_taps *t)
+{
+  int rc;
+  if ((rc = p3_batch_upload(c, raw, raw_bytes, b))) return rc;
+  if ((rc = p3_batch_run(c))) return rc;
+  if ((rc = p3_batch_download(c, pcm, t))) return rc;
+  if (c->have_next_tail) { memcpy(c->h_tail, c->next_tail, 512); c->have_next_tail = 0; }   /* reservoir for the next batch */
+  return P3_OK;
+}
+
+/* CUDA-event timing of the kernel sequence with everything resident in HBM.  The carried state is
+ * restored before every iteration so that each one decodes the same thing.  ms_stage: K1..K4. */
+extern "C" int p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_stage)
+{
+  if (!c || iters <= 0) return fail(P3_EINVAL, "bad argument");
+  CK(cudaSetDevice(c->device));
+  p3_state *save; CK(cudaMalloc(&save, sizeof(p3_state)));
+  CK(cudaMemcpyAsync(save, c->d_state[c->cur], sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
+  float tot = 0, st[4] = {0, 0, 0, 0};
+  for (int it = 0; it < iters; it++) {
+    CK(cudaMemcpyAsync(c->d_state[c->cur], save, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
+    c->launches = 0;
+    CK(cudaEventRecord(c->ev[8], c->stream));
+    for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames) {
+      int64_t f1 = f0 + c->chunk_frames < c->n_frames ? f0 + c->chunk_frames : c->n_frames;
+      bool single = c->n_frames <= c->chunk_frames;
+      int rc = run_chunk(c, f0, f1, single ? c->ev : NULL);
+      if (rc) { cudaFree(save); return rc; }
+    }
+    CK(cudaEventRecord(c->ev[9], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms; CK(cudaEventElapsedTime(&ms, c->ev[8], c->ev[9])); tot += ms;
+    if (c->n_frames <= c->chunk_frames)
+      for (int k = 0; k < 4; k++) { CK(cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1])); st[k] += ms; }
+  }
+  cudaFree(save);
+  if (ms_total) *ms_total = tot / iters;
+  if (ms_stage) for (int k = 0; k < 4; k++) ms_stage[k] = st[k] / iters;
+  return P3_OK;
+}

@@ -1,0 +1,486 @@
+/* p3_kernels.cu -- hand-written sm_100a kernels for the MP3 Layer III granule decode path.
+ *
+ *   k_huffman   K1  scalefactors + Huffman      (Read_Main_L3 1376-1435, Read_Huffman 2051-2115,
+ *                                                Huffman_Decode 1593-1643)
+ *   k_requant   K2  requantize+reorder+stereo+antialias, fused
+ *                                               (L3_Requantize 1829-1905, L3_Reorder 1786-1823,
+ *                                                L3_Stereo 1911-1972, L3_Antialias 1706-1732)
+ *   k_imdct     K3  IMDCT + window + overlap-add + frequency inversion
+ *                                               (IMDCT_Win 1649-1700, L3_Hybrid_Synthesis 1752-1780,
+ *                                                L3_Frequency_Inversion 1738-1746)
+ *   k_polyphase K4  matrixing + 512-tap window + int16 pack
+ *                                               (L3_Subband_Synthesis 1978-2045, Convert_Frame_S16 2307-2345)
+ *
+ * Arithmetic notes: the reference is compiled without FMA, sums run in index
+ * order in fp32, MS stereo multiplies by a double constant, the final PCM scale is a double
+ * multiply followed by truncation.  In P3_MODE_EXACT every one of these roundings is reproduced
+ * with __fmul_rn/__fadd_rn (which nvcc never contracts), so PCM is bit-identical.
+ */
+#include "p3_device.cuh"
+#include "p3_kernels.h"
+
+/* =============================================================================================
+ * K1: Huffman.  One CTA per group of K1_FPB frames, one thread per granule-channel.
+ * The group's main data (plus up to 512 bytes of reservoir before it) is gathered from the raw
+ * stream into shared memory as big-endian words -- the "bit reservoir" of Get_Main_Data
+ * (pdmp3.c:1096-1122) for the whole group at once; header and side-info bytes never reach smem.
+ * ============================================================================================= */
+__device__ __forceinline__ void k1_decode_pairs(const uint32_t *sw, const uint16_t *lut, uint32_t &pos,
+                                                uint32_t base, uint32_t pbits, uint32_t linbits,
+                                                int16_t *out, uint32_t from, uint32_t to)
+{
+  for (uint32_t i = from; i < to; i += 2) {
+    uint32_t w = p3_peek32(sw, pos);
+    uint32_t cw = pbits, used = 0;
+    uint32_t e = lut[base + (w >> (32 - cw))];
+    while (e & 0x8000u) {                               /* next LUT level */
+      used += cw; cw = (e >> 10) & 7;
+      e = lut[base + (e & 1023u) + ((w << used) >> (32 - cw))];
+    }
+    used += (e >> 8) & 31;
+    int x = (e >> 4) & 15, y = e & 15;
+    if (linbits) { pos += used; w = p3_peek32(sw, pos); used = 0; }   /* room for 2 x (13 linbits + sign) */
+    else w <<= used;                                                /* w: next unread bit at the MSB */
+    uint32_t u2 = 0;
+    if (linbits && x == 15) { x += (int)(w >> (32 - linbits)); w <<= linbits; u2 += linbits; }
+    if (x) { if (w >> 31) x = -x; w <<= 1; u2++; }
+    if (linbits && y == 15) { y += (int)(w >> (32 - linbits)); w <<= linbits; u2 += linbits; }
+    if (y) { if (w >> 31) y = -y; u2++; }
+    pos += used + u2;
+    *reinterpret_cast<uint32_t *>(out + i) = (uint32_t)(x & 0xffff) | ((uint32_t)y << 16);
+  }
+}
+
+extern "C" __global__ void __launch_bounds__(K1_THREADS)
+k_huffman(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
+          const p3_tables *__restrict__ T, const uint8_t *__restrict__ tail /*512 B before the batch*/,
+          int64_t f_first, int64_t f_end /*frames [f_first,f_end) decoded by this launch*/,
+          uint32_t smem_words, int16_t *__restrict__ is_out, int32_t *__restrict__ count1_out, uint8_t *__restrict__ scf_out)
+{
+  extern __shared__ uint32_t sm[];
+  uint32_t *sw = sm;                                     /* main-data words */
+  uint16_t *lut = reinterpret_cast<uint16_t *>(sm + smem_words);
+  __shared__ int64_t s_fb;
+
+  const int64_t F0 = f_first + (int64_t)blockIdx.x * K1_FPB;
+  const int64_t F1 = min(F0 + (int64_t)K1_FPB, f_end);
+  const uint64_t base0 = frames[F0].main_pos;            /* smem byte 512 <-> logical byte base0 */
+
+  for (uint32_t i = threadIdx.x; i < T->hlut_used; i += blockDim.x) lut[i] = T->hlut[i];
+  for (uint32_t i = threadIdx.x; i < smem_words; i += blockDim.x) sw[i] = 0;
+  if (threadIdx.x == 0) {                                /* earliest frame whose data reaches into the window */
+    int64_t fs = F0; uint32_t acc = 0;
+    while (fs > 0 && acc < 512) { fs--; acc += frames[fs].main_size; }
+    s_fb = fs;
+  }
+  __syncthreads();
+  uint8_t *sb8 = reinterpret_cast<uint8_t *>(sw);
+  {
+    /* bytes that precede frame 0 of the batch come from the context's tail buffer */
+    const int64_t fb = s_fb;
+    const int64_t lo = (int64_t)base0 - 512;             /* logical position of smem byte 0 */
+    if (fb == 0) {
+      int64_t first = (int64_t)frames[0].main_pos;       /* logical start of the batch */
+      for (int64_t L = lo + threadIdx.x; L < first; L += blockDim.x) {
+        int64_t back = first - L;                        /* 1..512 */
+        if (back <= 512) sb8[(uint32_t)(L - lo) ^ 3u] = tail[512 - back];
+      }
+    }
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (int64_t fs = fb + warp; fs < F1; fs += nwarp) {
+      const uint8_t *src = raw + frames[fs].main_off;
+      int64_t d0 = (int64_t)frames[fs].main_pos - lo;    /* smem byte of the frame's first data byte */
+      int32_t n = frames[fs].main_size;
+      for (int32_t b = lane; b < n; b += 32) {
+        int64_t d = d0 + b;
+        if (d >= 0) sb8[(uint32_t)d ^ 3u] = src[b];
+      }
+    }
+  }
+  __syncthreads();
+
+  const uint32_t gi = threadIdx.x;                        /* granule-channel within the group */
+  const int64_t f = F0 + (gi >> 2);
+  if (f >= F1) return;
+  const uint32_t gr = (gi >> 1) & 1, ch = gi & 1;
+  const p3_frame fr = frames[f];
+  const p3_gc g = gcs[4 * f + 2 * gr + ch];
+  const int64_t o = (f - f_first) * 4 + 2 * gr + ch;
+  int16_t *out = is_out + o * 576;
+  uint8_t *scf = scf_out + o * P3_SCF_STRIDE;
+  const bool live = ch < fr.nch && !(fr.flags & (P3_FRAME_NODATA | P3_FRAME_BAD)) && P3_GC_P23L(g) != 0;
+  for (int i = 0; i < P3_SCF_STRIDE / 4; i++) reinterpret_cast<uint32_t *>(scf)[i] = 0;
+  if (!live) {
+    for (int i = 0; i < 288; i++) reinterpret_cast<uint32_t *>(out)[i] = 0;
+    count1_out[o] = 0;
+    if (!(ch < fr.nch) || (fr.flags & (P3_FRAME_NODATA | P3_FRAME_BAD))) return;
+  }
+
+  const uint32_t fstart = (uint32_t)((int64_t)fr.main_pos - fr.main_begin - ((int64_t)base0 - 512)) * 8u;
+  uint32_t pos = fstart + P3_GC_START(g);
+  const uint32_t part2_start = pos;
+  const bool is_short = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
+  const uint32_t slen1 = T->slen[P3_GC_SFCOMP(g)][0], slen2 = T->slen[P3_GC_SFCOMP(g)][1];
+
+  /* ---- part 2: scalefactors (pdmp3.c:1382-1435).  A zero-length part has none. ---- */
+  if (P3_GC_P23L(g) != 0) {
+    if (is_short) {
+      uint32_t first = 0;
+      if (P3_GC_MIXED(g)) { for (int sfb = 0; sfb < 8; sfb++) scf[sfb] = (uint8_t)p3_getbits(sw, pos, slen1); first = 3; }
+      for (uint32_t sfb = first; sfb < 12; sfb++)
+        for (int win = 0; win < 3; win++) scf[P3_SCF_S_OFF + 3 * sfb + win] = (uint8_t)p3_getbits(sw, pos, sfb < 6 ? slen1 : slen2);
+    } else {
+      const uint32_t scfsi = gr == 1 ? (fr.scfsi >> (4 * ch)) & 15u : 0u;
+      /* granule 1 may reuse granule 0's scalefactors (scfsi): re-read them from granule 0's part 2 */
+      const p3_gc g0 = gcs[4 * f + ch];
+      const bool g0_long = !(P3_GC_WINSW(g0) && P3_GC_BTYPE(g0) == 2);
+      const uint32_t a1 = T->slen[P3_GC_SFCOMP(g0)][0], a2 = T->slen[P3_GC_SFCOMP(g0)][1];
+      const uint32_t g0pos = fstart + P3_GC_START(g0);
+      const uint32_t g0off[4] = {0, 6 * a1, 11 * a1, 11 * a1 + 5 * a2};
+      const int lo[5] = {0, 6, 11, 16, 21};
+      for (int band = 0; band < 4; band++) {
+        if ((scfsi >> band) & 1) {
+          uint32_t p = g0pos + g0off[band], n = band < 2 ? a1 : a2;
+          for (int sfb = lo[band]; sfb < lo[band + 1]; sfb++)
+            scf[sfb] = (g0_long && P3_GC_P23L(g0)) ? (uint8_t)p3_getbits(sw, p, n) : 0;
+        } else {
+          for (int sfb = lo[band]; sfb < lo[band + 1]; sfb++) scf[sfb] = (uint8_t)p3_getbits(sw, pos, band < 2 ? slen1 : slen2);
+        }
+      }
+    }
+  }
+  if (!live) return;
+
+  /* ---- part 3 (pdmp3.c:2063-2113) ---- */
+  const uint32_t bit_pos_end = part2_start + P3_GC_P23L(g) - 1;
+  uint32_t r1s, r2s;
+  if (is_short) { r1s = 36; r2s = 576; }
+  else { r1s = T->sfb_l[fr.sfreq][P3_GC_REG0(g) + 1]; r2s = T->sfb_l[fr.sfreq][P3_GC_REG0(g) + P3_GC_REG1(g) + 2]; }
+  const uint32_t bv2 = 2 * P3_GC_BIGV(g);
+  uint32_t lim[4] = {0, min(r1s, bv2), min(r2s, bv2), bv2};
+  if (lim[2] < lim[1]) lim[2] = lim[1];
+  #pragma unroll 1
+  for (int r = 0; r < 3; r++) {
+    if (lim[r + 1] <= lim[r]) continue;
+    const uint32_t t = P3_GC_TSEL(g, r);
+    const int book = T->table_book[t];
+    if (book < 0) {                                       /* empty tables: zeros, no bits (pdmp3.c:1599-1602) */
+      for (uint32_t i = lim[r]; i < lim[r + 1]; i += 2) *reinterpret_cast<uint32_t *>(out + i) = 0;
+    } else
+      k1_decode_pairs(sw, lut, pos, T->book_base[book], T->book_pbits[book], T->table_linbits[t], out, lim[r], lim[r + 1]);
+  }
+  /* count1 quads (pdmp3.c:2091-2103) */
+  uint32_t is_pos = bv2;
+  {
+    const bool tabB = P3_GC_C1TAB(g);                    /* reference quirk Q1: table B = leaf 0011, no code bits */
+    const uint32_t qbase = T->book_base[T->table_book[32]], qbits = T->book_pbits[T->table_book[32]];
+    while (is_pos <= 572 && pos <= bit_pos_end) {
+      uint32_t w = p3_peek32(sw, pos), used = 0, leaf = 3;
+      if (!tabB) { uint32_t e = lut[qbase + (w >> (32 - qbits))]; used = (e >> 8) & 31; leaf = e & 15; w <<= used; }
+      int v = (leaf >> 3) & 1, ww = (leaf >> 2) & 1, x = (leaf >> 1) & 1, y = leaf & 1;
+      if (v) { if (w >> 31) v = -1; w <<= 1; used++; }
+      if (ww) { if (w >> 31) ww = -1; w <<= 1; used++; }
+      if (x) { if (w >> 31) x = -1; w <<= 1; used++; }
+      if (y) { if (w >> 31) y = -1; used++; }
+      pos += used;
+      *reinterpret_cast<uint32_t *>(out + is_pos) = (uint32_t)(v & 0xffff) | ((uint32_t)ww << 16);
+      *reinterpret_cast<uint32_t *>(out + is_pos + 2) = (uint32_t)(x & 0xffff) | ((uint32_t)y << 16);
+      is_pos += 4;
+    }
+  }
+  if (pos > bit_pos_end + 1) is_pos = is_pos >= 4 ? is_pos - 4 : 0;      /* pdmp3.c:2105-2106 */
+  count1_out[o] = (int32_t)is_pos;
+  for (uint32_t i = is_pos; i < 576; i++) out[i] = 0;                  /* rzero region */
+}
+
+/* =============================================================================================
+ * K2: requantize + reorder + stereo + antialias, one CTA per granule (both channels: stereo
+ * processing couples them).  Output lines are produced directly in reordered position, so the
+ * reorder of short blocks costs nothing (the reference permutes through a scratch array).
+ * ============================================================================================= */
+__device__ __forceinline__ float k2_requant(const p3_tables *T, int v, uint32_t e2, int q)
+{
+  /* (t1*t2)*t3 with two separately rounded products (pdmp3.c:2132,2150) */
+  float t3 = T->pow43[v < 0 ? -v : v];
+  if (v < 0) t3 = -t3;
+  return __fmul_rn(__fmul_rn(T->t1h[e2], T->t2[q + P3_T2_BIAS]), t3);
+}
+
+extern "C" __global__ void __launch_bounds__(K2_THREADS)
+k_requant(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
+          int64_t f_first, int64_t f_end, const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1,
+          const uint8_t *__restrict__ scf, const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out,
+          float *__restrict__ xr_out)
+{
+  __shared__ float xs[2][576];
+  __shared__ uint8_t sscf[2][P3_SCF_STRIDE];
+  __shared__ int32_t sc1[2];
+
+  const int64_t gidx = blockIdx.x;                        /* granule index within this launch */
+  const int64_t f = f_first + (gidx >> 1);
+  const uint32_t gr = (uint32_t)(gidx & 1);
+  const p3_frame fr = frames[f];
+  const uint32_t nch = fr.nch, sf = fr.sfreq;
+  const int64_t o0 = gidx * 2;                            /* gc index of channel 0 within this launch */
+
+  if (threadIdx.x < 2 * P3_SCF_STRIDE) sscf[threadIdx.x / P3_SCF_STRIDE][threadIdx.x % P3_SCF_STRIDE] = scf[o0 * P3_SCF_STRIDE + threadIdx.x];
+  if (threadIdx.x < 2) {
+    /* effective count1: a zero-length part leaves the reference's count1 stale (Q6, pdmp3.c:2057-2061);
+     * the parser stored how many frames back the last non-empty part of this [gr][ch] slot lies */
+    const uint32_t ch = threadIdx.x;
+    const p3_gc g = gcs[4 * f + 2 * gr + ch];
+    int32_t c = 0;
+    if (ch < nch) {
+      uint32_t back = g.w3;
+      if (back == 0) c = count1[o0 + ch];
+      else if ((int64_t)back <= f - f_first) c = count1[o0 + ch - 4 * (int64_t)back];
+      else c = st_in->count1[gr][ch];                    /* older than this launch: carried state */
+    }
+    sc1[ch] = c;
+    if (f == f_end - 1) st_out->count1[gr][ch] = c;
+  }
+  __syncthreads();
+
+  for (uint32_t ch = 0; ch < nch; ch++) {
+    const p3_gc g = gcs[4 * f + 2 * gr + ch];
+    const bool is_short = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
+    const uint32_t first_short = is_short ? (P3_GC_MIXED(g) ? 36u : 0u) : 576u;
+    const uint32_t mult = P3_GC_SCALE(g) ? 2u : 1u, pre = P3_GC_PREF(g);
+    const int gg = (int)P3_GC_GAIN(g) - 210;
+    const int16_t *isp = is_in + (o0 + ch) * 576;
+    for (uint32_t d = threadIdx.x; d < 576; d += K2_THREADS) {
+      float r;
+      if (d >= first_short) {                             /* short-window line, taken from its bitstream position */
+        const uint32_t s = T->reorder_src[sf][d];
+        const uint32_t sw = T->line_sfbw_s[sf][s], sfb = sw & 15u, win = sw >> 4;
+        const uint32_t sc = sfb < 12 ? sscf[ch][P3_SCF_S_OFF + 3 * sfb + win] : 0u;     /* pseudo band 12: ISO 0 (Q5) */
+        r = k2_requant(T, isp[s], mult * sc, gg - 8 * (int)P3_GC_SBG(g, win));
+      } else {
+        const uint32_t sfb = T->line_sfb_l[sf][d];
+        const uint32_t sc = sfb < 21 ? sscf[ch][sfb] + pre * T->pretab[sfb] : 0u;       /* pseudo band 21: ISO 0 (Q5) */
+        r = k2_requant(T, isp[d], mult * sc, gg);
+      }
+      xs[ch][d] = r;
+    }
+  }
+  __syncthreads();
+
+  /* ---- stereo (pdmp3.c:1916-1971) ---- */
+  if (nch == 2 && fr.mode == 1 && fr.mode_ext != 0) {
+    const p3_gc g0 = gcs[4 * f + 2 * gr];
+    const uint32_t c0 = (uint32_t)sc1[0], c1r = (uint32_t)sc1[1];
+    const uint32_t msn = (fr.mode_ext & 2) ? (c0 > c1r ? c1r : c0) : 0u;              /* min(count1), sic (pdmp3.c:1920) */
+    const bool is_on = fr.mode_ext & 1;
+    const bool sh0 = P3_GC_WINSW(g0) && P3_GC_BTYPE(g0) == 2;
+    const uint32_t first_short0 = sh0 ? (P3_GC_MIXED(g0) ? 36u : 0u) : 576u;
+    for (uint32_t i = threadIdx.x; i < 576; i += K2_THREADS) {
+      float l = xs[0][i], r = xs[1][i];
+      if (i < msn) {
+        /* float sum times a double constant, rounded once to float (pdmp3.c:168,1923-1926) */
+        float a = __fadd_rn(l, r), b = __fsub_rn(l, r);
+        l = __double2float_rn(__dmul_rn((double)a, 0.70710678118654752440));
+        r = __double2float_rn(__dmul_rn((double)b, 0.70710678118654752440));
+      } else if (is_on) {
+        if (i >= first_short0) {
+          /* short-block intensity (pdmp3.c:2190-2220) in REORDERED position: band sfb occupies
+           * [3*s[sfb], 3*s[sfb+1]) and window `win` the win-th third of it (2201-2202) */
+          const uint32_t sw = T->line_sfbw_s[sf][i], sfb = sw & 15u, win = sw >> 4;
+          if (sfb < 12 && 3u * T->sfb_s[sf][sfb] >= c1r && sscf[0][P3_SCF_S_OFF + 3 * sfb + win] != 7) {
+            /* Q4: assignment through an `unsigned` (pdmp3.c:2191,2212-2213) */
+            float x = (float)(unsigned)(long long)l;
+            l = x; r = x;
+          }
+        } else {
+          const uint32_t sfb = T->line_sfb_l[sf][i];
+          const uint32_t lim = sh0 ? 8u : 21u;                                      /* mixed: long sfb 0..7 only (pdmp3.c:1944) */
+          if (sfb < lim && T->sfb_l[sf][sfb] >= c1r) {
+            const uint32_t p = sscf[0][sfb];                                        /* channel-0 scalefactor, sic (pdmp3.c:2163) */
+            if (p != 7) { float x = l; l = __fmul_rn(T->is_l[p & 7], x); r = __fmul_rn(T->is_r[p & 7], x); }
+          }
+        }
+      }
+      xs[0][i] = l; xs[1][i] = r;
+    }
+    __syncthreads();
+  }
+
+  /* ---- antialias (pdmp3.c:1706-1732) ---- */
+  for (uint32_t ch = 0; ch < nch; ch++) {
+    const p3_gc g = gcs[4 * f + 2 * gr + ch];
+    const bool sh = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
+    const uint32_t sblim = sh ? (P3_GC_MIXED(g) ? 2u : 1u) : 32u;
+    for (uint32_t t = threadIdx.x; t < 31 * 8; t += K2_THREADS) {
+      const uint32_t sb = 1 + (t >> 3), i = t & 7;
+      if (sb < sblim) {
+        const uint32_t li = 18 * sb - 1 - i, ui = 18 * sb + i;
+        const float a = xs[ch][li], b = xs[ch][ui], cs = T->cs[i], ca = T->ca[i];
+        xs[ch][li] = __fsub_rn(__fmul_rn(a, cs), __fmul_rn(b, ca));
+        xs[ch][ui] = __fadd_rn(__fmul_rn(b, cs), __fmul_rn(a, ca));
+      }
+    }
+  }
+  __syncthreads();
+  for (uint32_t ch = 0; ch < nch; ch++)
+    for (uint32_t i = threadIdx.x; i < 576; i += K2_THREADS) xr_out[(o0 + ch) * 576 + i] = xs[ch][i];
+}
+
+/* =============================================================================================
+ * K3: IMDCT + window + overlap-add + frequency inversion.  One CTA per granule-channel, one
+ * thread per output sample (time index i = warp, subband sb = lane, so stores are coalesced in
+ * the slot-major layout [i][sb] that the polyphase kernel consumes).
+ * Overlap-add without a serial dependency: y[i] = firsthalf(g)[i] + secondhalf(g-1)[i]; the second
+ * term is recomputed from the previous granule's spectrum (same 36 MACs per sample as forming all
+ * 36 outputs of one granule), or taken from the carried state for the first granule of a launch.
+ * ============================================================================================= */
+__device__ __forceinline__ float k3_imdct_sample(const p3_tables *T, const float *in /*18 lines of one subband*/,
+                                                 uint32_t bt, uint32_t p /*0..35*/)
+{
+  if (bt == 2) {                                          /* three 12-point transforms (pdmp3.c:1673-1686) */
+    float acc = 0.0f;
+    #pragma unroll
+    for (int w = 0; w < 3; w++) {
+      const int q = (int)p - 6 * w - 6;
+      if (q >= 0 && q < 12) {
+        float sum = 0.0f;
+        #pragma unroll
+        for (int m = 0; m < 6; m++) sum = __fadd_rn(sum, __fmul_rn(in[w + 3 * m], T->cos12[m][q]));
+        acc = __fadd_rn(acc, __fmul_rn(sum, T->imdct_win[2][q]));
+      }
+    }
+    return acc;
+  }
+  float sum = 0.0f;                                       /* 36-point (pdmp3.c:1689-1698) */
+  #pragma unroll
+  for (int m = 0; m < 18; m++) sum = __fadd_rn(sum, __fmul_rn(in[m], T->cos36[m][p]));
+  return __fmul_rn(sum, T->imdct_win[bt][p]);
+}
+
+extern "C" __global__ void __launch_bounds__(K3_THREADS)
+k_imdct(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
+        int64_t f_first, int64_t f_end, const float *__restrict__ xr, const p3_state *__restrict__ st_in,
+        p3_state *__restrict__ st_out, float *__restrict__ y_out)
+{
+  __shared__ float cur[576], prv[576];
+  const int64_t o = blockIdx.x;                           /* granule-channel within the launch */
+  const int64_t gidx = o >> 1;                            /* granule within the launch */
+  const uint32_t ch = (uint32_t)(o & 1);
+  const int64_t f = f_first + (gidx >> 1);
+  const uint32_t gr = (uint32_t)(gidx & 1);
+  if (ch >= frames[f].nch) return;
+  const p3_gc g = gcs[4 * f + 2 * gr + ch];
+  const bool have_prev = gidx > 0;
+  p3_gc gp = g;
+  if (have_prev) { const int64_t gp_idx = gidx - 1; gp = gcs[4 * (f_first + (gp_idx >> 1)) + 2 * (gp_idx & 1) + ch]; }
+
+  for (uint32_t i = threadIdx.x; i < 576; i += K3_THREADS) {
+    cur[i] = xr[o * 576 + i];
+    prv[i] = have_prev ? xr[(o - 2) * 576 + i] : st_in->store[ch][i];
+  }
+  __syncthreads();
+
+  const uint32_t sb = threadIdx.x & 31, i = threadIdx.x >> 5;           /* i in 0..17 */
+  const uint32_t bt = (P3_GC_WINSW(g) && P3_GC_MIXED(g) && sb < 2) ? 0u : P3_GC_BTYPE(g);      /* pdmp3.c:1769-1771 */
+  const float a = k3_imdct_sample(T, cur + 18 * sb, bt, i);
+  float b;
+  if (have_prev) {
+    const uint32_t btp = (P3_GC_WINSW(gp) && P3_GC_MIXED(gp) && sb < 2) ? 0u : P3_GC_BTYPE(gp);
+    b = k3_imdct_sample(T, prv + 18 * sb, btp, i + 18);
+  } else b = prv[18 * sb + i];
+  float yv = __fadd_rn(a, b);                                            /* rawout[i] + store[i] (pdmp3.c:1775) */
+  if ((sb & 1) && (i & 1)) yv = -yv;                                     /* frequency inversion (pdmp3.c:1741-1743) */
+  y_out[o * 576 + i * 32 + sb] = yv;
+
+  /* last granule of the launch: leave its second half behind as the next launch's overlap */
+  if (gidx == 2 * (f_end - f_first) - 1)
+    st_out->store[ch][18 * sb + i] = k3_imdct_sample(T, cur + 18 * sb, bt, i + 18);
+}
+
+/* =============================================================================================
+ * K4: polyphase synthesis + PCM.  One CTA per K4_GRAN granules (both channels).
+ * Phase A matrixes every slot of the chunk (plus nothing else: the 15 history slots are matrixed
+ * from the previous granule's samples, or come from the carried state at the start of a launch):
+ *   V(t)[i] = sum_j N[i][j] * S(t)[j]                               (pdmp3.c:2010-2014)
+ * Phase B windows and sums without ever shifting a FIFO:
+ *   pcm(t)[j] = sum_{k<16} D[32k+j] * V(t-k)[(k odd ? 32 : 0) + j]  (pdmp3.c:2015-2026)
+ * ============================================================================================= */
+extern "C" __global__ void __launch_bounds__(K4_THREADS)
+k_polyphase(const p3_frame *__restrict__ frames, const p3_tables *__restrict__ T, int64_t f_first, int64_t f_end,
+            const float *__restrict__ y, const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out,
+            int16_t *__restrict__ pcm)
+{
+  extern __shared__ float smf[];
+  float *Nt = smf;                                        /* [32][64] transposed matrixing matrix: Nt[j][i] */
+  float *D = Nt + 2048;                                   /* [512] */
+  float *S = D + 512;                                     /* [2][15+K4_SLOTS][32] subband samples per slot */
+  float *V = S + 2 * (15 + K4_SLOTS) * 32;                /* [2][15+K4_SLOTS][64] */
+  const int NS = 15 + K4_SLOTS;
+
+  const int64_t ngran = 2 * (f_end - f_first);
+  const int64_t g0 = (int64_t)blockIdx.x * K4_GRAN;
+  const int64_t g1 = min(g0 + (int64_t)K4_GRAN, ngran);
+  const int nslots = (int)(g1 - g0) * 18;
+  const uint32_t nch = frames[f_first].nch;
+
+  for (int i = threadIdx.x; i < 2048; i += K4_THREADS) Nt[(i & 31) * 64 + (i >> 5)] = T->synth_n[i >> 5][i & 31];
+  for (int i = threadIdx.x; i < 512; i += K4_THREADS) D[i] = T->synth_d[i];
+  /* subband samples: chunk slots at rows 15.., history rows 0..14 from the previous granule */
+  for (uint32_t ch = 0; ch < nch; ch++) {
+    for (int e = threadIdx.x; e < (nslots + 15) * 32; e += K4_THREADS) {
+      const int row = e >> 5, j = e & 31;                 /* row 0..14 history (slot -15..-1), 15.. chunk */
+      const int64_t t = g0 * 18 + row - 15;               /* slot index within the launch */
+      float v = 0.0f;
+      if (t >= 0) { const int64_t gg = t / 18; const int ss = (int)(t % 18); v = y[(gg * 2 + ch) * 576 + ss * 32 + j]; }
+      S[(ch * NS + row) * 32 + j] = v;
+    }
+  }
+  __syncthreads();
+  /* phase A */
+  for (uint32_t ch = 0; ch < nch; ch++) {
+    for (int e = threadIdx.x; e < (nslots + 15) * 64; e += K4_THREADS) {
+      const int row = e >> 6, i = e & 63;
+      const int64_t t = g0 * 18 + row - 15;
+      float sum;
+      if (t >= 0) {
+        const float *s = S + (ch * NS + row) * 32;
+        sum = 0.0f;
+        #pragma unroll
+        for (int j = 0; j < 32; j++) sum = __fadd_rn(sum, __fmul_rn(Nt[j * 64 + i], s[j]));
+      } else sum = st_in->vhist[ch][(int)(-t) - 1][i];    /* before the launch: carried history */
+      V[(ch * NS + row) * 64 + i] = sum;
+    }
+  }
+  __syncthreads();
+  /* phase B */
+  for (int e = threadIdx.x; e < nslots * 32; e += K4_THREADS) {
+    const int r = e >> 5, j = e & 31;                     /* chunk slot r, output sample j */
+    const int64_t gg = g0 + r / 18;                       /* granule within the launch */
+    const p3_frame &fr = frames[f_first + (gg >> 1)];
+    int32_t out[2] = {0, 0};
+    for (uint32_t ch = 0; ch < nch; ch++) {
+      const float *v = V + (ch * NS + r + 15) * 64;
+      float sum = 0.0f;
+      #pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const float u = __fmul_rn(v[-64 * k + ((k & 1) ? 32 : 0) + j], D[32 * k + j]);
+        sum = __fadd_rn(sum, u);
+      }
+      const double d = __dmul_rn((double)sum, 32767.0);   /* double multiply, truncation (pdmp3.c:2028) */
+      int32_t s = (d > -2147483649.0 && d < 2147483648.0) ? __double2int_rz(d) : (int32_t)0x80000000;   /* x86 cvttsd2si */
+      s = s > 32767 ? 32767 : (s < -32767 ? -32767 : s);  /* clamp is +-32767 (pdmp3.c:2029-2030) */
+      out[ch] = s;
+    }
+    if (fr.flags & P3_FRAME_DECODE) {
+      const int64_t sample = (int64_t)fr.pcm_index * 1152 + (gg & 1) * 576 + (r % 18) * 32 + j;
+      if (nch == 2) reinterpret_cast<uint32_t *>(pcm)[sample] = (uint32_t)(out[0] & 0xffff) | ((uint32_t)out[1] << 16);
+      else pcm[sample] = (int16_t)out[0];
+    }
+  }
+  /* the last chunk leaves the matrixed vectors of its last 15 slots as the next launch's history */
+  if (g1 == ngran) {
+    for (uint32_t ch = 0; ch < nch; ch++)
+      for (int e = threadIdx.x; e < 15 * 64; e += K4_THREADS) {
+        const int age = e >> 6, i = e & 63;               /* age+1 slots back from the end */
+        st_out->vhist[ch][age][i] = V[(ch * NS + 15 + nslots - 1 - age) * 64 + i];
+      }
+  }
+}

@@ -1,0 +1,30 @@
+/* p3_kernels.h -- launch geometry shared by p3_kernels.cu and p3_cabi.cu */
+#pragma once
+#include <stdint.h>
+#include "p3_tables.h"
+#include "../../include/pdmp3_b200.h"
+
+#define K1_FPB      32                 /* frames per CTA in the Huffman kernel */
+#define K1_THREADS  (K1_FPB * 4)       /* one thread per granule-channel       */
+#define K2_THREADS  192                /* requantize kernel: one CTA per granule, 3 lines per thread */
+#define K3_THREADS  576                /* IMDCT kernel: one CTA per granule-channel, one thread per output sample */
+#define K4_GRAN     4                  /* polyphase kernel: granules per CTA   */
+#define K4_SLOTS    (K4_GRAN * 18)
+#define K4_THREADS  256
+
+struct p3_state;
+
+#ifdef __CUDACC__
+extern "C" {
+__global__ void k_huffman(const uint8_t *raw, const p3_frame *frames, const p3_gc *gcs, const p3_tables *T,
+                          const uint8_t *tail, int64_t f_first, int64_t f_end, uint32_t smem_words,
+                          int16_t *is_out, int32_t *count1_out, uint8_t *scf_out);
+__global__ void k_requant(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end,
+                          const int16_t *is_in, const int32_t *count1, const uint8_t *scf,
+                          const p3_state *st_in, p3_state *st_out, float *xr_out);
+__global__ void k_imdct(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end,
+                        const float *xr, const p3_state *st_in, p3_state *st_out, float *y_out);
+__global__ void k_polyphase(const p3_frame *frames, const p3_tables *T, int64_t f_first, int64_t f_end,
+                            const float *y, const p3_state *st_in, p3_state *st_out, int16_t *pcm);
+}
+#endif

@@ -79,13 +79,14 @@ static void parse_side(const uint8_t *si, p3_frame *fr, p3_gc *gc)
   if (bad) fr->flags |= P3_FRAME_BAD;
 }
 
-typedef struct { const uint8_t *data; p3_frame *fr; p3_gc *gc; int64_t lo, hi; } job_t;
+typedef struct { const uint8_t *data; p3_frame *fr; p3_gc *gc; int64_t lo, hi; int any_empty; } job_t;
 static void *worker(void *arg)
 {
   job_t *j = (job_t *)arg;
   for (int64_t f = j->lo; f < j->hi; f++) {
     p3_frame *fr = &j->fr[f];
     parse_side(j->data + fr->main_off - (fr->nch == 1 ? 17 : 32), fr, &j->gc[4 * f]);
+    for (unsigned k = 0; k < 4; k++) if ((k & 1) < fr->nch && P3_GC_P23L(j->gc[4 * f + k]) == 0) j->any_empty = 1;
   }
   return NULL;
 }
@@ -116,6 +117,7 @@ int p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_parse_s
     unsigned prot = h[1] & 1, br = h[2] >> 4, sf = (h[2] >> 2) & 3, pad = (h[2] >> 1) & 1;
     unsigned mode = h[3] >> 6, mext = (h[3] >> 4) & 3;
     unsigned nch = mode == 3 ? 1 : 2, silen = nch == 1 ? 17 : 32;
+    if (nf > 0 && (nch != fr[0].nch || sf != fr[0].sfreq)) { stop = 3; pos = p; break; }   /* format change: next batch */
     unsigned fsize = 144u * k_bitrate[br] * 1000u / k_sfreq[sf] + pad;            /* pdmp3.c:1135-1138 */
     unsigned hdr = 4 + (prot ? 0 : 2);
     if (fsize < hdr + silen || p + fsize > n) break;                              /* incomplete frame */
@@ -144,15 +146,27 @@ int p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_parse_s
   /* ---- phase 2: side info, in parallel ---- */
   int nt = o->nthreads;
   if (nt <= 0) { long c = sysconf(_SC_NPROCESSORS_ONLN); nt = c > 16 ? 16 : (int)c; }
-  if (nf < 4096 || nt < 2) { job_t j = {data, fr, out->gcs, 0, nf}; worker(&j); }
+  int any_empty = 0;
+  if (nf < 4096 || nt < 2) { job_t j = {data, fr, out->gcs, 0, nf, 0}; worker(&j); any_empty = j.any_empty; }
   else {
     pthread_t th[64]; job_t jb[64];
     if (nt > 64) nt = 64;
     for (int t = 0; t < nt; t++) {
-      jb[t] = (job_t){data, fr, out->gcs, nf * t / nt, nf * (t + 1) / nt};
+      jb[t] = (job_t){data, fr, out->gcs, nf * t / nt, nf * (t + 1) / nt, 0};
       if (pthread_create(&th[t], NULL, worker, &jb[t])) { worker(&jb[t]); th[t] = 0; }
     }
-    for (int t = 0; t < nt; t++) if (th[t]) pthread_join(th[t], NULL);
+    for (int t = 0; t < nt; t++) { if (th[t]) pthread_join(th[t], NULL); any_empty |= jb[t].any_empty; }
+  }
+  /* Q6 (pdmp3.c:2057-2061): a zero-length part leaves count1 of its [gr][ch] slot stale.  Record how
+   * many frames back the slot was last written so the device can fetch that count1 (w3 = 0: own). */
+  if (any_empty) {
+    int64_t last[4] = {-1, -1, -1, -1};
+    for (int64_t f = 0; f < nf; f++) for (unsigned k = 0; k < 4; k++) {
+      if ((k & 1) >= fr[f].nch) continue;
+      p3_gc *g = &out->gcs[4 * f + k];
+      if (P3_GC_P23L(*g) != 0 || (fr[f].flags & (P3_FRAME_NODATA | P3_FRAME_BAD))) { last[k] = f; g->w3 = 0; }
+      else g->w3 = last[k] >= 0 ? (uint32_t)(f - last[k]) : 0x7fffffffu;
+    }
   }
   return P3_OK;
 }

@@ -1,0 +1,48 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the oracle restatement, the
+compiled reference (oracle/_ref, when it travelled with the repo) and the committed fixtures.
+Bit-exact for integer stages; P3_MODE_EXACT is also bit-exact in PCM; P3_MODE_FAST within 1 LSB."""
+import numpy as np, pytest
+import p3harness as H
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = dict(
+    cfg1=dict(H.CONFIGS["cfg1_128k_stereo_long"]),
+    cfg3=dict(H.CONFIGS["cfg3_320k_js_ms"]),
+    cfg4=dict(H.CONFIGS["cfg4_vbr_mixed"]),
+    mono=dict(mode=3, blocks=1, bitrate_index=7),
+    k48=dict(sfreq=1, mode=1, mode_ext=-1, blocks=1, bitrate_index=11),
+    k32=dict(sfreq=2, mode=1, mode_ext=-1, blocks=1, bitrate_index=12),
+    crc=dict(crc=1, mode=1, mode_ext=3, blocks=1),
+    c1b=dict(count1_b_pm=500, mode=1, mode_ext=-1, blocks=1),
+    garbage=dict(garbage_pm=200, blocks=1),
+    nores=dict(reservoir=0, blocks=1, bitrate_index=5),
+    dual=dict(mode=2, blocks=1, overrun_pm=200),
+    loud=dict(gain=200, blocks=1),
+    lowrate=dict(bitrate_index=1, blocks=1, mode=1, mode_ext=-1),
+)
+
+
+def feq(a, b):
+    """float arrays equal bit for bit, +0 == -0"""
+    return ((a.view(np.uint32) == b.view(np.uint32)) | ((a == 0) & (b == 0)))
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_stage_taps_exact_vs_oracle(gpu_ctx, name):
+    s, _ = H.synth(150, seed=21, **VARIANTS[name])
+    o = H.oracle_decode(s, lookahead=1152)
+    gpu_ctx.reset()
+    pcm, t = gpu_ctx.decode(s, lookahead=1152, taps=True)
+    n = o["n_frames"]
+    assert pcm.shape[0] == n
+    nch = pcm.shape[2]
+    assert np.array_equal(t["is_huff"][:, :, :nch], o["is_huff"][:, :, :nch]), "Huffman output"
+    assert np.array_equal(t["count1"][:, :, :nch], o["count1"][:, :, :nch]), "count1"
+    assert feq(t["xr"][:, :, :nch], o["xr_ali"][:, :, :nch]).all(), "requantize/reorder/stereo/antialias"
+    assert feq(t["y"][:, :, :nch], o["y_hyb"][:, :, :nch]).all(), "hybrid synthesis"
+    assert np.array_equal(pcm, o["pcm"]), "PCM"
+    if H.have_ref():
+        r = H.ref_decode(s, taps=False)
+        ref = r["pcm"] if nch == 2 else r["pcm"][:, :, :1]
+        assert np.array_equal(pcm, ref), "PCM vs compiled reference"
