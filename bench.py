@@ -1,0 +1,252 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the MP3 Layer III granule decode path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl reference]
+
+A step = one pass of the hot path (Huffman -> requantize/reorder/stereo/antialias -> IMDCT ->
+polyphase -> int16 PCM) over one batch of synthetic frames per GPU.  Workload (BASELINE.json
+configs[2], and per GPU of configs[4]): 1 000 000 frames of 44.1 kHz 320 kbps CBR joint stereo (MS),
+bit reservoir in use; the stream is a 15 625-frame seeded block tiled 64x (distinct addresses, so
+nothing is reused from L2; input 1.04 GB + output 4.6 GB per step >> the 126 MB L2).
+Metric: decoded PCM sample-frames per second (1152 per MP3 frame), whole job over all N GPUs.
+
+  value     kernels only, inputs resident in HBM, CUDA events, max over ranks
+  e2e       the same work through the drop-in pdmp3_* C API with HOST buffers: pdmp3_feed() of the
+            byte stream + pdmp3_read() into a host PCM buffer (parse, H2D, kernels, D2H all inside)
+  roofline  dominant kernel: algorithmic bytes (frame bytes + 4608 PCM bytes per frame)
+            per launch / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref) timed on this box's host cores
+--impl reference: times only the reference CPU decoder (all host cores, forked processes).
+"""
+import argparse, ctypes as C, json, os, subprocess, sys, tempfile, threading, time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+
+BLOCK = 15625
+CFG = dict(bitrate_index=14, mode=1, mode_ext=2, blocks=0)       # configs[2]: 320 kbps CBR joint stereo (MS), long blocks
+WORKLOAD = "1M-frame 44.1kHz 320kbps CBR joint-stereo(MS) synthetic stream, full on-device pipeline (BASELINE configs[2]; per GPU of configs[4])"
+
+
+def make_stream(n_frames, seed=1):
+    import p3harness as H
+    nblk = (n_frames + BLOCK - 1) // BLOCK
+    blk, _ = H.synth(min(BLOCK, n_frames), seed=seed, **CFG)
+    if nblk == 1:
+        return blk
+    return np.tile(blk, nblk)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []; self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._rd, daemon=True); self.t.start()
+        except Exception:
+            self.p = None
+
+    def _rd(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15); self.p.terminate()
+        try: self.p.wait(timeout=2)
+        except Exception: pass
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def ref_cpu_throughput(stream_block_frames, nprocs, frames_per_proc):
+    """Time oracle/_ref/ref_bench (the unmodified reference) on `nprocs` forked processes."""
+    import p3harness as H
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
+    if not os.path.exists(exe):
+        return None
+    s, _ = H.synth(frames_per_proc + 2, seed=3, **CFG)
+    fr, gc, info = H.parse(s, lookahead=0)
+    d = tempfile.mkdtemp(prefix="p3bench", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    sp, op = os.path.join(d, "s.mp3"), os.path.join(d, "off.bin")
+    big = np.tile(s, nprocs); big.tofile(sp)
+    np.arange(nprocs + 1, dtype=np.uint64).__mul__(len(s)).astype("<u8").tofile(op)
+    best = None
+    for _ in range(2):
+        out = subprocess.run([exe, sp, str(nprocs), op], stdout=subprocess.PIPE, text=True).stdout.split()
+        frames, secs = int(out[0]), float(out[1])
+        if best is None or secs < best[1]:
+            best = (frames, secs)
+    for f in (sp, op):
+        os.unlink(f)
+    os.rmdir(d)
+    return best[0] * 1152 / best[1], best[0], best[1]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=1000000, help="frames per GPU per step")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    ncores = os.cpu_count() or 1
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        per = 4096
+        vals = []
+        for i in range(max(a.warmup, 0) + max(a.steps, 1)):
+            r = ref_cpu_throughput(BLOCK, ncores, per)
+            if r is None:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_bench not built (reference sources absent at build time)"})); return 0
+            if i >= a.warmup:
+                vals.append(r)
+        v = float(np.median([x[0] for x in vals])); fr = vals[0][1]
+        sample = "%d forked processes x %d frames of the same 320 kbps joint-stereo stream, pdmp3_read() 16 KiB / pdmp3_feed() 4096 B loop (pdmp3.c:2564-2584), -O2 IEEE build" % (ncores, per)
+        print(json.dumps({"impl": "reference", "metric": "decoded_pcm_sample_frames_per_sec", "value": v, "unit": "sample-frames/s",
+                          "x_realtime_44k1": v / 44100.0, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": 1e3 * fr * 1152 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "frames_per_step": fr},
+                          "cpu_baseline": {"value": v, "unit": "sample-frames/s", "cores": ncores, "kind": "reference", "sample": sample},
+                          "e2e": {"value": v, "unit": "sample-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import pdmp3_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the decoder has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nf = a.frames
+    stream = make_stream(nf)
+    # rank r > 0 decodes a shard of one long stream: 2 warm-up frames in front (reservoir bytes + filter state)
+    warm = 2 if rank > 0 else 0
+    if warm:
+        blk_tail = make_stream(min(BLOCK, nf))
+        fr_b, _, _ = __import__("p3harness").parse(blk_tail, lookahead=0)
+        cut = int(fr_b["main_off"][-2]) - 36
+        stream = np.concatenate([blk_tail[cut:], stream])
+    ctx = pdmp3_b200.Context(local, pdmp3_b200.MODE_FAST if a.mode == "fast" else pdmp3_b200.MODE_EXACT)
+    t0 = time.time(); parsed = pdmp3_b200.parse_stream(stream, lookahead=0, warmup=warm); t_parse = time.time() - t0
+    n_frames = parsed.n_pcm_frames
+    ctx.upload(parsed); ctx.sync()
+    def barrier():
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(a.warmup, 3)):
+        ctx.run()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    ms_tot, ms_stage = ctx.time(a.steps)                    # CUDA events on the context stream, K steps
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count()
+    t = torch.tensor([ms_tot], dtype=torch.float64, device="cuda")
+    if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * n_frames * 1152 / (ms * 1e-3)
+
+    # ---- gather of PCM to rank 0 (config 5), timed separately ----
+    gather = None
+    if world > 1:
+        nbytes = n_frames * 4608
+        ptr = pdmp3_b200.lib().p3_batch_pcm_device(ctx.h, None)
+        class _W: pass
+        w = _W(); w.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        mine = torch.as_tensor(w, device="cuda")
+        dst = [torch.empty(nbytes, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
+        barrier(); dist.gather(mine, dst, dst=0); barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); dist.gather(mine, dst, dst=0); e1.record(); barrier()
+        tg = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda"); dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather = {"ms": float(tg.item()), "bytes_to_rank0": nbytes * (world - 1),
+                  "value_with_gather": world * n_frames * 1152 / ((ms + float(tg.item())) * 1e-3)}
+
+    # ---- end to end through the drop-in C API, host buffers ----
+    e2e = None
+    if not a.no_e2e:
+        L = pdmp3_b200.lib()
+        raw_bytes = len(stream)
+        hin = torch.empty(raw_bytes, dtype=torch.uint8).pin_memory(); hin.numpy()[:] = stream
+        out_bytes = (parsed.n_frames) * 4608
+        hout = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+        dec = pdmp3_b200.Decoder("b200:ring=%d,device=%d" % (raw_bytes + 4096, local))
+        times = []
+        for it in range(2 + a.steps):
+            dec.open_feed()
+            barrier(); t0 = time.perf_counter()
+            rc = L.pdmp3_feed(dec.h, hin.data_ptr(), raw_bytes); assert rc == 0, rc
+            done = C.c_size_t(0)
+            rc = L.pdmp3_read(dec.h, hout.data_ptr(), out_bytes, C.byref(done))
+            torch.cuda.synchronize(); dt = time.perf_counter() - t0
+            if it >= 2: times.append((dt, done.value))
+        dec.close()
+        dt = float(np.median([x[0] for x in times])); done_b = times[0][1]
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1: dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * (done_b / 4) / float(tt.item()), "unit": "sample-frames/s", "h2d_bytes_per_step": int(raw_bytes + parsed.n_frames * 96),
+               "d2h_bytes_per_step": int(done_b), "ms_per_step": 1e3 * float(tt.item()),
+               "api": "pdmp3_new(\"b200:ring=..\") + pdmp3_feed() + pdmp3_read() with pinned host buffers; host parse, H2D, kernels, D2H inside the timed region"}
+
+    if rank != 0:
+        if world > 1: dist.destroy_process_group()
+        return 0
+    peak, peak_src = peaks()
+    frame_bytes = len(stream) / parsed.n_frames
+    alg_bytes = (frame_bytes + 4608.0) * n_frames
+    names = ["k_huffman", "k_requant", "k_imdct", "k_polyphase"]
+    dom = int(np.argmax(ms_stage)) if sum(ms_stage) > 0 else 0
+    dom_ms = ms_stage[dom] if sum(ms_stage) > 0 else ms
+    roof = {"bound": "hbm", "kernel": names[dom], "achieved": alg_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": alg_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_frame": frame_bytes + 4608.0,
+            "whole_path": {"achieved": alg_bytes / (ms * 1e-3) / 1e9, "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak},
+            "stage_ms": dict(zip(names, ms_stage))}
+    cpu = None
+    if not a.no_cpu and world == 1:
+        r = ref_cpu_throughput(BLOCK, ncores, 4096)
+        if r:
+            cpu = {"value": r[0], "unit": "sample-frames/s", "cores": ncores, "kind": "reference",
+                   "sample": "%d forked processes x 4096 frames of the same stream type, reference API loop, %.2f s wall" % (ncores, r[2])}
+    print(json.dumps({"metric": "decoded_pcm_sample_frames_per_sec", "value": value, "unit": "sample-frames/s",
+                      "x_realtime_44k1": value / 44100.0, "int16_samples_per_sec": 2 * value, "frames_per_sec": value / 1152,
+                      "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "frames_per_gpu": int(n_frames), "mode": a.mode,
+                                 "l2": "inputs+outputs (5.6 GB per step) exceed the 126 MB L2; no flush needed",
+                                 "parallelism": "frame-sharded x%d, no data-path collective" % world, "host_parse_s": t_parse},
+                      "clocks": clocks, "e2e": e2e, "gpu_launches": launches * a.steps, "roofline": roof, "cpu_baseline": cpu,
+                      "gather_to_rank0": gather}))
+    if world > 1: dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

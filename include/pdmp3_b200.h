@@ -95,6 +95,11 @@ typedef struct {
 
 int  p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *opts, p3_parse_state *state, p3_parsed *out);
 void p3_parsed_free(p3_parsed *p);
+int  p3_find_header(const uint8_t *data, uint64_t n, int *nch, int *sfreq);   /* 1 found, 0 need more, -1 none within 1152 B */
+
+/* page-locked host memory for stream / PCM buffers (NULL if no device is usable) */
+void *p3_host_alloc(size_t bytes);
+void  p3_host_free(void *p);
 
 /* ---- device context ------------------------------------------------------------------------ */
 typedef struct p3_ctx p3_ctx;

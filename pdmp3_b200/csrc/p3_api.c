@@ -1,3 +1,238 @@
-/* p3_api.c -- placeholder translation unit; the streaming API (pdmp3_new ... pdmp3_getformat)
- * is implemented in the next milestone. */
+/* p3_api.c -- the reference's streaming API (libmpg123 subset) on top of the batch decoder.
+ * Plain C.  Same prototypes, return codes and observable behaviour as pdmp3.c:2351-2535; what is
+ * different is WHEN work happens: pdmp3_read() parses as many buffered frames as the caller's
+ * buffer can hold and sends them through the GPU as one batch instead of decoding frame by frame.
+ *
+ *   reference                          here
+ *   pdmp3_new        2351-2353         malloc + option string (ignored by the reference)
+ *   pdmp3_open_feed  2369-2384         reset cursors and the device-side filter state
+ *   pdmp3_feed       2391-2423         copy into the input buffer; PDMP3_NO_SPACE if it does not fit
+ *   pdmp3_read       2431-2481         flush pending PCM, then batch-decode; 1152-byte look-ahead rule (2445)
+ *   pdmp3_decode     2491-2520         feed(min(free,insize)) + read, or header peek
+ *   pdmp3_getformat  2526-2535         rate / channels / encoding of the last header
+ *   pdmp3            2540-2589         CLI loop, raw writer only
+ *
+ * Documented differences (supersets, SURVEY 8b "hazards"): the input buffer is linear with
+ * compaction, so feeding exactly `ring` bytes into an empty buffer works; a frame is only read when
+ * it is completely buffered; a frame whose main_data_begin underflows the reservoir is emitted as
+ * silence instead of being re-read (Q8).
+ */
 #include "../../include/pdmp3.h"
+#include "../../include/pdmp3_b200.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+#define P3_DEFAULT_RING 16384u              /* INBUF_SIZE (pdmp3.c:123) */
+
+struct pdmp3_handle {
+  unsigned char *in; size_t cap, istart, iend;      /* buffered bytes are in[istart,iend) */
+  size_t processed;
+  int16_t *pcm;                                     /* one frame: the partially delivered frame */
+  size_t pend_pos, pend_end;                        /* undelivered PCM bytes of it: [pend_pos,pend_end) */
+  int in_pinned;
+  p3_ctx *ctx; int device; int ctx_failed;
+  p3_parse_state ps;
+  int new_header;                                   /* 0 none yet, 1 seen, -1 reported (pdmp3.c:1318,2470,2531) */
+  int nch, sfreq;
+  int opened;
+};
+
+static const long k_rates[3] = {44100, 48000, 32000};
+
+pdmp3_handle *pdmp3_new(const char *decoder, int *error)
+{
+  pdmp3_handle *id = (pdmp3_handle *)calloc(1, sizeof *id);
+  if (!id) { if (error) *error = PDMP3_ERR; return NULL; }
+  id->cap = P3_DEFAULT_RING; id->device = 0;
+  if (decoder) {                                    /* "b200:ring=<bytes>,device=<n>" */
+    const char *p;
+    if ((p = strstr(decoder, "ring="))) { unsigned long long v = strtoull(p + 5, NULL, 10); if (v >= 4096) id->cap = (size_t)v; }
+    if ((p = strstr(decoder, "device="))) id->device = atoi(p + 7);
+  }
+  if (id->cap > (1u << 20)) { id->in = (unsigned char *)p3_host_alloc(id->cap); id->in_pinned = id->in != NULL; }   /* page-locked: full-speed H2D */
+  if (!id->in) id->in = (unsigned char *)malloc(id->cap);
+  if (!id->in) { free(id); if (error) *error = PDMP3_ERR; return NULL; }
+  id->ps.nch = id->ps.sfreq = -1; id->nch = 2; id->sfreq = 0;
+  if (error) *error = PDMP3_OK;
+  return id;
+}
+
+void pdmp3_delete(pdmp3_handle *id)
+{
+  if (!id) return;
+  if (id->ctx) p3_ctx_destroy(id->ctx);
+  if (id->in_pinned) p3_host_free(id->in); else free(id->in);
+  free(id->pcm); free(id);
+}
+
+int pdmp3_open_feed(pdmp3_handle *id)
+{
+  if (!id) return PDMP3_ERR;
+  id->istart = id->iend = 0; id->processed = 0; id->new_header = 0;
+  id->pend_pos = id->pend_end = 0;
+  memset(&id->ps, 0, sizeof id->ps); id->ps.nch = id->ps.sfreq = -1;
+  if (id->ctx) p3_ctx_reset(id->ctx);               /* hsynth_init / synth_init / g_main_data_top (pdmp3.c:2377-2379) */
+  id->opened = 1;
+  return PDMP3_OK;
+}
+
+static size_t in_filled(const pdmp3_handle *id) { return id->iend - id->istart; }
+static size_t in_free(const pdmp3_handle *id) { return id->cap - in_filled(id); }
+
+int pdmp3_feed(pdmp3_handle *id, const unsigned char *in, size_t size)
+{
+  if (!(id && in && size)) return PDMP3_ERR;
+  if (size > in_free(id)) return PDMP3_NO_SPACE;
+  if (id->iend + size > id->cap) {                  /* compact */
+    memmove(id->in, id->in + id->istart, in_filled(id));
+    id->iend -= id->istart; id->istart = 0;
+  }
+  memcpy(id->in + id->iend, in, size);
+  id->iend += size;
+  return PDMP3_OK;
+}
+
+static int ensure_ctx(pdmp3_handle *id)
+{
+  if (id->ctx) return PDMP3_OK;
+  if (id->ctx_failed) return PDMP3_ERR;
+  if (p3_ctx_create(id->device, &id->ctx) != P3_OK) {
+    fprintf(stderr, "pdmp3_b200: %s\n", p3_last_error());
+    id->ctx_failed = 1; id->ctx = NULL;
+    return PDMP3_ERR;
+  }
+  return PDMP3_OK;
+}
+
+int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_t *done)
+{
+  if (!(id && outmemory && outsize && done)) return PDMP3_ERR;
+  int res = PDMP3_ERR;
+  *done = 0;
+  if (id->pend_pos < id->pend_end) {                /* rest of a previously decoded frame (pdmp3.c:2437-2442) */
+    size_t n = id->pend_end - id->pend_pos; if (n > outsize) n = outsize;
+    memcpy(outmemory, (unsigned char *)id->pcm + id->pend_pos, n);
+    id->pend_pos += n; outmemory += n; outsize -= n; *done += n;
+    res = PDMP3_OK;
+  }
+  while (outsize) {
+    if (in_filled(id) < 2 * 576) { res = PDMP3_NEED_MORE; break; }          /* pdmp3.c:2445,2466 */
+    size_t fbytes = 1152 * sizeof(int16_t) * (size_t)(id->nch == 1 ? 1 : 2);
+    /* whole frames go straight into the caller's buffer; a trailing partial frame is decoded into
+     * the handle and handed out piecewise (the reference's ostart cursor, pdmp3.c:2317-2344) */
+    int direct = outsize >= fbytes;
+    p3_parse_opts po = {direct ? (int64_t)(outsize / fbytes) : 1, 2 * 576, 0, 0};
+    p3_parse_state ps = id->ps;
+    p3_parsed pb;
+    if (p3_parse(id->in + id->istart, in_filled(id), &po, &ps, &pb) != P3_OK) { res = PDMP3_ERR; break; }
+    if (pb.n_frames == 0) {
+      int stop = pb.stop;
+      p3_parsed_free(&pb);
+      res = stop == 2 ? PDMP3_ERR : PDMP3_NEED_MORE;                         /* no header within a frame's length: pdmp3.c:1337 */
+      break;
+    }
+    if (ensure_ctx(id) != PDMP3_OK) { p3_parsed_free(&pb); res = PDMP3_ERR; break; }
+    int nch = pb.frames[0].nch;
+    size_t fb2 = 1152 * sizeof(int16_t) * (size_t)nch;
+    if (fb2 != fbytes) {                                                      /* channel count changed: re-plan with the right frame size */
+      id->nch = nch; p3_parsed_free(&pb); continue;
+    }
+    int16_t *target = (int16_t *)outmemory;
+    if (!direct) {
+      if (!id->pcm) { id->pcm = (int16_t *)malloc(1152 * 2 * sizeof(int16_t)); if (!id->pcm) { p3_parsed_free(&pb); res = PDMP3_ERR; break; } }
+      target = id->pcm;
+    }
+    for (int64_t f = 0; f < pb.n_frames; f++) pb.frames[f].pcm_index = (uint32_t)f;   /* slots restart at 0 for every batch */
+    if (p3_decode_batch(id->ctx, id->in + id->istart, in_filled(id), &pb, target, NULL) != P3_OK) {
+      fprintf(stderr, "pdmp3_b200: %s\n", p3_last_error());
+      p3_parsed_free(&pb); res = PDMP3_ERR; break;
+    }
+    id->ps = ps; id->ps.pcm_index = 0;
+    id->sfreq = pb.frames[pb.n_frames - 1].sfreq;
+    if (!id->new_header) id->new_header = 1;                                 /* pdmp3.c:1318 */
+    id->istart += pb.consumed; id->processed += pb.consumed;
+    if (id->istart == id->iend) id->istart = id->iend = 0;
+    if (direct) {
+      size_t n = (size_t)pb.n_frames * fbytes;
+      outmemory += n; outsize -= n; *done += n;
+    } else {
+      memcpy(outmemory, id->pcm, outsize);
+      id->pend_pos = outsize; id->pend_end = fbytes;
+      *done += outsize; outmemory += outsize; outsize = 0;
+    }
+    res = PDMP3_OK;
+    p3_parsed_free(&pb);
+  }
+  if (id->new_header == 1 && res == PDMP3_OK) res = PDMP3_NEW_FORMAT;       /* pdmp3.c:2470-2472 */
+  return res;
+}
+
+int pdmp3_decode(pdmp3_handle *id, const unsigned char *in, size_t insize, unsigned char *out, size_t outsize, size_t *done)
+{
+  if (!id || !done) return PDMP3_ERR;
+  size_t fr = in_free(id);
+  int res;
+  *done = 0;
+  if (fr > insize) fr = insize;                     /* silently drops what does not fit (pdmp3.c:2497-2498) */
+  res = pdmp3_feed(id, in, fr);
+  if (res == PDMP3_OK) {
+    if (out && outsize) { size_t avail = 0; res = pdmp3_read(id, out, outsize, &avail); *done = avail; }
+    else if (id->processed == 0) {                  /* header peek (pdmp3.c:2507-2516) */
+      int nch, sf;
+      res = PDMP3_NEED_MORE;
+      if (in_filled(id) > 4) {
+        int r = p3_find_header(id->in + id->istart, in_filled(id), &nch, &sf);
+        if (r == 1) { id->nch = nch; id->sfreq = sf; if (!id->new_header) id->new_header = 1; res = PDMP3_OK; }
+        else if (r < 0) res = PDMP3_ERR;
+      }
+      if (id->new_header == 1) res = PDMP3_NEW_FORMAT;
+    }
+  }
+  return res;
+}
+
+int pdmp3_getformat(pdmp3_handle *id, long *rate, int *channels, int *encoding)
+{
+  if (!(id && rate && channels && encoding)) return PDMP3_ERR;
+  *encoding = PDMP3_ENC_SIGNED_16;
+  *rate = k_rates[id->sfreq % 3];
+  *channels = id->nch == 1 ? 1 : 2;
+  id->new_header = -1;
+  return PDMP3_OK;
+}
+
+/* CLI loop of the reference (pdmp3.c:2540-2589): read 16 KiB of PCM at a time, feed 4096 bytes on
+ * NEED_MORE.  Output: <file>.raw, or stdout for "-" (the OUTPUT_RAW writer, pdmp3.c:2236-2257). */
+void pdmp3(char * const *mp3s)
+{
+  unsigned char out[16384], in[4096];
+  pdmp3_handle *id;
+  if (!mp3s) return;
+  if (*mp3s && !strncmp("/dev/dsp", *mp3s, 8)) mp3s++;        /* OSS device argument: accepted, ignored */
+  id = pdmp3_new(NULL, NULL);
+  if (!id) { fputs("Cannot open stream API (out of memory)", stderr); exit(0); }
+  while (*mp3s) {
+    const char *filename = *mp3s++;
+    FILE *fp = !strcmp(filename, "-") ? stdin : fopen(filename, "r");
+    int fd, res; size_t done;
+    if (!fp) { fputs("Cannot open file\n", stderr); exit(0); }
+    if (strcmp(filename, "-")) { char fname[1024]; snprintf(fname, sizeof fname - 1, "%s.raw", filename); fd = open(fname, O_WRONLY | O_CREAT | O_TRUNC, 0666); if (fd == -1) { perror(fname); exit(-1); } }
+    else fd = 1;
+    pdmp3_open_feed(id);
+    while ((res = pdmp3_read(id, out, sizeof out, &done)) != PDMP3_ERR) {
+      if (done && write(fd, out, done) != (ssize_t)done) { fputs("Unable to write raw data\n", stderr); exit(-1); }
+      if (res == PDMP3_NEED_MORE) {
+        size_t n = fread(in, 1, sizeof in, fp);
+        if (!n) break;
+        pdmp3_feed(id, in, n);
+      }
+    }
+    if (fd != 1) close(fd);
+    if (fp != stdin) fclose(fp);
+  }
+  pdmp3_delete(id);
+}

@@ -42,6 +42,9 @@ struct p3_ctx {
   uint8_t next_tail[512]; int have_next_tail;
 };
 
+extern "C" void *p3_host_alloc(size_t bytes) { void *p = NULL; return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : NULL; }
+extern "C" void p3_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 extern "C" int p3_ctx_create(int device, p3_ctx **out)
 {
   int ndev = 0;

@@ -28,6 +28,16 @@ static inline int header_ok(const uint8_t *p)
   return 1;
 }
 
+/* Search_Header without consuming (pdmp3.c:1322-1340): 1 = header found, 0 = need more data,
+ * -1 = no valid header within 1152 bytes of garbage. */
+int p3_find_header(const uint8_t *data, uint64_t n, int *nch, int *sfreq)
+{
+  uint64_t lim = n < 4 ? 0 : (n - 3 < 1153 ? n - 3 : 1153);
+  for (uint64_t p = 0; p < lim; p++)
+    if (header_ok(data + p)) { *nch = (data[p + 3] >> 6) == 3 ? 1 : 2; *sfreq = (data[p + 2] >> 2) & 3; return 1; }
+  return lim == 1153 ? -1 : 0;
+}
+
 typedef struct { const uint8_t *d; unsigned pos; } bitrd;
 static inline unsigned getbits(bitrd *b, unsigned n)     /* MSB first, n <= 16 (pdmp3.c:1547-1561) */
 {
