@@ -111,6 +111,8 @@ int  p3_ctx_create(int device, p3_ctx **out);
 void p3_ctx_destroy(p3_ctx *c);
 int  p3_ctx_reset(p3_ctx *c);                 /* zero overlap / FIFO / reservoir state (pdmp3_open_feed, pdmp3.c:2377-2379) */
 int  p3_ctx_set_mode(p3_ctx *c, int mode);
+int  p3_ctx_set_taps(p3_ctx *c, int on);              /* keep stage taps of the next batches on the device */
+int  p3_ctx_set_frames_per_cta(p3_ctx *c, int n);     /* FAST mode: frames each CTA walks (default 32) */
 const char *p3_last_error(void);
 
 /* Tap buffers (device side, optional; for stage-level parity tests). NULL = not captured. */

@@ -64,6 +64,8 @@ def lib():
     L.p3_ctx_destroy.argtypes = [C.c_void_p]
     L.p3_ctx_reset.argtypes = [C.c_void_p]
     L.p3_ctx_set_mode.argtypes = [C.c_void_p, C.c_int]
+    L.p3_ctx_set_taps.argtypes = [C.c_void_p, C.c_int]
+    L.p3_ctx_set_frames_per_cta.argtypes = [C.c_void_p, C.c_int]
     L.p3_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3Parsed), C.c_void_p, C.POINTER(P3Taps)]
     L.p3_batch_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3Parsed)]
     L.p3_batch_run.argtypes = [C.c_void_p]
@@ -144,6 +146,9 @@ class Context:
 
     def set_mode(self, mode):
         _check(lib().p3_ctx_set_mode(self.h, mode), "p3_ctx_set_mode")
+
+    def set_frames_per_cta(self, n):
+        _check(lib().p3_ctx_set_frames_per_cta(self.h, n), "p3_ctx_set_frames_per_cta")
 
     def reset(self):
         _check(lib().p3_ctx_reset(self.h), "p3_ctx_reset")

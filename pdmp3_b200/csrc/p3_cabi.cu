@@ -7,6 +7,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdarg.h>
+#include <math.h>
+
+extern "C" int p3_fused_upload_consts(const p3_tables *T, const float *dct4);
+extern "C" __global__ void k_synth_fast(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_cta,
+    const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, float *xr_tap, float *y_tap);
 
 static thread_local char g_err[512];
 static int fail(int code, const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); return code; }
@@ -38,7 +43,7 @@ struct p3_ctx {
   int64_t n_frames, n_pcm_frames; uint32_t nch; uint64_t raw_bytes;
   uint32_t k1_smem_words; int64_t chunk_frames;
   p3_frame *h_frames_last; /* unused */
-  int launches;
+  int launches; int taps; int fpc;
   uint8_t next_tail[512]; int have_next_tail;
 };
 
@@ -66,7 +71,12 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
   CK(cudaMalloc(&c->d_tail, 512)); CK(cudaMemset(c->d_tail, 0, 512));
   CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_polyphase, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  c->chunk_frames = 1 << 18;
+  c->chunk_frames = 1 << 18; c->fpc = 32;
+  {
+    static float dct4[18 * 18];
+    for (int k = 0; k < 18; k++) for (int m = 0; m < 18; m++) dct4[k * 18 + m] = (float)cos(3.14159265358979323846 / 18.0 * (k + 0.5) * (m + 0.5));
+    if (p3_fused_upload_consts(p3_tables_get(), dct4) != 0) return fail(P3_ECUDA, "constant upload failed");
+  }
   *out = c;
   return P3_OK;
 }
@@ -96,6 +106,8 @@ extern "C" int p3_ctx_reset(p3_ctx *c)
 }
 
 extern "C" int p3_ctx_set_mode(p3_ctx *c, int mode) { if (!c || (mode != P3_MODE_EXACT && mode != P3_MODE_FAST)) return fail(P3_EINVAL, "bad mode"); c->mode = mode; return P3_OK; }
+extern "C" int p3_ctx_set_taps(p3_ctx *c, int on) { if (!c) return P3_EINVAL; c->taps = on; return P3_OK; }
+extern "C" int p3_ctx_set_frames_per_cta(p3_ctx *c, int n) { if (!c || n < 1) return P3_EINVAL; c->fpc = n; return P3_OK; }
 extern "C" void *p3_ctx_stream(p3_ctx *c) { return c ? (void *)c->stream : NULL; }
 extern "C" int p3_kernel_launch_count(p3_ctx *c) { return c ? c->launches : 0; }
 
@@ -130,8 +142,10 @@ extern "C" int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes
   if ((rc = ensure(&c->is16, (size_t)cf * 4 * 576 * 2))) return rc;
   if ((rc = ensure(&c->count1, (size_t)cf * 4 * 4))) return rc;
   if ((rc = ensure(&c->scf, (size_t)cf * 4 * P3_SCF_STRIDE))) return rc;
-  if ((rc = ensure(&c->xr, (size_t)cf * 4 * 576 * 4))) return rc;
-  if ((rc = ensure(&c->y, (size_t)cf * 4 * 576 * 4))) return rc;
+  if (c->mode == P3_MODE_EXACT || c->taps) {
+    if ((rc = ensure(&c->xr, (size_t)cf * 4 * 576 * 4))) return rc;
+    if ((rc = ensure(&c->y, (size_t)cf * 4 * 576 * 4))) return rc;
+  }
   /* K1 shared-memory window: 512 reservoir bytes + the largest group of K1_FPB frames */
   uint64_t maxg = 0;
   for (int64_t f0 = 0; f0 < nf; f0 += K1_FPB) {
@@ -162,6 +176,16 @@ static int run_chunk(p3_ctx *c, int64_t f0, int64_t f1, cudaEvent_t *ev)
       (const uint8_t *)c->raw.p, fr, gc, c->d_tables, c->d_tail, f0, f1, c->k1_smem_words,
       (int16_t *)c->is16.p, (int32_t *)c->count1.p, (uint8_t *)c->scf.p);
   if (ev) CK(cudaEventRecord(ev[1], c->stream));
+  if (c->mode == P3_MODE_FAST) {
+    /* K2+K3+K4 fused (p3_fused.cu) */
+    k_synth_fast<<<(unsigned)((nf + c->fpc - 1) / c->fpc), 128, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
+        (const int16_t *)c->is16.p, (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so, (int16_t *)c->pcm.p,
+        c->taps ? (float *)c->xr.p : NULL, c->taps ? (float *)c->y.p : NULL);
+    if (ev) { CK(cudaEventRecord(ev[2], c->stream)); CK(cudaEventRecord(ev[3], c->stream)); CK(cudaEventRecord(ev[4], c->stream)); }
+    CK(cudaGetLastError());
+    c->cur ^= 1; c->launches += 2;
+    return P3_OK;
+  }
   k_requant<<<(unsigned)(2 * nf), K2_THREADS, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, (const int16_t *)c->is16.p,
       (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so, (float *)c->xr.p);
   if (ev) CK(cudaEventRecord(ev[2], c->stream));
@@ -226,6 +250,8 @@ extern "C" int p3_batch_download(p3_ctx *c, int16_t *pcm, const p3_taps *t)
 extern "C" int p3_decode_batch(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *b, int16_t *pcm, const p3_taps *t)
 {
   int rc;
+  if (!c) return fail(P3_EINVAL, "null ctx");
+  c->taps = t != NULL;
   if ((rc = p3_batch_upload(c, raw, raw_bytes, b))) return rc;
   if ((rc = p3_batch_run(c))) return rc;
   if ((rc = p3_batch_download(c, pcm, t))) return rc;

@@ -17,6 +17,7 @@ struct p3_state {
   float vhist[2][15][64];         /* matrixed vectors of the last 15 slots, [ch][age-1][i], age 1 = most recent */
   int32_t count1[2][2];           /* effective count1 of the last frame, [gr][ch]                   */
   int32_t pad[4];
+  float xhist[2][15][32];         /* FAST mode: 32-point DCT of the last 15 slots, [ch][age-1][k]   */
 };
 
 /* ---- MSB-first bit access over big-endian words in shared memory (pdmp3.c:1489-1527) ---- */

@@ -1,0 +1,311 @@
+/* p3_fused.cu -- FAST mode: requantize + reorder + stereo + antialias + IMDCT + polyphase + PCM in
+ * ONE kernel (the whole of Decode_L3, pdmp3.c:1024-1060, plus Convert_Frame_S16, 2307-2345).
+ *
+ * Only the Huffman output (int16 spectra) is read and only int16 PCM is written; everything in
+ * between lives in shared memory and registers.  One CTA walks a run of consecutive frames so the
+ * two pieces of state the reference keeps in static arrays -- the IMDCT overlap (store, pdmp3.c:1755)
+ * and the 16-slot polyphase FIFO (v_vec, pdmp3.c:1983) -- stay on chip; a run is primed by decoding
+ * the frame in front of it without emitting PCM (halo of one frame).
+ *
+ * Transforms are evaluated with fast algorithms instead of the reference's O(N^2) loops:
+ *   - 36-point IMDCT = 18-point DCT-IV plus sign/index symmetry (4x fewer MACs than pdmp3.c:1689-1698)
+ *   - 64x32 matrixing = 32-point DCT-II (Lee) plus symmetry: V[i] is +-X[k] or 0, so only X[0..31] is kept
+ *     (pdmp3.c:2010-2014 needs 2048 MACs per slot, this needs ~290 flops)
+ *   - the 512-tap window (pdmp3.c:2015-2026) runs from registers with a sliding 33-slot history.
+ * Sums are therefore taken in a different order than the reference: PCM differs by at most 1 LSB
+ * (tests/test_gpu_fast.py); the stages up to antialias keep the reference's exact arithmetic.
+ */
+#include "p3_device.cuh"
+#include "p3_kernels.h"
+#include "p3_lee.inc"
+
+struct p3_fconst {
+  float dct4[18][18];              /* cos(pi/18 (k+1/2)(m+1/2)) */
+  float win[4][36];
+  float cos12[6][12];
+  float cs[8], ca[8], is_l[8], is_r[8];
+  float t1h[40];
+  float t2[320];
+};
+__constant__ p3_fconst FC;
+
+extern "C" int p3_fused_upload_consts(const p3_tables *T, const float *dct4)
+{
+  static p3_fconst h;
+  memcpy(h.dct4, dct4, sizeof h.dct4);
+  memcpy(h.win, T->imdct_win, sizeof h.win); memcpy(h.cos12, T->cos12, sizeof h.cos12);
+  memcpy(h.cs, T->cs, 32); memcpy(h.ca, T->ca, 32); memcpy(h.is_l, T->is_l, 32); memcpy(h.is_r, T->is_r, 32);
+  memcpy(h.t1h, T->t1h, sizeof h.t1h); memcpy(h.t2, T->t2, sizeof h.t2);
+  return (int)cudaMemcpyToSymbol(FC, &h, sizeof h);
+}
+
+/* ---- 32-point DCT-II, Lee's recursion, fully unrolled in registers ---------------------------- */
+template <int N> struct Lee { static __device__ __forceinline__ const float *k(); };
+#define LEE_TAB(N) template <> struct Lee<N> { static __device__ __forceinline__ float c(int i) { constexpr float t[N / 2] = P3_LEE##N; return t[i]; } };
+LEE_TAB(32) LEE_TAB(16) LEE_TAB(8) LEE_TAB(4) LEE_TAB(2)
+
+template <int N> __device__ __forceinline__ void dct2(float (&x)[N])
+{
+  if constexpr (N == 1) return;
+  else {
+    float a[N / 2], b[N / 2];
+    #pragma unroll
+    for (int i = 0; i < N / 2; i++) { a[i] = x[i] + x[N - 1 - i]; b[i] = (x[i] - x[N - 1 - i]) * Lee<N>::c(i); }
+    dct2<N / 2>(a); dct2<N / 2>(b);
+    #pragma unroll
+    for (int i = 0; i < N / 2; i++) { x[2 * i] = a[i]; x[2 * i + 1] = (i + 1 < N / 2) ? b[i] + b[i + 1] : b[i]; }
+  }
+}
+
+#define FT 128                     /* threads per CTA */
+#define XPITCH 33
+#define XSLOTS 64
+
+__device__ __forceinline__ float fq_requant(const float *__restrict__ pow43, int v, uint32_t e2, int q)
+{
+  float t3 = __ldg(pow43 + (v < 0 ? -v : v));
+  if (v < 0) t3 = -t3;
+  return __fmul_rn(__fmul_rn(FC.t1h[e2], FC.t2[q + P3_T2_BIAS]), t3);
+}
+
+extern "C" __global__ void __launch_bounds__(FT)
+k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
+             int64_t f_first, int64_t f_end, int frames_per_cta,
+             const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf,
+             const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm,
+             float *__restrict__ xr_tap, float *__restrict__ y_tap)
+{
+  __shared__ float xs[4][576];
+  __shared__ float tails[3][2][576];
+  __shared__ float xring[2][XSLOTS][XPITCH];
+  __shared__ uint8_t s_sfb_l[576], s_sfbw_s[576];
+  __shared__ uint16_t s_reo[576];
+  __shared__ uint8_t s_scf[4][P3_SCF_STRIDE];
+  __shared__ int32_t s_c1[4];
+  __shared__ uint32_t s_sfreq;
+
+  const int tid = threadIdx.x;
+  const int64_t c0 = f_first + (int64_t)blockIdx.x * frames_per_cta;
+  const int64_t c1 = min(c0 + (int64_t)frames_per_cta, f_end);
+  const int warm = blockIdx.x > 0 ? 1 : 0;
+  const uint32_t nch = frames[c0].nch;
+
+  /* window coefficients of this thread's output column j, signs of the V<->X symmetry folded in */
+  const int j = tid & 31, wgr = (tid >> 5) & 1, wch = tid >> 6;
+  float ce[8], co[8]; int ia, ib;
+  {
+    /* even k: V[j]:   j<16 -> +X[16+j];  j==16 -> 0;  j>16 -> -X[48-j]
+       odd  k: V[32+j]: j<16 -> -X[16-j]; j>=16 -> -X[j-16]                       (see tools/proto/fast_transforms.py) */
+    float se = j < 16 ? 1.0f : (j == 16 ? 0.0f : -1.0f);
+    ia = j < 16 ? 16 + j : (j == 16 ? 0 : 48 - j);
+    ib = j < 16 ? 16 - j : j - 16;
+    #pragma unroll
+    for (int k = 0; k < 8; k++) { ce[k] = se * T->synth_d[64 * k + j]; co[k] = -T->synth_d[64 * k + 32 + j]; }
+  }
+
+  /* carried state */
+  for (int i = tid; i < 2 * 576; i += FT) {
+    (&tails[2][0][0])[i] = warm ? 0.0f : st_in->store[i / 576][i % 576];
+    (&tails[0][0][0])[i] = 0.0f; (&tails[1][0][0])[i] = 0.0f;
+  }
+  for (int i = tid; i < 2 * XSLOTS * XPITCH; i += FT) (&xring[0][0][0])[i] = 0.0f;
+  __syncthreads();
+  if (!warm)
+    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, s = r / 32, k = r % 32; xring[ch][s][k] = st_in->xhist[ch][14 - s][k]; }
+  if (tid == 0) s_sfreq = 0xffffffffu;
+  __syncthreads();
+
+  int n = 0;                                              /* frame iteration within this CTA */
+  for (int64_t f = c0 - warm; f < c1; f++, n++) {
+    const p3_frame fr = frames[f];
+    const int64_t o0 = (f - f_first) * 4;
+    const bool emit = !(warm && n == 0) && (fr.flags & P3_FRAME_DECODE);
+    if (s_sfreq != fr.sfreq) {                            /* per-line helper tables of this sample rate */
+      __syncthreads();
+      for (int i = tid; i < 576; i += FT) { s_sfb_l[i] = T->line_sfb_l[fr.sfreq][i]; s_sfbw_s[i] = T->line_sfbw_s[fr.sfreq][i]; s_reo[i] = T->reorder_src[fr.sfreq][i]; }
+      if (tid == 0) s_sfreq = fr.sfreq;
+    }
+    for (int i = tid; i < 4 * P3_SCF_STRIDE; i += FT) (&s_scf[0][0])[i] = scf[o0 * P3_SCF_STRIDE + i];
+    if (tid < 4) {                                        /* effective count1 (Q6), as in k_requant */
+      const uint32_t gr = tid >> 1, ch = tid & 1;
+      int32_t c = 0;
+      if (ch < nch) {
+        const uint32_t back = gcs[4 * f + tid].w3;
+        if (back == 0) c = count1[o0 + tid];
+        else if ((int64_t)back <= f - f_first) c = count1[o0 + tid - 4 * (int64_t)back];
+        else c = st_in->count1[gr][ch];
+      }
+      s_c1[tid] = c;
+      if (f == f_end - 1) st_out->count1[gr][ch] = c;
+    }
+    __syncthreads();
+
+    /* ---- A: requantize + reorder (exact arithmetic of pdmp3.c:2121-2152) ---- */
+    for (int e = tid; e < 4 * 576; e += FT) {
+      const uint32_t gcl = e / 576, d = e % 576, ch = gcl & 1;
+      float r = 0.0f;
+      if (ch < nch) {
+        const p3_gc g = gcs[4 * f + gcl];
+        const bool is_short = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
+        const uint32_t first_short = is_short ? (P3_GC_MIXED(g) ? 36u : 0u) : 576u;
+        const uint32_t mult = P3_GC_SCALE(g) ? 2u : 1u;
+        const int gg = (int)P3_GC_GAIN(g) - 210;
+        const int16_t *isp = is_in + (o0 + gcl) * 576;
+        if (d >= first_short) {
+          const uint32_t s = s_reo[d], sw = s_sfbw_s[s], sfb = sw & 15u, win = sw >> 4;
+          const uint32_t sc = sfb < 12 ? s_scf[gcl][P3_SCF_S_OFF + 3 * sfb + win] : 0u;
+          r = fq_requant(T->pow43, isp[s], mult * sc, gg - 8 * (int)P3_GC_SBG(g, win));
+        } else {
+          const uint32_t sfb = s_sfb_l[d];
+          const uint32_t sc = sfb < 21 ? s_scf[gcl][sfb] + P3_GC_PREF(g) * T->pretab[sfb] : 0u;
+          r = fq_requant(T->pow43, isp[d], mult * sc, gg);
+        }
+      }
+      xs[gcl][d] = r;
+    }
+    __syncthreads();
+
+    /* ---- B: stereo (pdmp3.c:1916-1971), both granules ---- */
+    if (nch == 2 && fr.mode == 1 && fr.mode_ext != 0) {
+      for (int e = tid; e < 2 * 576; e += FT) {
+        const uint32_t gr = e / 576, i = e % 576;
+        const p3_gc g0 = gcs[4 * f + 2 * gr];
+        const uint32_t cl = (uint32_t)s_c1[2 * gr], c1r = (uint32_t)s_c1[2 * gr + 1];
+        const uint32_t msn = (fr.mode_ext & 2) ? (cl > c1r ? c1r : cl) : 0u;
+        const bool sh0 = P3_GC_WINSW(g0) && P3_GC_BTYPE(g0) == 2;
+        const uint32_t first_short0 = sh0 ? (P3_GC_MIXED(g0) ? 36u : 0u) : 576u;
+        float l = xs[2 * gr][i], r = xs[2 * gr + 1][i];
+        if (i < msn) {
+          float a = __fadd_rn(l, r), b = __fsub_rn(l, r);
+          l = __double2float_rn(__dmul_rn((double)a, 0.70710678118654752440));
+          r = __double2float_rn(__dmul_rn((double)b, 0.70710678118654752440));
+        } else if (fr.mode_ext & 1) {
+          if (i >= first_short0) {
+            const uint32_t sw = s_sfbw_s[i], sfb = sw & 15u, win = sw >> 4;
+            if (sfb < 12 && 3u * T->sfb_s[fr.sfreq][sfb] >= c1r && s_scf[2 * gr][P3_SCF_S_OFF + 3 * sfb + win] != 7) {
+              float x = (float)(unsigned)(long long)l; l = x; r = x;             /* Q4 */
+            }
+          } else {
+            const uint32_t sfb = s_sfb_l[i], lim = sh0 ? 8u : 21u;
+            if (sfb < lim && T->sfb_l[fr.sfreq][sfb] >= c1r) {
+              const uint32_t p = s_scf[2 * gr][sfb];
+              if (p != 7) { float x = l; l = __fmul_rn(FC.is_l[p & 7], x); r = __fmul_rn(FC.is_r[p & 7], x); }
+            }
+          }
+        }
+        xs[2 * gr][i] = l; xs[2 * gr + 1][i] = r;
+      }
+      __syncthreads();
+    }
+
+    /* ---- C: antialias (pdmp3.c:1706-1732) ---- */
+    for (int e = tid; e < 4 * 248; e += FT) {
+      const uint32_t gcl = e / 248, t = e % 248, sb = 1 + (t >> 3), i = t & 7;
+      if ((gcl & 1) < nch) {
+        const p3_gc g = gcs[4 * f + gcl];
+        const bool sh = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
+        const uint32_t sblim = sh ? (P3_GC_MIXED(g) ? 2u : 1u) : 32u;
+        if (sb < sblim) {
+          const uint32_t li = 18 * sb - 1 - i, ui = 18 * sb + i;
+          const float a = xs[gcl][li], b = xs[gcl][ui];
+          xs[gcl][li] = __fsub_rn(__fmul_rn(a, FC.cs[i]), __fmul_rn(b, FC.ca[i]));
+          xs[gcl][ui] = __fadd_rn(__fmul_rn(b, FC.cs[i]), __fmul_rn(a, FC.ca[i]));
+        }
+      }
+    }
+    __syncthreads();
+    if (xr_tap) for (int e = tid; e < 4 * 576; e += FT) xr_tap[o0 * 576 + e] = (&xs[0][0])[e];
+
+    /* ---- D: IMDCT + window; first half in place, second half to the tail buffer ---- */
+    {
+      const uint32_t gcl = tid >> 5, sb = tid & 31, gr = gcl >> 1, ch = gcl & 1;
+      if (ch < nch) {
+        const p3_gc g = gcs[4 * f + gcl];
+        const uint32_t bt = (P3_GC_WINSW(g) && P3_GC_MIXED(g) && sb < 2) ? 0u : P3_GC_BTYPE(g);
+        float *x = &xs[gcl][18 * sb];
+        float *tl = &tails[gr == 0 ? 0 : 1 + (n & 1)][ch][18 * sb];
+        float in[18];
+        #pragma unroll
+        for (int m = 0; m < 18; m++) in[m] = x[m];
+        if (bt != 2) {
+          #pragma unroll
+          for (int k = 0; k < 18; k++) {
+            float t = 0.0f;
+            #pragma unroll
+            for (int m = 0; m < 18; m++) t = fmaf(in[m], FC.dct4[k][m], t);
+            if (k < 9) { tl[8 - k] = -t * FC.win[bt][26 - k]; tl[9 + k] = -t * FC.win[bt][27 + k]; }
+            else { x[k - 9] = t * FC.win[bt][k - 9]; x[26 - k] = -t * FC.win[bt][26 - k]; }
+          }
+        } else {
+          /* three 12-point transforms (pdmp3.c:1673-1686): raw[6w+6+p] += win2[p] * sum_m in[w+3m] cos12[m][p] */
+          float raw[36];
+          #pragma unroll
+          for (int p = 0; p < 36; p++) raw[p] = 0.0f;
+          #pragma unroll
+          for (int w = 0; w < 3; w++)
+            #pragma unroll
+            for (int p = 0; p < 12; p++) {
+              float sum = 0.0f;
+              #pragma unroll
+              for (int m = 0; m < 6; m++) sum = fmaf(in[w + 3 * m], FC.cos12[m][p], sum);
+              raw[6 * w + 6 + p] += sum * FC.win[2][p];
+            }
+          #pragma unroll
+          for (int i = 0; i < 18; i++) { x[i] = raw[i]; tl[i] = raw[18 + i]; }
+        }
+      }
+    }
+    __syncthreads();
+
+    /* ---- E: overlap-add + frequency inversion + 32-point DCT per time slot -> X ring ---- */
+    if (tid < 72) {
+      const uint32_t gr = tid / 36, r = tid % 36, ch = r / 18, ss = r % 18;
+      if (ch < nch) {
+        const float *cur = &xs[2 * gr + ch][0];
+        const float *prv = gr == 0 ? &tails[2 - (n & 1)][ch][0] : &tails[0][ch][0];
+        float s[32];
+        #pragma unroll
+        for (int sb = 0; sb < 32; sb++) {
+          float v = cur[18 * sb + ss] + prv[18 * sb + ss];                 /* rawout + store (pdmp3.c:1775) */
+          s[sb] = ((sb & 1) && (ss & 1)) ? -v : v;                         /* frequency inversion (1741-1743) */
+        }
+        if (y_tap) {
+          #pragma unroll
+          for (int sb = 0; sb < 32; sb++) y_tap[(o0 + 2 * gr + ch) * 576 + ss * 32 + sb] = s[sb];
+        }
+        dct2<32>(s);
+        float *X = &xring[ch][(15 + n * 36 + gr * 18 + ss) & (XSLOTS - 1)][0];
+        #pragma unroll
+        for (int k = 0; k < 32; k++) X[k] = s[k];
+      }
+    }
+    __syncthreads();
+
+    /* ---- F: 512-tap window from registers + PCM ---- */
+    if (wch < (int)nch && emit) {
+      const int t0 = 15 + n * 36 + wgr * 18;                               /* ring slot of this granule's first time slot */
+      float A[33], B[33];                                                  /* A[i] = X(t0-15+i)[ia], B[i] = X(t0-15+i)[ib] */
+      #pragma unroll
+      for (int i = 0; i < 33; i++) { const float *X = &xring[wch][(t0 - 15 + i) & (XSLOTS - 1)][0]; A[i] = X[ia]; B[i] = X[ib]; }
+      const int64_t base = ((int64_t)fr.pcm_index * 1152 + wgr * 576 + j) * nch + wch;
+      #pragma unroll
+      for (int ss = 0; ss < 18; ss++) {
+        float sum = 0.0f;
+        #pragma unroll
+        for (int k = 0; k < 8; k++) { sum = fmaf(ce[k], A[15 + ss - 2 * k], sum); sum = fmaf(co[k], B[15 + ss - 2 * k - 1], sum); }
+        const double d = __dmul_rn((double)sum, 32767.0);
+        int32_t s = (d > -2147483649.0 && d < 2147483648.0) ? __double2int_rz(d) : (int32_t)0x80000000;
+        s = s > 32767 ? 32767 : (s < -32767 ? -32767 : s);
+        pcm[base + (int64_t)ss * 32 * nch] = (int16_t)s;
+      }
+    }
+    /* next iteration's first __syncthreads() orders F's ring reads against E's writes */
+  }
+  __syncthreads();
+  if (c1 == f_end) {                                       /* leave the state for the next launch */
+    const int last = n - 1;
+    for (int i = tid; i < 2 * 576; i += FT) st_out->store[i / 576][i % 576] = tails[1 + (last & 1)][i / 576][i % 576];
+    const int tl = 15 + last * 36 + 35;
+    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, age = r / 32, k = r % 32; st_out->xhist[ch][age][k] = xring[ch][(tl - age) & (XSLOTS - 1)][k]; }
+  }
+}

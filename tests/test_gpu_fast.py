@@ -1,0 +1,57 @@
+"""FAST mode (fused kernel, fast transforms): PCM within 1 LSB of int16 of the oracle / reference
+(the tolerance BASELINE.json's north_star states), integer stages and the requantize..antialias
+stages still bit-exact, results independent of how frames are split over CTAs and batches."""
+import numpy as np, pytest
+import p3harness as H
+from test_gpu_parity import VARIANTS, feq
+
+pytestmark = pytest.mark.gpu
+
+PCM_TOL_LSB = 1          # |pcm - pcm_ref| <= 1 LSB of int16, every sample
+
+
+@pytest.fixture(scope="module")
+def fast_ctx():
+    import pdmp3_b200
+    c = pdmp3_b200.Context(0, pdmp3_b200.MODE_FAST)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_fast_within_one_lsb(fast_ctx, name):
+    s, _ = H.synth(150, seed=31, **VARIANTS[name])
+    o = H.oracle_decode(s, lookahead=1152)
+    fast_ctx.reset()
+    pcm, t = fast_ctx.decode(s, lookahead=1152, taps=True)
+    nch = pcm.shape[2]
+    assert np.array_equal(t["is_huff"][:, :, :nch], o["is_huff"][:, :, :nch])
+    assert feq(t["xr"][:, :, :nch], o["xr_ali"][:, :, :nch]).all(), "requantize..antialias must stay bit-exact"
+    ya, yb = t["y"][:, :, :nch].astype(np.float64), o["y_hyb"][:, :, :nch].astype(np.float64)
+    scale = np.abs(yb).max() + 1e-30
+    assert np.abs(ya - yb).max() <= 3e-5 * scale, "hybrid synthesis (fast IMDCT) drifted"
+    d = np.abs(pcm.astype(np.int32) - o["pcm"].astype(np.int32))
+    assert d.max() <= PCM_TOL_LSB, "max |diff| = %d LSB" % d.max()
+    assert (d == 0).mean() > 0.90, "only %.3f of samples exactly equal" % (d == 0).mean()
+
+
+def test_fast_partition_independent(fast_ctx):
+    """Same PCM bit for bit whether a CTA walks 3 or 32 frames, and whether the stream is decoded
+    as one batch or as four batches with carried state."""
+    import pdmp3_b200
+    s, _ = H.synth(260, seed=8, **H.CONFIGS["cfg4_vbr_mixed"])
+    fast_ctx.reset(); fast_ctx.set_frames_per_cta(32); a = fast_ctx.decode(s, lookahead=0)
+    fast_ctx.reset(); fast_ctx.set_frames_per_cta(3); b = fast_ctx.decode(s, lookahead=0)
+    fast_ctx.set_frames_per_cta(32)
+    assert np.array_equal(a, b)
+    # four batches through the parser state / context state
+    fast_ctx.reset()
+    st = pdmp3_b200._binding.P3ParseState(0, 0, 0, -1, -1)
+    pos, parts = 0, []
+    while True:
+        p = pdmp3_b200.parse_stream(s[pos:], lookahead=0, max_frames=70, state=st)
+        if p.n_frames == 0: break
+        for f in range(p.n_frames): p.c.frames[f].pcm_index = f
+        parts.append(fast_ctx.decode_parsed(p)); pos += p.consumed
+    c = np.concatenate(parts)
+    assert np.array_equal(a, c)

@@ -46,3 +46,22 @@ def test_stage_taps_exact_vs_oracle(gpu_ctx, name):
         r = H.ref_decode(s, taps=False)
         ref = r["pcm"] if nch == 2 else r["pcm"][:, :, :1]
         assert np.array_equal(pcm, ref), "PCM vs compiled reference"
+
+
+def test_exact_batches_with_carried_state(gpu_ctx):
+    """Streaming continuity: four batches with state carried in the context == one batch, bit for bit
+    (IMDCT overlap, polyphase history, bit reservoir tail, stale count1)."""
+    import pdmp3_b200
+    s, _ = H.synth(230, seed=12, **H.CONFIGS["cfg4_vbr_mixed"])
+    gpu_ctx.reset(); a = gpu_ctx.decode(s, lookahead=0)
+    gpu_ctx.reset()
+    st = pdmp3_b200._binding.P3ParseState(0, 0, 0, -1, -1)
+    pos, parts = 0, []
+    while True:
+        p = pdmp3_b200.parse_stream(s[pos:], lookahead=0, max_frames=61, state=st)
+        if p.n_frames == 0: break
+        for f in range(p.n_frames): p.c.frames[f].pcm_index = f
+        parts.append(gpu_ctx.decode_parsed(p)); pos += p.consumed
+    assert np.array_equal(a, np.concatenate(parts))
+    o = H.oracle_decode(s, lookahead=0)
+    assert np.array_equal(a, o["pcm"])
