@@ -105,7 +105,14 @@ extern "C" int p3_ctx_reset(p3_ctx *c)
   return P3_OK;
 }
 
-extern "C" int p3_ctx_set_mode(p3_ctx *c, int mode) { if (!c || (mode != P3_MODE_EXACT && mode != P3_MODE_FAST)) return fail(P3_EINVAL, "bad mode"); c->mode = mode; return P3_OK; }
+extern "C" int p3_ctx_set_mode(p3_ctx *c, int mode)
+{
+  if (!c || (mode != P3_MODE_EXACT && mode != P3_MODE_FAST)) return fail(P3_EINVAL, "bad mode");
+  c->mode = mode;
+  /* frames per kernel-sequence launch: EXACT keeps fp32 intermediates of every stage in HBM (28 KB/frame), FAST only the int16 spectra */
+  c->chunk_frames = mode == P3_MODE_FAST ? (1 << 21) : (1 << 18);
+  return P3_OK;
+}
 extern "C" int p3_ctx_set_taps(p3_ctx *c, int on) { if (!c) return P3_EINVAL; c->taps = on; return P3_OK; }
 extern "C" int p3_ctx_set_frames_per_cta(p3_ctx *c, int n) { if (!c || n < 1) return P3_EINVAL; c->fpc = n; return P3_OK; }
 extern "C" void *p3_ctx_stream(p3_ctx *c) { return c ? (void *)c->stream : NULL; }
@@ -153,7 +160,7 @@ extern "C" int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes
     uint64_t span = b->frames[f1 - 1].main_pos + b->frames[f1 - 1].main_size - b->frames[f0].main_pos;
     if (span > maxg) maxg = span;
   }
-  c->k1_smem_words = (uint32_t)((512 + maxg + 16 + 3) / 4);
+  c->k1_smem_words = (uint32_t)((512 + maxg + 16 + 3) / 4 + 3) & ~3u;   /* multiple of 16 bytes: the staging areas behind it hold uint4 */
   if ((size_t)c->k1_smem_words * 4 + sizeof(((p3_tables *)0)->hlut) > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
   CK(cudaMemcpyAsync(c->raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->frames.p, b->frames, (size_t)nf * sizeof(p3_frame), cudaMemcpyHostToDevice, c->stream));
@@ -171,7 +178,7 @@ static int run_chunk(p3_ctx *c, int64_t f0, int64_t f1, cudaEvent_t *ev)
   p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
   CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));   /* fields a launch does not rewrite carry over */
   if (ev) CK(cudaEventRecord(ev[0], c->stream));
-  size_t smem1 = (size_t)c->k1_smem_words * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
+  size_t smem1 = (size_t)c->k1_smem_words * 4 + (8 + 16) * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
   k_huffman<<<(unsigned)((nf + K1_FPB - 1) / K1_FPB), K1_THREADS, smem1, c->stream>>>(
       (const uint8_t *)c->raw.p, fr, gc, c->d_tables, c->d_tail, f0, f1, c->k1_smem_words,
       (int16_t *)c->is16.p, (int32_t *)c->count1.p, (uint8_t *)c->scf.p);

@@ -59,7 +59,17 @@ template <int N> __device__ __forceinline__ void dct2(float (&x)[N])
 
 #define FT 128                     /* threads per CTA */
 #define XPITCH 33
-#define XSLOTS 64
+#define XSLOTS 52                  /* >= 15 history + 36 new slots; 52*33 floats per channel */
+
+/* per granule-channel parameters, unpacked once per frame by threads 0..3 */
+struct gcpar {
+  int32_t  c1;                     /* effective count1 (Q6) */
+  int32_t  gg;                     /* global_gain - 210 */
+  uint16_t first_short;            /* first line that uses short windows (576: none) */
+  uint8_t  mult, pre, bt, mixed, ws, live;
+  uint8_t  sbg8[3];                /* 8 * subblock_gain */
+  uint8_t  sblim;                  /* antialias subband limit */
+};
 
 __device__ __forceinline__ float fq_requant(const float *__restrict__ pow43, int v, uint32_t e2, int q)
 {
@@ -68,7 +78,9 @@ __device__ __forceinline__ float fq_requant(const float *__restrict__ pow43, int
   return __fmul_rn(__fmul_rn(FC.t1h[e2], FC.t2[q + P3_T2_BIAS]), t3);
 }
 
-extern "C" __global__ void __launch_bounds__(FT)
+__device__ __forceinline__ int ring_slot(int s) { return s % XSLOTS; }
+
+extern "C" __global__ void __launch_bounds__(FT, 5)
 k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
              int64_t f_first, int64_t f_end, int frames_per_cta,
              const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf,
@@ -78,10 +90,11 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   __shared__ float xs[4][576];
   __shared__ float tails[3][2][576];
   __shared__ float xring[2][XSLOTS][XPITCH];
+  __shared__ __align__(16) int16_t isbuf[4][576];
   __shared__ uint8_t s_sfb_l[576], s_sfbw_s[576];
   __shared__ uint16_t s_reo[576];
-  __shared__ uint8_t s_scf[4][P3_SCF_STRIDE];
-  __shared__ int32_t s_c1[4];
+  __shared__ __align__(16) uint8_t s_scf[4][P3_SCF_STRIDE];
+  __shared__ gcpar s_par[4];
   __shared__ uint32_t s_sfreq;
 
   const int tid = threadIdx.x;
@@ -100,7 +113,7 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
     ia = j < 16 ? 16 + j : (j == 16 ? 0 : 48 - j);
     ib = j < 16 ? 16 - j : j - 16;
     #pragma unroll
-    for (int k = 0; k < 8; k++) { ce[k] = se * T->synth_d[64 * k + j]; co[k] = -T->synth_d[64 * k + 32 + j]; }
+    for (int k = 0; k < 8; k++) { ce[k] = se * T->synth_d[64 * k + j] * 32767.0f; co[k] = -T->synth_d[64 * k + 32 + j] * 32767.0f; }
   }
 
   /* carried state */
@@ -113,6 +126,16 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   if (!warm)
     for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, s = r / 32, k = r % 32; xring[ch][s][k] = st_in->xhist[ch][14 - s][k]; }
   if (tid == 0) s_sfreq = 0xffffffffu;
+
+  /* software pipeline: the spectra of frame n+1 are fetched into registers while frame n is processed */
+  uint32_t pre[9]; uint32_t pre_scf = 0;
+  const uint32_t *isw = reinterpret_cast<const uint32_t *>(is_in);
+  {
+    const int64_t o0 = (c0 - warm - f_first) * 4;
+    #pragma unroll
+    for (int k = 0; k < 9; k++) pre[k] = __ldg(isw + o0 * 288 + tid + FT * k);
+    if (tid < 64) pre_scf = __ldg(reinterpret_cast<const uint32_t *>(scf + o0 * P3_SCF_STRIDE) + tid);
+  }
   __syncthreads();
 
   int n = 0;                                              /* frame iteration within this CTA */
@@ -125,86 +148,114 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       for (int i = tid; i < 576; i += FT) { s_sfb_l[i] = T->line_sfb_l[fr.sfreq][i]; s_sfbw_s[i] = T->line_sfbw_s[fr.sfreq][i]; s_reo[i] = T->reorder_src[fr.sfreq][i]; }
       if (tid == 0) s_sfreq = fr.sfreq;
     }
-    for (int i = tid; i < 4 * P3_SCF_STRIDE; i += FT) (&s_scf[0][0])[i] = scf[o0 * P3_SCF_STRIDE + i];
-    if (tid < 4) {                                        /* effective count1 (Q6), as in k_requant */
+    /* land the prefetched spectra / scalefactors in shared memory, start the next fetch */
+    {
+      uint32_t *ib32 = reinterpret_cast<uint32_t *>(&isbuf[0][0]);
+      #pragma unroll
+      for (int k = 0; k < 9; k++) ib32[tid + FT * k] = pre[k];
+      if (tid < 64) reinterpret_cast<uint32_t *>(&s_scf[0][0])[tid] = pre_scf;
+      if (f + 1 < c1) {
+        #pragma unroll
+        for (int k = 0; k < 9; k++) pre[k] = __ldg(isw + (o0 + 4) * 288 + tid + FT * k);
+        if (tid < 64) pre_scf = __ldg(reinterpret_cast<const uint32_t *>(scf + (o0 + 4) * P3_SCF_STRIDE) + tid);
+      }
+    }
+    if (tid < 4) {                                        /* unpack the side info of this granule-channel once */
       const uint32_t gr = tid >> 1, ch = tid & 1;
+      const p3_gc g = gcs[4 * f + tid];
+      gcpar p;
       int32_t c = 0;
-      if (ch < nch) {
-        const uint32_t back = gcs[4 * f + tid].w3;
+      if (ch < nch) {                                     /* effective count1 (Q6), as in k_requant */
+        const uint32_t back = g.w3;
         if (back == 0) c = count1[o0 + tid];
         else if ((int64_t)back <= f - f_first) c = count1[o0 + tid - 4 * (int64_t)back];
         else c = st_in->count1[gr][ch];
       }
-      s_c1[tid] = c;
       if (f == f_end - 1) st_out->count1[gr][ch] = c;
+      const bool is_short = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
+      p.c1 = c; p.gg = (int)P3_GC_GAIN(g) - 210;
+      p.first_short = is_short ? (P3_GC_MIXED(g) ? 36 : 0) : 576;
+      p.mult = P3_GC_SCALE(g) ? 2 : 1; p.pre = P3_GC_PREF(g); p.bt = P3_GC_BTYPE(g); p.mixed = P3_GC_MIXED(g); p.ws = P3_GC_WINSW(g);
+      p.live = ch < nch;
+      p.sbg8[0] = 8 * P3_GC_SBG(g, 0); p.sbg8[1] = 8 * P3_GC_SBG(g, 1); p.sbg8[2] = 8 * P3_GC_SBG(g, 2);
+      p.sblim = is_short ? (P3_GC_MIXED(g) ? 2 : 1) : 32;
+      s_par[tid] = p;
     }
     __syncthreads();
 
     /* ---- A: requantize + reorder (exact arithmetic of pdmp3.c:2121-2152) ---- */
-    for (int e = tid; e < 4 * 576; e += FT) {
-      const uint32_t gcl = e / 576, d = e % 576, ch = gcl & 1;
-      float r = 0.0f;
-      if (ch < nch) {
-        const p3_gc g = gcs[4 * f + gcl];
-        const bool is_short = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
-        const uint32_t first_short = is_short ? (P3_GC_MIXED(g) ? 36u : 0u) : 576u;
-        const uint32_t mult = P3_GC_SCALE(g) ? 2u : 1u;
-        const int gg = (int)P3_GC_GAIN(g) - 210;
-        const int16_t *isp = is_in + (o0 + gcl) * 576;
-        if (d >= first_short) {
-          const uint32_t s = s_reo[d], sw = s_sfbw_s[s], sfb = sw & 15u, win = sw >> 4;
-          const uint32_t sc = sfb < 12 ? s_scf[gcl][P3_SCF_S_OFF + 3 * sfb + win] : 0u;
-          r = fq_requant(T->pow43, isp[s], mult * sc, gg - 8 * (int)P3_GC_SBG(g, win));
-        } else {
-          const uint32_t sfb = s_sfb_l[d];
-          const uint32_t sc = sfb < 21 ? s_scf[gcl][sfb] + P3_GC_PREF(g) * T->pretab[sfb] : 0u;
-          r = fq_requant(T->pow43, isp[d], mult * sc, gg);
+    #pragma unroll 1
+    for (int gcl = 0; gcl < 4; gcl++) {
+      const gcpar p = s_par[gcl];
+      if (!p.live) { for (int d = tid; d < 576; d += FT) xs[gcl][d] = 0.0f; continue; }
+      const int16_t *isp = isbuf[gcl];
+      const uint8_t *sc8 = s_scf[gcl];
+      #pragma unroll
+      for (int it = 0; it < 5; it++) {
+        const int d = tid + FT * it;
+        if (d < 576) {
+          float r;
+          if (d >= p.first_short) {
+            const uint32_t s = s_reo[d], sw = s_sfbw_s[s], sfb = sw & 15u, win = sw >> 4;
+            const uint32_t sc = sfb < 12 ? sc8[P3_SCF_S_OFF + 3 * sfb + win] : 0u;
+            r = fq_requant(T->pow43, isp[s], p.mult * sc, p.gg - (int)p.sbg8[win]);
+          } else {
+            const uint32_t sfb = s_sfb_l[d];
+            const uint32_t sc = sfb < 21 ? sc8[sfb] + p.pre * T->pretab[sfb] : 0u;
+            r = fq_requant(T->pow43, isp[d], p.mult * sc, p.gg);
+          }
+          xs[gcl][d] = r;
         }
       }
-      xs[gcl][d] = r;
     }
     __syncthreads();
 
     /* ---- B: stereo (pdmp3.c:1916-1971), both granules ---- */
     if (nch == 2 && fr.mode == 1 && fr.mode_ext != 0) {
-      for (int e = tid; e < 2 * 576; e += FT) {
-        const uint32_t gr = e / 576, i = e % 576;
-        const p3_gc g0 = gcs[4 * f + 2 * gr];
-        const uint32_t cl = (uint32_t)s_c1[2 * gr], c1r = (uint32_t)s_c1[2 * gr + 1];
+      #pragma unroll 1
+      for (int gr = 0; gr < 2; gr++) {
+        const uint32_t cl = (uint32_t)s_par[2 * gr].c1, c1r = (uint32_t)s_par[2 * gr + 1].c1;
         const uint32_t msn = (fr.mode_ext & 2) ? (cl > c1r ? c1r : cl) : 0u;
-        const bool sh0 = P3_GC_WINSW(g0) && P3_GC_BTYPE(g0) == 2;
-        const uint32_t first_short0 = sh0 ? (P3_GC_MIXED(g0) ? 36u : 0u) : 576u;
-        float l = xs[2 * gr][i], r = xs[2 * gr + 1][i];
-        if (i < msn) {
-          float a = __fadd_rn(l, r), b = __fsub_rn(l, r);
-          l = __double2float_rn(__dmul_rn((double)a, 0.70710678118654752440));
-          r = __double2float_rn(__dmul_rn((double)b, 0.70710678118654752440));
-        } else if (fr.mode_ext & 1) {
-          if (i >= first_short0) {
-            const uint32_t sw = s_sfbw_s[i], sfb = sw & 15u, win = sw >> 4;
-            if (sfb < 12 && 3u * T->sfb_s[fr.sfreq][sfb] >= c1r && s_scf[2 * gr][P3_SCF_S_OFF + 3 * sfb + win] != 7) {
-              float x = (float)(unsigned)(long long)l; l = x; r = x;             /* Q4 */
-            }
-          } else {
-            const uint32_t sfb = s_sfb_l[i], lim = sh0 ? 8u : 21u;
-            if (sfb < lim && T->sfb_l[fr.sfreq][sfb] >= c1r) {
-              const uint32_t p = s_scf[2 * gr][sfb];
-              if (p != 7) { float x = l; l = __fmul_rn(FC.is_l[p & 7], x); r = __fmul_rn(FC.is_r[p & 7], x); }
+        const uint32_t first_short0 = s_par[2 * gr].first_short;
+        const bool sh0 = first_short0 < 576;
+        const bool is_on = fr.mode_ext & 1;
+        #pragma unroll
+        for (int it = 0; it < 5; it++) {
+          const uint32_t i = tid + FT * it;
+          if (i >= 576) break;
+          float l = xs[2 * gr][i], r = xs[2 * gr + 1][i];
+          if (i < msn) {
+            float a = __fadd_rn(l, r), b = __fsub_rn(l, r);
+            l = __double2float_rn(__dmul_rn((double)a, 0.70710678118654752440));
+            r = __double2float_rn(__dmul_rn((double)b, 0.70710678118654752440));
+            xs[2 * gr][i] = l; xs[2 * gr + 1][i] = r;
+          } else if (is_on) {
+            if (i >= first_short0) {
+              const uint32_t sw = s_sfbw_s[i], sfb = sw & 15u, win = sw >> 4;
+              if (sfb < 12 && 3u * T->sfb_s[fr.sfreq][sfb] >= c1r && s_scf[2 * gr][P3_SCF_S_OFF + 3 * sfb + win] != 7) {
+                float x = (float)(unsigned)(long long)l;                               /* Q4 */
+                xs[2 * gr][i] = x; xs[2 * gr + 1][i] = x;
+              }
+            } else {
+              const uint32_t sfb = s_sfb_l[i], lim = sh0 ? 8u : 21u;
+              if (sfb < lim && T->sfb_l[fr.sfreq][sfb] >= c1r) {
+                const uint32_t pp = s_scf[2 * gr][sfb];
+                if (pp != 7) { xs[2 * gr][i] = __fmul_rn(FC.is_l[pp & 7], l); xs[2 * gr + 1][i] = __fmul_rn(FC.is_r[pp & 7], l); }
+              }
             }
           }
         }
-        xs[2 * gr][i] = l; xs[2 * gr + 1][i] = r;
       }
       __syncthreads();
     }
 
-    /* ---- C: antialias (pdmp3.c:1706-1732) ---- */
-    for (int e = tid; e < 4 * 248; e += FT) {
-      const uint32_t gcl = e / 248, t = e % 248, sb = 1 + (t >> 3), i = t & 7;
-      if ((gcl & 1) < nch) {
-        const p3_gc g = gcs[4 * f + gcl];
-        const bool sh = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
-        const uint32_t sblim = sh ? (P3_GC_MIXED(g) ? 2u : 1u) : 32u;
+    /* ---- C: antialias (pdmp3.c:1706-1732): 31 boundaries x 8 butterflies per granule-channel ---- */
+    #pragma unroll 1
+    for (int gcl = 0; gcl < 4; gcl++) {
+      const uint32_t sblim = s_par[gcl].live ? s_par[gcl].sblim : 0;
+      #pragma unroll
+      for (int it = 0; it < 2; it++) {
+        const uint32_t t = tid + FT * it, sb = 1 + (t >> 3), i = t & 7;
         if (sb < sblim) {
           const uint32_t li = 18 * sb - 1 - i, ui = 18 * sb + i;
           const float a = xs[gcl][li], b = xs[gcl][ui];
@@ -219,9 +270,9 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
     /* ---- D: IMDCT + window; first half in place, second half to the tail buffer ---- */
     {
       const uint32_t gcl = tid >> 5, sb = tid & 31, gr = gcl >> 1, ch = gcl & 1;
-      if (ch < nch) {
-        const p3_gc g = gcs[4 * f + gcl];
-        const uint32_t bt = (P3_GC_WINSW(g) && P3_GC_MIXED(g) && sb < 2) ? 0u : P3_GC_BTYPE(g);
+      const gcpar p = s_par[gcl];
+      if (p.live) {
+        const uint32_t bt = (p.ws && p.mixed && sb < 2) ? 0u : p.bt;
         float *x = &xs[gcl][18 * sb];
         float *tl = &tails[gr == 0 ? 0 : 1 + (n & 1)][ch][18 * sb];
         float in[18];
@@ -240,15 +291,15 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
           /* three 12-point transforms (pdmp3.c:1673-1686): raw[6w+6+p] += win2[p] * sum_m in[w+3m] cos12[m][p] */
           float raw[36];
           #pragma unroll
-          for (int p = 0; p < 36; p++) raw[p] = 0.0f;
+          for (int q = 0; q < 36; q++) raw[q] = 0.0f;
           #pragma unroll
           for (int w = 0; w < 3; w++)
             #pragma unroll
-            for (int p = 0; p < 12; p++) {
+            for (int q = 0; q < 12; q++) {
               float sum = 0.0f;
               #pragma unroll
-              for (int m = 0; m < 6; m++) sum = fmaf(in[w + 3 * m], FC.cos12[m][p], sum);
-              raw[6 * w + 6 + p] += sum * FC.win[2][p];
+              for (int m = 0; m < 6; m++) sum = fmaf(in[w + 3 * m], FC.cos12[m][q], sum);
+              raw[6 * w + 6 + q] += sum * FC.win[2][q];
             }
           #pragma unroll
           for (int i = 0; i < 18; i++) { x[i] = raw[i]; tl[i] = raw[18 + i]; }
@@ -274,7 +325,7 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
           for (int sb = 0; sb < 32; sb++) y_tap[(o0 + 2 * gr + ch) * 576 + ss * 32 + sb] = s[sb];
         }
         dct2<32>(s);
-        float *X = &xring[ch][(15 + n * 36 + gr * 18 + ss) & (XSLOTS - 1)][0];
+        float *X = &xring[ch][ring_slot(15 + n * 36 + gr * 18 + ss)][0];
         #pragma unroll
         for (int k = 0; k < 32; k++) X[k] = s[k];
       }
@@ -284,28 +335,32 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
     /* ---- F: 512-tap window from registers + PCM ---- */
     if (wch < (int)nch && emit) {
       const int t0 = 15 + n * 36 + wgr * 18;                               /* ring slot of this granule's first time slot */
-      float A[33], B[33];                                                  /* A[i] = X(t0-15+i)[ia], B[i] = X(t0-15+i)[ib] */
-      #pragma unroll
-      for (int i = 0; i < 33; i++) { const float *X = &xring[wch][(t0 - 15 + i) & (XSLOTS - 1)][0]; A[i] = X[ia]; B[i] = X[ib]; }
       const int64_t base = ((int64_t)fr.pcm_index * 1152 + wgr * 576 + j) * nch + wch;
       #pragma unroll
-      for (int ss = 0; ss < 18; ss++) {
-        float sum = 0.0f;
+      for (int h = 0; h < 2; h++) {                                        /* two runs of 9 slots keep the history in 48 registers */
+        float A[24], B[24];                                                /* A[i] = X(t0-15+9h+i)[ia], B[i] = X(t0-15+9h+i)[ib] */
+        int rs = ring_slot(t0 - 15 + 9 * h);
         #pragma unroll
-        for (int k = 0; k < 8; k++) { sum = fmaf(ce[k], A[15 + ss - 2 * k], sum); sum = fmaf(co[k], B[15 + ss - 2 * k - 1], sum); }
-        const double d = __dmul_rn((double)sum, 32767.0);
-        int32_t s = (d > -2147483649.0 && d < 2147483648.0) ? __double2int_rz(d) : (int32_t)0x80000000;
-        s = s > 32767 ? 32767 : (s < -32767 ? -32767 : s);
-        pcm[base + (int64_t)ss * 32 * nch] = (int16_t)s;
+        for (int i = 0; i < 24; i++) { const float *X = &xring[wch][rs][0]; A[i] = X[ia]; B[i] = X[ib]; rs = rs + 1 == XSLOTS ? 0 : rs + 1; }
+        #pragma unroll
+        for (int s9 = 0; s9 < 9; s9++) {
+          float sum = 0.0f;
+          #pragma unroll
+          for (int k = 0; k < 8; k++) { sum = fmaf(ce[k], A[15 + s9 - 2 * k], sum); sum = fmaf(co[k], B[15 + s9 - 2 * k - 1], sum); }
+          /* (int32)(sum*32767.0) with the scale folded into the window; x86 gives INT_MIN out of range */
+          int32_t s = fabsf(sum) < 2147483648.0f ? __float2int_rz(sum) : (int32_t)0x80000000;
+          s = max(-32767, min(32767, s));
+          pcm[base + (int64_t)(9 * h + s9) * 32 * nch] = (int16_t)s;
+        }
       }
     }
-    /* next iteration's first __syncthreads() orders F's ring reads against E's writes */
+    /* the first __syncthreads() of the next iteration orders F's ring reads against E's writes */
   }
   __syncthreads();
   if (c1 == f_end) {                                       /* leave the state for the next launch */
     const int last = n - 1;
     for (int i = tid; i < 2 * 576; i += FT) st_out->store[i / 576][i % 576] = tails[1 + (last & 1)][i / 576][i % 576];
     const int tl = 15 + last * 36 + 35;
-    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, age = r / 32, k = r % 32; st_out->xhist[ch][age][k] = xring[ch][(tl - age) & (XSLOTS - 1)][k]; }
+    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, age = r / 32, k = r % 32; st_out->xhist[ch][age][k] = xring[ch][ring_slot(tl - age)][k]; }
   }
 }
