@@ -106,7 +106,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=1000000, help="frames per GPU per step")
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--mode", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--mode", default="fast", choices=["exact", "fast"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
@@ -197,7 +197,7 @@ def main():
         hin = torch.empty(raw_bytes, dtype=torch.uint8).pin_memory(); hin.numpy()[:] = stream
         out_bytes = (parsed.n_frames) * 4608
         hout = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
-        dec = pdmp3_b200.Decoder("b200:ring=%d,device=%d" % (raw_bytes + 4096, local))
+        dec = pdmp3_b200.Decoder("b200:ring=%d,device=%d,mode=%s" % (raw_bytes + 4096, local, a.mode))
         times = []
         for it in range(2 + a.steps):
             dec.open_feed()

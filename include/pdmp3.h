@@ -6,10 +6,12 @@
  *
  * Extension that stays inside the reference's signature: pdmp3_new()'s `decoder` string,
  * which the reference ignores (pdmp3.c:2351-2353), selects options, e.g.
- *     pdmp3_new("b200:ring=1073741824,device=0", &err)
+ *     pdmp3_new("b200:ring=1073741824,device=0,mode=exact", &err)
  * `ring` = capacity of the input buffer in bytes (default 16384 = INBUF_SIZE, pdmp3.c:123,
  * which reproduces the reference's PDMP3_NO_SPACE behaviour exactly).  A large ring lets one
  * pdmp3_feed()+pdmp3_read() pair push a whole stream through the GPU in one batch.
+ * `mode` = fast (default: fused kernel with fast transforms, PCM within 1 LSB of the reference) or
+ * exact (direct-form transforms in the reference's summation order, PCM bit-identical).
  */
 #ifndef PDMP3_H
 #define PDMP3_H

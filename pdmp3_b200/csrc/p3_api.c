@@ -34,7 +34,7 @@ struct pdmp3_handle {
   int16_t *pcm;                                     /* one frame: the partially delivered frame */
   size_t pend_pos, pend_end;                        /* undelivered PCM bytes of it: [pend_pos,pend_end) */
   int in_pinned;
-  p3_ctx *ctx; int device; int ctx_failed;
+  p3_ctx *ctx; int device; int ctx_failed; int mode;
   p3_parse_state ps;
   int new_header;                                   /* 0 none yet, 1 seen, -1 reported (pdmp3.c:1318,2470,2531) */
   int nch, sfreq;
@@ -47,11 +47,12 @@ pdmp3_handle *pdmp3_new(const char *decoder, int *error)
 {
   pdmp3_handle *id = (pdmp3_handle *)calloc(1, sizeof *id);
   if (!id) { if (error) *error = PDMP3_ERR; return NULL; }
-  id->cap = P3_DEFAULT_RING; id->device = 0;
+  id->cap = P3_DEFAULT_RING; id->device = 0; id->mode = P3_MODE_FAST;
   if (decoder) {                                    /* "b200:ring=<bytes>,device=<n>" */
     const char *p;
     if ((p = strstr(decoder, "ring="))) { unsigned long long v = strtoull(p + 5, NULL, 10); if (v >= 4096) id->cap = (size_t)v; }
     if ((p = strstr(decoder, "device="))) id->device = atoi(p + 7);
+    if (strstr(decoder, "mode=exact")) id->mode = P3_MODE_EXACT;   /* bit-identical PCM; default is FAST (<= 1 LSB) */
   }
   if (id->cap > (1u << 20)) { id->in = (unsigned char *)p3_host_alloc(id->cap); id->in_pinned = id->in != NULL; }   /* page-locked: full-speed H2D */
   if (!id->in) id->in = (unsigned char *)malloc(id->cap);
@@ -105,6 +106,7 @@ static int ensure_ctx(pdmp3_handle *id)
     id->ctx_failed = 1; id->ctx = NULL;
     return PDMP3_ERR;
   }
+  p3_ctx_set_mode(id->ctx, id->mode);
   return PDMP3_OK;
 }
 

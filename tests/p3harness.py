@@ -130,11 +130,11 @@ def parse(stream, lookahead=1152, max_frames=0, warmup=0, nthreads=1, lib=None):
     lib.p3_parsed_free(C.byref(out))
     return fr, gc, info
 
-def oracle_decode(stream, lookahead=1152, taps=True):
+def oracle_decode(stream, lookahead=1152, taps=True, warmup=0):
     """Parse with the product parser, decode with the oracle restatement."""
     lib = oracle_lib()
     stream = np.ascontiguousarray(stream, dtype=np.uint8)
-    fr, gc, info = parse(stream, lookahead)
+    fr, gc, info = parse(stream, lookahead, warmup=warmup)
     n = info["n_frames"]; nch = int(fr["nch"][0]) if n else 2
     shapes = dict(is_huff=((n, 2, 2, 576), np.int16), count1=((n, 2, 2), np.int32), scf_l=((n, 2, 2, 21), np.uint8),
                   scf_s=((n, 2, 2, 12, 3), np.uint8), xr_req=((n, 2, 2, 576), np.float32), xr_reo=((n, 2, 2, 576), np.float32),
