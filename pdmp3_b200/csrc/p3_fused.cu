@@ -26,6 +26,7 @@ struct p3_fconst {
   float cs[8], ca[8], is_l[8], is_r[8];
   float t1h[40];
   float t2[320];
+  float pretab[24];
 };
 __constant__ p3_fconst FC;
 
@@ -36,6 +37,7 @@ extern "C" int p3_fused_upload_consts(const p3_tables *T, const float *dct4)
   memcpy(h.win, T->imdct_win, sizeof h.win); memcpy(h.cos12, T->cos12, sizeof h.cos12);
   memcpy(h.cs, T->cs, 32); memcpy(h.ca, T->ca, 32); memcpy(h.is_l, T->is_l, 32); memcpy(h.is_r, T->is_r, 32);
   memcpy(h.t1h, T->t1h, sizeof h.t1h); memcpy(h.t2, T->t2, sizeof h.t2);
+  for (int i = 0; i < 24; i++) h.pretab[i] = (float)T->pretab[i];
   return (int)cudaMemcpyToSymbol(FC, &h, sizeof h);
 }
 
@@ -57,9 +59,50 @@ template <int N> __device__ __forceinline__ void dct2(float (&x)[N])
   }
 }
 
+
+/* ---- 18-point DCT-IV via two 9-point DCT-IIs (tools/proto/fast_transforms.py) -------------------
+ * y[m] = x[m] * 2cos(pi(2m+1)/72);  Y = DCT-II-18(y) by one Lee split into two DCT-II-9;
+ * t[0] = Y[0]/2, t[k] = Y[k] - t[k-1].   ~125 flops instead of 324. */
+__device__ __forceinline__ void dct9(const float (&x)[9], float (&X)[9])
+{
+  constexpr float C10 = 9.848077530e-01f, C20 = 9.396926208e-01f, C30 = 8.660254038e-01f, C40 = 7.660444431e-01f, C50 = 6.427876097e-01f, C70 = 3.420201433e-01f, C80 = 1.736481777e-01f;
+  const float s0 = x[0] + x[8], s1 = x[1] + x[7], s2 = x[2] + x[6], s3 = x[3] + x[5], x4 = x[4];
+  const float d0 = x[0] - x[8], d1 = x[1] - x[7], d2 = x[2] - x[6], d3 = x[3] - x[5];
+  const float h1 = 0.5f * s1;
+  X[0] = (s0 + s1) + (s2 + s3) + x4;
+  X[2] = fmaf(s0, C20, fmaf(-s2, C80, fmaf(-s3, C40, h1 - x4)));
+  X[4] = fmaf(s0, C40, fmaf(-s2, C20, fmaf(s3, C80, x4 - h1)));
+  X[6] = fmaf(s0 + s2 + s3, 0.5f, -(s1 + x4));
+  X[8] = fmaf(s0, C80, fmaf(s2, C40, fmaf(-s3, C20, x4 - h1)));
+  const float e1 = d1 * C30;
+  X[1] = fmaf(d0, C10, fmaf(d2, C50, fmaf(d3, C70, e1)));
+  X[3] = (d0 - d2 - d3) * C30;
+  X[5] = fmaf(d0, C50, fmaf(-d2, C70, fmaf(d3, C10, -e1)));
+  X[7] = fmaf(d0, C70, fmaf(d2, C10, fmaf(-d3, C50, -e1)));
+}
+
+__device__ __forceinline__ void dct4_18(const float (&x)[18], float (&t)[18])
+{
+  constexpr float PRE[18] = {1.998096443e+00f, 1.982889723e+00f, 1.952592014e+00f, 1.907433901e+00f, 1.847759065e+00f, 1.774021666e+00f, 1.686782892e+00f, 1.586706681e+00f, 1.474554674e+00f, 1.351180415e+00f, 1.217522858e+00f, 1.074599217e+00f, 9.234972265e-01f, 7.653668647e-01f, 6.014115990e-01f, 4.328792279e-01f, 2.610523844e-01f, 8.723877473e-02f};
+  constexpr float LEE[9] = {5.019099188e-01f, 5.176380902e-01f, 5.516889595e-01f, 6.103872944e-01f, 7.071067812e-01f, 8.717233978e-01f, 1.183100792e+00f, 1.931851653e+00f, 5.736856623e+00f};
+  float a[9], b[9], A[9], B[9];
+  #pragma unroll
+  for (int m = 0; m < 9; m++) {
+    const float u = x[m] * PRE[m], v = x[17 - m] * PRE[17 - m];
+    a[m] = u + v; b[m] = (u - v) * LEE[m];
+  }
+  dct9(a, A); dct9(b, B);
+  t[0] = 0.5f * A[0];
+  #pragma unroll
+  for (int k = 1; k < 18; k++) {
+    const float Y = (k & 1) ? (k == 17 ? B[8] : B[k >> 1] + B[(k >> 1) + 1]) : A[k >> 1];
+    t[k] = Y - t[k - 1];
+  }
+}
+
 #define FT 128                     /* threads per CTA */
 #define XPITCH 33
-#define XSLOTS 52                  /* >= 15 history + 36 new slots; 52*33 floats per channel */
+#define XSLOTS 51                  /* 15 history slots + the 36 slots of one frame, linear */
 
 /* per granule-channel parameters, unpacked once per frame by threads 0..3 */
 struct gcpar {
@@ -71,14 +114,13 @@ struct gcpar {
   uint8_t  sblim;                  /* antialias subband limit */
 };
 
-__device__ __forceinline__ float fq_requant(const float *__restrict__ pow43, int v, uint32_t e2, int q)
+/* |is|^(4/3) with the sign, times the band scale: (t1*t2)*t3 with both products rounded (pdmp3.c:2132,2150) */
+__device__ __forceinline__ float fq_requant(const float *__restrict__ pow43, int v, float scale)
 {
   float t3 = __ldg(pow43 + (v < 0 ? -v : v));
   if (v < 0) t3 = -t3;
-  return __fmul_rn(__fmul_rn(FC.t1h[e2], FC.t2[q + P3_T2_BIAS]), t3);
+  return __fmul_rn(scale, t3);
 }
-
-__device__ __forceinline__ int ring_slot(int s) { return s % XSLOTS; }
 
 extern "C" __global__ void __launch_bounds__(FT, 5)
 k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
@@ -95,6 +137,7 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   __shared__ uint16_t s_reo[576];
   __shared__ __align__(16) uint8_t s_scf[4][P3_SCF_STRIDE];
   __shared__ gcpar s_par[4];
+  __shared__ float s_scale[4][40];                       /* fl(t1*t2) per scalefactor band: long sfb 0..21, short 3*sfb+win */
   __shared__ uint32_t s_sfreq;
 
   const int tid = threadIdx.x;
@@ -124,7 +167,7 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   for (int i = tid; i < 2 * XSLOTS * XPITCH; i += FT) (&xring[0][0][0])[i] = 0.0f;
   __syncthreads();
   if (!warm)
-    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, s = r / 32, k = r % 32; xring[ch][s][k] = st_in->xhist[ch][14 - s][k]; }
+    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, s = r / 32, k = r % 32; xring[ch][36 + s][k] = st_in->xhist[ch][14 - s][k]; }
   if (tid == 0) s_sfreq = 0xffffffffu;
 
   /* software pipeline: the spectra of frame n+1 are fetched into registers while frame n is processed */
@@ -148,6 +191,8 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       for (int i = tid; i < 576; i += FT) { s_sfb_l[i] = T->line_sfb_l[fr.sfreq][i]; s_sfbw_s[i] = T->line_sfbw_s[fr.sfreq][i]; s_reo[i] = T->reorder_src[fr.sfreq][i]; }
       if (tid == 0) s_sfreq = fr.sfreq;
     }
+    /* the last 15 slots of the previous frame become the history of this one */
+    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, sl = r >> 5, k = r & 31; xring[ch][sl][k] = xring[ch][36 + sl][k]; }
     /* land the prefetched spectra / scalefactors in shared memory, start the next fetch */
     {
       uint32_t *ib32 = reinterpret_cast<uint32_t *>(&isbuf[0][0]);
@@ -182,6 +227,26 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       s_par[tid] = p;
     }
     __syncthreads();
+    /* band scales fl(t1*t2): 2^(-(scale?1:0.5)*(scalefac+preflag*pretab)) * 2^((gain-210-8*sbg)/4) (pdmp3.c:2127-2128,2144-2146).
+     * long blocks: index = sfb (0..21); short: 3*sfb+win; mixed: long bands 0..7 sit in the unused short slots 0..7 */
+    for (int e = tid; e < 4 * 40; e += FT) {
+      const int gcl = e / 40, b = e % 40;
+      const gcpar p = s_par[gcl];
+      float v = 0.0f;
+      if (p.live) {
+        const bool longband = p.first_short == 576 ? b < 22 : (p.first_short == 36 && b < 8);
+        if (longband) {
+          const uint32_t sc = b < 21 ? s_scf[gcl][b] + p.pre * (uint32_t)FC.pretab[b] : 0u;
+          v = __fmul_rn(FC.t1h[p.mult * sc], FC.t2[p.gg + P3_T2_BIAS]);
+        } else if (p.first_short < 576 && b < 39) {
+          const int sfb = b / 3, win = b % 3;
+          const uint32_t sc = sfb < 12 ? s_scf[gcl][P3_SCF_S_OFF + 3 * sfb + win] : 0u;
+          v = __fmul_rn(FC.t1h[p.mult * sc], FC.t2[p.gg - (int)p.sbg8[win] + P3_T2_BIAS]);
+        }
+      }
+      s_scale[gcl][b] = v;
+    }
+    __syncthreads();
 
     /* ---- A: requantize + reorder (exact arithmetic of pdmp3.c:2121-2152) ---- */
     #pragma unroll 1
@@ -189,21 +254,16 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       const gcpar p = s_par[gcl];
       if (!p.live) { for (int d = tid; d < 576; d += FT) xs[gcl][d] = 0.0f; continue; }
       const int16_t *isp = isbuf[gcl];
-      const uint8_t *sc8 = s_scf[gcl];
+      const float *scl = s_scale[gcl];
       #pragma unroll
       for (int it = 0; it < 5; it++) {
         const int d = tid + FT * it;
         if (d < 576) {
           float r;
           if (d >= p.first_short) {
-            const uint32_t s = s_reo[d], sw = s_sfbw_s[s], sfb = sw & 15u, win = sw >> 4;
-            const uint32_t sc = sfb < 12 ? sc8[P3_SCF_S_OFF + 3 * sfb + win] : 0u;
-            r = fq_requant(T->pow43, isp[s], p.mult * sc, p.gg - (int)p.sbg8[win]);
-          } else {
-            const uint32_t sfb = s_sfb_l[d];
-            const uint32_t sc = sfb < 21 ? sc8[sfb] + p.pre * T->pretab[sfb] : 0u;
-            r = fq_requant(T->pow43, isp[d], p.mult * sc, p.gg);
-          }
+            const uint32_t s = s_reo[d], sw = s_sfbw_s[s];
+            r = fq_requant(T->pow43, isp[s], scl[3 * (sw & 15u) + (sw >> 4)]);
+          } else r = fq_requant(T->pow43, isp[d], scl[s_sfb_l[d]]);
           xs[gcl][d] = r;
         }
       }
@@ -279,13 +339,12 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
         #pragma unroll
         for (int m = 0; m < 18; m++) in[m] = x[m];
         if (bt != 2) {
+          float t[18];
+          dct4_18(in, t);
           #pragma unroll
-          for (int k = 0; k < 18; k++) {
-            float t = 0.0f;
-            #pragma unroll
-            for (int m = 0; m < 18; m++) t = fmaf(in[m], FC.dct4[k][m], t);
-            if (k < 9) { tl[8 - k] = -t * FC.win[bt][26 - k]; tl[9 + k] = -t * FC.win[bt][27 + k]; }
-            else { x[k - 9] = t * FC.win[bt][k - 9]; x[26 - k] = -t * FC.win[bt][26 - k]; }
+          for (int k = 0; k < 9; k++) {                                    /* 36-point IMDCT from the DCT-IV by symmetry */
+            tl[8 - k] = -t[k] * FC.win[bt][26 - k]; tl[9 + k] = -t[k] * FC.win[bt][27 + k];
+            x[k] = t[9 + k] * FC.win[bt][k]; x[17 - k] = -t[9 + k] * FC.win[bt][17 - k];
           }
         } else {
           /* three 12-point transforms (pdmp3.c:1673-1686): raw[6w+6+p] += win2[p] * sum_m in[w+3m] cos12[m][p] */
@@ -325,7 +384,7 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
           for (int sb = 0; sb < 32; sb++) y_tap[(o0 + 2 * gr + ch) * 576 + ss * 32 + sb] = s[sb];
         }
         dct2<32>(s);
-        float *X = &xring[ch][ring_slot(15 + n * 36 + gr * 18 + ss)][0];
+        float *X = &xring[ch][15 + gr * 18 + ss][0];
         #pragma unroll
         for (int k = 0; k < 32; k++) X[k] = s[k];
       }
@@ -334,14 +393,13 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
 
     /* ---- F: 512-tap window from registers + PCM ---- */
     if (wch < (int)nch && emit) {
-      const int t0 = 15 + n * 36 + wgr * 18;                               /* ring slot of this granule's first time slot */
       const int64_t base = ((int64_t)fr.pcm_index * 1152 + wgr * 576 + j) * nch + wch;
       #pragma unroll
       for (int h = 0; h < 2; h++) {                                        /* two runs of 9 slots keep the history in 48 registers */
-        float A[24], B[24];                                                /* A[i] = X(t0-15+9h+i)[ia], B[i] = X(t0-15+9h+i)[ib] */
-        int rs = ring_slot(t0 - 15 + 9 * h);
+        float A[24], B[24];                                                /* A[i] = X(first-15+9h+i)[ia], B likewise with ib */
+        const float *X0 = &xring[wch][wgr * 18 + 9 * h][0];
         #pragma unroll
-        for (int i = 0; i < 24; i++) { const float *X = &xring[wch][rs][0]; A[i] = X[ia]; B[i] = X[ib]; rs = rs + 1 == XSLOTS ? 0 : rs + 1; }
+        for (int i = 0; i < 24; i++) { A[i] = X0[i * XPITCH + ia]; B[i] = X0[i * XPITCH + ib]; }
         #pragma unroll
         for (int s9 = 0; s9 < 9; s9++) {
           float sum = 0.0f;
@@ -360,7 +418,7 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   if (c1 == f_end) {                                       /* leave the state for the next launch */
     const int last = n - 1;
     for (int i = tid; i < 2 * 576; i += FT) st_out->store[i / 576][i % 576] = tails[1 + (last & 1)][i / 576][i % 576];
-    const int tl = 15 + last * 36 + 35;
-    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, age = r / 32, k = r % 32; st_out->xhist[ch][age][k] = xring[ch][ring_slot(tl - age)][k]; }
+    (void)last;
+    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, age = r / 32, k = r % 32; st_out->xhist[ch][age][k] = xring[ch][50 - age][k]; }
   }
 }

@@ -25,11 +25,37 @@
  * stream into shared memory as big-endian words -- the "bit reservoir" of Get_Main_Data
  * (pdmp3.c:1096-1122) for the whole group at once; header and side-info bytes never reach smem.
  * ============================================================================================= */
-/* one Huffman-coded pair at bit position `pos` (pdmp3.c:1593-1643); tb = base | pbits<<16 | linbits<<24 */
-__device__ __forceinline__ uint32_t k1_pair(const uint32_t *sw, const uint16_t *lut, uint32_t &pos, uint32_t tb)
+/* MSB-first bit buffer in two registers over the big-endian words in shared memory.  `hi:lo` hold
+ * the next `nb` bits left-aligned and always end on a word boundary, so a refill is one aligned
+ * word load that is off the critical path of the symbol chain (pdmp3.c:1489-1527 does a byte
+ * access per BIT). */
+struct k1_bits {
+  const uint32_t *sw; uint32_t hi, lo, nb, widx;
+  __device__ __forceinline__ void init(const uint32_t *s, uint32_t bitpos)
+  {
+    sw = s; widx = (bitpos >> 5) + 2;
+    const uint32_t a = s[bitpos >> 5], b = s[(bitpos >> 5) + 1], sh = bitpos & 31;
+    hi = __funnelshift_l(b, a, sh); lo = b << sh; nb = 64 - sh;
+  }
+  __device__ __forceinline__ uint32_t pos() const { return widx * 32 - nb; }      /* absolute bit position */
+  __device__ __forceinline__ void skip(uint32_t n)                                /* n <= 32 */
+  {
+    hi = __funnelshift_l(lo, hi, n); lo = n >= 32 ? 0u : lo << n; nb -= n;
+    if (nb <= 32) {                                                               /* one whole word fits */
+      const uint32_t w = sw[widx++];
+      hi |= nb == 32 ? 0u : (nb == 0 ? w : w >> nb);
+      lo = nb == 0 ? 0u : w << (32 - nb);
+      if (nb == 32) lo = w;
+      nb += 32;
+    }
+  }
+};
+
+/* one Huffman-coded pair (pdmp3.c:1593-1643); tb = base | pbits<<16 | linbits<<24 */
+__device__ __forceinline__ uint32_t k1_pair(k1_bits &bb, const uint16_t *lut, uint32_t tb)
 {
   const uint32_t base = tb & 0xffffu, linbits = (tb >> 24) & 31u;
-  uint32_t w = p3_peek32(sw, pos);
+  uint32_t w = bb.hi;                                   /* >= 33 valid bits: the longest code has 19 */
   uint32_t cw = (tb >> 16) & 31u, used = 0;
   uint32_t e = lut[base + (w >> (32 - cw))];
   while (e & 0x8000u) {                                 /* next LUT level (codes longer than 8 bits) */
@@ -38,15 +64,14 @@ __device__ __forceinline__ uint32_t k1_pair(const uint32_t *sw, const uint16_t *
   }
   used += (e >> 8) & 31;
   int x = (e >> 4) & 15, y = e & 15;
-  pos += used;
-  if (linbits) w = p3_peek32(sw, pos);                  /* room for 2 x (13 linbits + sign) */
-  else w <<= used;                                      /* w: next unread bit at the MSB */
+  bb.skip(used);
+  w = bb.hi;                                            /* >= 33 valid bits: 2 x (13 linbits + sign) = 28 */
   uint32_t u2 = 0;
   if (linbits && x == 15) { x += (int)(w >> (32 - linbits)); w <<= linbits; u2 += linbits; }
   if (x) { if (w >> 31) x = -x; w <<= 1; u2++; }
   if (linbits && y == 15) { y += (int)(w >> (32 - linbits)); w <<= linbits; u2 += linbits; }
   if (y) { if (w >> 31) y = -y; u2++; }
-  pos += u2;
+  bb.skip(u2);
   return (uint32_t)(x & 0xffff) | ((uint32_t)y << 16);
 }
 
@@ -199,24 +224,26 @@ k_huffman(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames, 
       /* one loop over all big_values pairs; the table changes at the region boundaries, so every lane of
        * the warp stays in the same loop whatever its region split */
       uint32_t tb = tbs[0];
+      k1_bits bb; bb.init(sw, pos);
       for (uint32_t i = 0; i < bv2; i += 2) {
         if (i == r1s) tb = tbs[1];
         if (i == r2s) tb = tbs[2];
-        ob.put(tb == 0xffffffffu ? 0u : k1_pair(sw, lut, pos, tb));       /* empty tables: zeros, no bits (pdmp3.c:1599-1602) */
+        ob.put(tb == 0xffffffffu ? 0u : k1_pair(bb, lut, tb));            /* empty tables: zeros, no bits (pdmp3.c:1599-1602) */
       }
       /* count1 quads (pdmp3.c:2091-2103) */
       uint32_t is_pos = bv2;
       const bool tabB = P3_GC_C1TAB(g);                  /* reference quirk Q1: table B = leaf 0011, no code bits */
       const uint32_t qbase = T->book_base[T->table_book[32]], qbits = T->book_pbits[T->table_book[32]];
+      pos = bb.pos();
       while (is_pos <= 572 && pos <= bit_pos_end) {
-        uint32_t w = p3_peek32(sw, pos), used = 0, leaf = 3;
+        uint32_t w = bb.hi, used = 0, leaf = 3;
         if (!tabB) { uint32_t e = lut[qbase + (w >> (32 - qbits))]; used = (e >> 8) & 31; leaf = e & 15; w <<= used; }
         int v = (leaf >> 3) & 1, ww = (leaf >> 2) & 1, x = (leaf >> 1) & 1, y = leaf & 1;
         if (v) { if (w >> 31) v = -1; w <<= 1; used++; }
         if (ww) { if (w >> 31) ww = -1; w <<= 1; used++; }
         if (x) { if (w >> 31) x = -1; w <<= 1; used++; }
         if (y) { if (w >> 31) y = -1; used++; }
-        pos += used;
+        bb.skip(used); pos += used;
         ob.put((uint32_t)(v & 0xffff) | ((uint32_t)ww << 16));
         ob.put((uint32_t)(x & 0xffff) | ((uint32_t)y << 16));
         is_pos += 4;

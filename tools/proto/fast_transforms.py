@@ -82,3 +82,52 @@ for t in range(15, T):
             acc += D[32 * k + j] * sg * X[t - k][ix]
         assert abs(ref - acc) < 1e-9
 print("fast transform algebra OK")
+
+# ---------- 18-point DCT-IV through two 9-point DCT-IIs (stage D of k_synth_fast) ----------
+def dct9(x):
+    c = lambda deg: np.cos(np.deg2rad(deg))
+    s0, s1, s2, s3, x4 = x[0] + x[8], x[1] + x[7], x[2] + x[6], x[3] + x[5], x[4]
+    d0, d1, d2, d3 = x[0] - x[8], x[1] - x[7], x[2] - x[6], x[3] - x[5]
+    X = np.empty(9)
+    X[0] = s0 + s1 + s2 + s3 + x4
+    X[2] = s0 * c(20) + s1 * 0.5 - s2 * c(80) - s3 * c(40) - x4
+    X[4] = s0 * c(40) - s1 * 0.5 - s2 * c(20) + s3 * c(80) + x4
+    X[6] = (s0 + s2 + s3) * 0.5 - s1 - x4
+    X[8] = s0 * c(80) - s1 * 0.5 + s2 * c(40) - s3 * c(20) + x4
+    X[1] = d0 * c(10) + d1 * c(30) + d2 * c(50) + d3 * c(70)
+    X[3] = (d0 - d2 - d3) * c(30)
+    X[5] = d0 * c(50) - d1 * c(30) - d2 * c(70) + d3 * c(10)
+    X[7] = d0 * c(70) - d1 * c(30) + d2 * c(10) - d3 * c(50)
+    return X
+
+x9 = np.random.randn(9)
+assert np.allclose(dct9(x9), dct2_direct(x9, 9), atol=1e-12)
+
+def dct4_18_fast(x):
+    m = np.arange(18)
+    y = x * 2 * np.cos(pi * (2 * m + 1) / 72)
+    a = y[:9] + y[::-1][:9]
+    b = (y[:9] - y[::-1][:9]) / (2 * np.cos(pi * (2 * np.arange(9) + 1) / 36))
+    A, B = dct9(a), dct9(b)
+    Y = np.empty(18); Y[0::2] = A; Y[1::2] = B + np.append(B[1:], 0.0)
+    t = np.empty(18); t[0] = Y[0] / 2
+    for k in range(1, 18): t[k] = Y[k] - t[k - 1]
+    return t
+
+x = np.random.randn(18)
+assert np.allclose(dct4_18(x), dct4_18_fast(x), atol=1e-10)
+# single precision error of the recursion, relative to the output scale
+xf = np.random.randn(2000, 18).astype(np.float32)
+def f32(v): return np.asarray(v, dtype=np.float32)
+err = 0
+for r in xf[:200]:
+    ref = dct4_18(r.astype(np.float64))
+    m = np.arange(18)
+    y = f32(r * f32(2 * np.cos(pi * (2 * m + 1) / 72)))
+    a = f32(y[:9] + y[::-1][:9]); b = f32(f32(y[:9] - y[::-1][:9]) * f32(1 / (2 * np.cos(pi * (2 * np.arange(9) + 1) / 36))))
+    A, B = f32(dct9(a.astype(np.float64))), f32(dct9(b.astype(np.float64)))
+    Y = np.empty(18, np.float32); Y[0::2] = A; Y[1::2] = f32(B + np.append(B[1:], np.float32(0)))
+    t = np.empty(18, np.float32); t[0] = Y[0] * np.float32(0.5)
+    for k in range(1, 18): t[k] = np.float32(Y[k] - t[k - 1])
+    err = max(err, np.abs(t - ref).max() / np.abs(ref).max())
+print("fast DCT-IV-18 OK; fp32 relative error (max over 200 vectors): %.2e" % err)
