@@ -191,7 +191,8 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       for (int i = tid; i < 576; i += FT) { s_sfb_l[i] = T->line_sfb_l[fr.sfreq][i]; s_sfbw_s[i] = T->line_sfbw_s[fr.sfreq][i]; s_reo[i] = T->reorder_src[fr.sfreq][i]; }
       if (tid == 0) s_sfreq = fr.sfreq;
     }
-    /* the last 15 slots of the previous frame become the history of this one */
+    /* the last 15 slots of the previous frame become the history of this one (stage F of that frame must be done) */
+    __syncthreads();
     for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, sl = r >> 5, k = r & 31; xring[ch][sl][k] = xring[ch][36 + sl][k]; }
     /* land the prefetched spectra / scalefactors in shared memory, start the next fetch */
     {
@@ -412,7 +413,6 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
         }
       }
     }
-    /* the first __syncthreads() of the next iteration orders F's ring reads against E's writes */
   }
   __syncthreads();
   if (c1 == f_end) {                                       /* leave the state for the next launch */
