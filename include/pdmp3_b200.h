@@ -132,6 +132,10 @@ typedef struct {
 int p3_decode_batch(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *batch,
                     int16_t *pcm, const p3_taps *host_taps);
 
+/* Asynchronous, double-buffered variant behind pdmp3_read(): enqueue upload, kernels and PCM download of
+ * one batch and return; takes ownership of *batch.  raw/pcm must stay valid until p3_batch_sync(). */
+int p3_decode_batch_async(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, p3_parsed *batch, int16_t *pcm);
+
 /* Device-resident variant used by the benchmark and the multi-GPU driver: upload once, run the
  * kernels any number of times, download once.  Pointers returned are DEVICE pointers. */
 int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *batch);

@@ -25,8 +25,10 @@
 #include <stdint.h>
 #include <fcntl.h>
 #include <unistd.h>
+#include <pthread.h>
 
 #define P3_DEFAULT_RING 16384u              /* INBUF_SIZE (pdmp3.c:123) */
+#define P3_API_CHUNK    32768               /* frames per GPU batch inside one pdmp3_read() */
 
 struct pdmp3_handle {
   unsigned char *in; size_t cap, istart, iend;      /* buffered bytes are in[istart,iend) */
@@ -84,6 +86,23 @@ int pdmp3_open_feed(pdmp3_handle *id)
 static size_t in_filled(const pdmp3_handle *id) { return id->iend - id->istart; }
 static size_t in_free(const pdmp3_handle *id) { return id->cap - in_filled(id); }
 
+/* large feeds are copied by a few threads (a single core moves ~10 GB/s, the PCIe link 50+) */
+typedef struct { unsigned char *d; const unsigned char *s; size_t n; } cpjob;
+static void *cp_worker(void *a) { cpjob *j = (cpjob *)a; memcpy(j->d, j->s, j->n); return NULL; }
+static void big_memcpy(unsigned char *d, const unsigned char *s, size_t n)
+{
+  enum { NT = 8 };
+  if (n < ((size_t)32 << 20)) { memcpy(d, s, n); return; }
+  pthread_t th[NT]; cpjob jb[NT]; int ok[NT];
+  for (int t = 0; t < NT; t++) {
+    size_t lo = n * t / NT, hi = n * (t + 1) / NT;
+    jb[t].d = d + lo; jb[t].s = s + lo; jb[t].n = hi - lo;
+    ok[t] = pthread_create(&th[t], NULL, cp_worker, &jb[t]) == 0;
+    if (!ok[t]) cp_worker(&jb[t]);
+  }
+  for (int t = 0; t < NT; t++) if (ok[t]) pthread_join(th[t], NULL);
+}
+
 int pdmp3_feed(pdmp3_handle *id, const unsigned char *in, size_t size)
 {
   if (!(id && in && size)) return PDMP3_ERR;
@@ -92,7 +111,7 @@ int pdmp3_feed(pdmp3_handle *id, const unsigned char *in, size_t size)
     memmove(id->in, id->in + id->istart, in_filled(id));
     id->iend -= id->istart; id->istart = 0;
   }
-  memcpy(id->in + id->iend, in, size);
+  big_memcpy(id->in + id->iend, in, size);
   id->iend += size;
   return PDMP3_OK;
 }
@@ -113,7 +132,7 @@ static int ensure_ctx(pdmp3_handle *id)
 int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_t *done)
 {
   if (!(id && outmemory && outsize && done)) return PDMP3_ERR;
-  int res = PDMP3_ERR;
+  int res = PDMP3_ERR, inflight = 0;
   *done = 0;
   if (id->pend_pos < id->pend_end) {                /* rest of a previously decoded frame (pdmp3.c:2437-2442) */
     size_t n = id->pend_end - id->pend_pos; if (n > outsize) n = outsize;
@@ -124,10 +143,14 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
   while (outsize) {
     if (in_filled(id) < 2 * 576) { res = PDMP3_NEED_MORE; break; }          /* pdmp3.c:2445,2466 */
     size_t fbytes = 1152 * sizeof(int16_t) * (size_t)(id->nch == 1 ? 1 : 2);
-    /* whole frames go straight into the caller's buffer; a trailing partial frame is decoded into
-     * the handle and handed out piecewise (the reference's ostart cursor, pdmp3.c:2317-2344) */
+    /* whole frames go straight into the caller's buffer, P3_API_CHUNK frames per GPU batch, the batches
+     * double-buffered (upload / kernels / download overlap, and so does the parsing of the next batch);
+     * a trailing partial frame is decoded into the handle and handed out piecewise (the reference's
+     * ostart cursor, pdmp3.c:2317-2344) */
     int direct = outsize >= fbytes;
-    p3_parse_opts po = {direct ? (int64_t)(outsize / fbytes) : 1, 2 * 576, 0, 0};
+    int64_t want = direct ? (int64_t)(outsize / fbytes) : 1;
+    if (want > P3_API_CHUNK) want = P3_API_CHUNK;
+    p3_parse_opts po = {want, 2 * 576, want >= 8192 ? 4 : 1, 0};
     p3_parse_state ps = id->ps;
     p3_parsed pb;
     if (p3_parse(id->in + id->istart, in_filled(id), &po, &ps, &pb) != P3_OK) { res = PDMP3_ERR; break; }
@@ -149,17 +172,19 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
       target = id->pcm;
     }
     for (int64_t f = 0; f < pb.n_frames; f++) pb.frames[f].pcm_index = (uint32_t)f;   /* slots restart at 0 for every batch */
-    if (p3_decode_batch(id->ctx, id->in + id->istart, in_filled(id), &pb, target, NULL) != P3_OK) {
-      fprintf(stderr, "pdmp3_b200: %s\n", p3_last_error());
-      p3_parsed_free(&pb); res = PDMP3_ERR; break;
-    }
+    int64_t nfr = pb.n_frames; uint64_t used = pb.consumed; int sf_last = pb.frames[pb.n_frames - 1].sfreq;
+    const uint64_t upl = in_filled(id) < used + 64 ? in_filled(id) : used + 64;   /* bytes this batch can touch */
+    int rc = direct ? p3_decode_batch_async(id->ctx, id->in + id->istart, upl, &pb, target)
+                    : p3_decode_batch(id->ctx, id->in + id->istart, upl, &pb, target, NULL);
+    p3_parsed_free(&pb);                                                     /* (the async call took the arrays over) */
+    if (rc != P3_OK) { fprintf(stderr, "pdmp3_b200: %s\n", p3_last_error()); res = PDMP3_ERR; break; }
+    inflight |= direct;
     id->ps = ps; id->ps.pcm_index = 0;
-    id->sfreq = pb.frames[pb.n_frames - 1].sfreq;
+    id->sfreq = sf_last;
     if (!id->new_header) id->new_header = 1;                                 /* pdmp3.c:1318 */
-    id->istart += pb.consumed; id->processed += pb.consumed;
-    if (id->istart == id->iend) id->istart = id->iend = 0;
+    id->istart += used; id->processed += used;
     if (direct) {
-      size_t n = (size_t)pb.n_frames * fbytes;
+      size_t n = (size_t)nfr * fbytes;
       outmemory += n; outsize -= n; *done += n;
     } else {
       memcpy(outmemory, id->pcm, outsize);
@@ -167,8 +192,9 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
       *done += outsize; outmemory += outsize; outsize = 0;
     }
     res = PDMP3_OK;
-    p3_parsed_free(&pb);
   }
+  if (inflight && p3_batch_sync(id->ctx) != P3_OK) { fprintf(stderr, "pdmp3_b200: %s\n", p3_last_error()); res = PDMP3_ERR; }
+  if (id->istart == id->iend) id->istart = id->iend = 0;
   if (id->new_header == 1 && res == PDMP3_OK) res = PDMP3_NEW_FORMAT;       /* pdmp3.c:2470-2472 */
   return res;
 }

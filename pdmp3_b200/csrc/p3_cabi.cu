@@ -31,18 +31,28 @@ static int ensure(dbuf *b, size_t n)
   return P3_OK;
 }
 
+/* One in-flight batch: its inputs, its PCM and the events that order H2D -> kernels -> D2H.  Two slots
+ * let the upload of batch k+1 and the download of batch k-1 overlap the kernels of batch k. */
+struct p3_slot {
+  dbuf raw, frames, gcs, pcm;
+  uint8_t *d_tail; uint8_t *h_tail;       /* 512 main-data bytes in front of the batch (pinned host copy) */
+  cudaEvent_t h2d_done, compute_done, d2h_done;
+  p3_parsed keep; int have_keep;          /* host descriptors owned until the upload has completed */
+  int busy;
+};
+
 struct p3_ctx {
   int device, mode;
-  cudaStream_t stream;
+  cudaStream_t stream, s_h2d, s_d2h;     /* kernels | uploads | downloads */
   cudaEvent_t ev[10];
   p3_tables *d_tables;
   p3_state *d_state[2]; int cur;          /* double-buffered carried state: kernels read [cur], write [cur^1] */
-  uint8_t *d_tail; uint8_t h_tail[512];   /* last 512 main-data bytes before the current batch */
-  dbuf raw, frames, gcs, is16, count1, scf, xr, y, pcm;
-  /* current batch */
+  uint8_t h_tail[512];                    /* last 512 main-data bytes before the next batch */
+  p3_slot slot[2]; int cur_slot;
+  dbuf is16, count1, scf, xr, y;          /* intermediates, only touched by the kernel stream */
+  /* current (most recently uploaded) batch */
   int64_t n_frames, n_pcm_frames; uint32_t nch; uint64_t raw_bytes;
   uint32_t k1_smem_words; int64_t chunk_frames;
-  p3_frame *h_frames_last; /* unused */
   int launches; int taps; int fpc;
   uint8_t next_tail[512]; int have_next_tail;
 };
@@ -64,11 +74,19 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
   if (!c) return fail(P3_ENOMEM, "calloc");
   c->device = device; c->mode = P3_MODE_EXACT;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    p3_slot *sl = &c->slot[i];
+    CK(cudaEventCreateWithFlags(&sl->h2d_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sl->compute_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sl->d2h_done, cudaEventDisableTiming));
+    CK(cudaMalloc(&sl->d_tail, 512)); CK(cudaMemset(sl->d_tail, 0, 512));
+    CK(cudaHostAlloc((void **)&sl->h_tail, 512, cudaHostAllocDefault)); memset(sl->h_tail, 0, 512);
+  }
   for (int i = 0; i < 10; i++) CK(cudaEventCreate(&c->ev[i]));
   CK(cudaMalloc(&c->d_tables, sizeof(p3_tables)));
   CK(cudaMemcpy(c->d_tables, p3_tables_get(), sizeof(p3_tables), cudaMemcpyHostToDevice));
   for (int i = 0; i < 2; i++) { CK(cudaMalloc(&c->d_state[i], sizeof(p3_state))); CK(cudaMemset(c->d_state[i], 0, sizeof(p3_state))); }
-  CK(cudaMalloc(&c->d_tail, 512)); CK(cudaMemset(c->d_tail, 0, 512));
   CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_polyphase, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   c->chunk_frames = 1 << 18; c->fpc = 32;
@@ -81,16 +99,30 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
   return P3_OK;
 }
 
+static void slot_release(p3_slot *sl)
+{
+  if (sl->busy) { cudaEventSynchronize(sl->d2h_done); sl->busy = 0; }
+  if (sl->have_keep) { p3_parsed_free(&sl->keep); sl->have_keep = 0; }
+}
+
 extern "C" void p3_ctx_destroy(p3_ctx *c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  dbuf *bs[] = {&c->raw, &c->frames, &c->gcs, &c->is16, &c->count1, &c->scf, &c->xr, &c->y, &c->pcm};
+  cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_d2h);
+  for (int i = 0; i < 2; i++) {
+    p3_slot *sl = &c->slot[i];
+    slot_release(sl);
+    dbuf *bs[] = {&sl->raw, &sl->frames, &sl->gcs, &sl->pcm};
+    for (dbuf *b : bs) if (b->p) cudaFree(b->p);
+    cudaFree(sl->d_tail); cudaFreeHost(sl->h_tail);
+    cudaEventDestroy(sl->h2d_done); cudaEventDestroy(sl->compute_done); cudaEventDestroy(sl->d2h_done);
+  }
+  dbuf *bs[] = {&c->is16, &c->count1, &c->scf, &c->xr, &c->y};
   for (dbuf *b : bs) if (b->p) cudaFree(b->p);
-  cudaFree(c->d_tables); cudaFree(c->d_state[0]); cudaFree(c->d_state[1]); cudaFree(c->d_tail);
+  cudaFree(c->d_tables); cudaFree(c->d_state[0]); cudaFree(c->d_state[1]);
   for (int i = 0; i < 10; i++) cudaEventDestroy(c->ev[i]);
-  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->stream); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
   free(c);
 }
 
@@ -98,9 +130,8 @@ extern "C" int p3_ctx_reset(p3_ctx *c)
 {
   if (!c) return fail(P3_EINVAL, "null ctx");
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < 2; i++) CK(cudaMemset(c->d_state[i], 0, sizeof(p3_state)));
-  CK(cudaMemset(c->d_tail, 0, 512));
+  CK(cudaStreamSynchronize(c->s_h2d)); CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->s_d2h));
+  for (int i = 0; i < 2; i++) { slot_release(&c->slot[i]); CK(cudaMemset(c->d_state[i], 0, sizeof(p3_state))); }
   memset(c->h_tail, 0, 512); c->have_next_tail = 0;
   return P3_OK;
 }
@@ -130,10 +161,9 @@ static void compute_tail(const uint8_t *raw, const p3_parsed *b, const uint8_t p
   if (filled < 512) memcpy(out, prev_tail + filled, (size_t)(512 - filled));
 }
 
-extern "C" int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *b)
+/* Stage a parsed batch in slot `sl`: allocate, size K1's window, enqueue the uploads on `st`. */
+static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *b, cudaStream_t st)
 {
-  if (!c || !raw || !b) return fail(P3_EINVAL, "null argument");
-  CK(cudaSetDevice(c->device));
   int64_t nf = b->n_frames;
   c->n_frames = nf; c->n_pcm_frames = b->n_pcm_frames; c->raw_bytes = raw_bytes;
   c->nch = nf ? b->frames[0].nch : 2;
@@ -141,10 +171,10 @@ extern "C" int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes
   for (int64_t f = 1; f < nf; f++)
     if (b->frames[f].nch != c->nch) return fail(P3_EINVAL, "channel count changes inside a batch (frame %lld)", (long long)f);
   int rc;
-  if ((rc = ensure(&c->raw, raw_bytes + 64))) return rc;
-  if ((rc = ensure(&c->frames, (size_t)nf * sizeof(p3_frame)))) return rc;
-  if ((rc = ensure(&c->gcs, (size_t)nf * 4 * sizeof(p3_gc)))) return rc;
-  if ((rc = ensure(&c->pcm, (size_t)(b->n_pcm_frames ? b->n_pcm_frames : 1) * 1152 * c->nch * sizeof(int16_t)))) return rc;
+  if ((rc = ensure(&sl->raw, raw_bytes + 64))) return rc;
+  if ((rc = ensure(&sl->frames, (size_t)nf * sizeof(p3_frame)))) return rc;
+  if ((rc = ensure(&sl->gcs, (size_t)nf * 4 * sizeof(p3_gc)))) return rc;
+  if ((rc = ensure(&sl->pcm, (size_t)(b->n_pcm_frames ? b->n_pcm_frames : 1) * 1152 * c->nch * sizeof(int16_t)))) return rc;
   int64_t cf = nf < c->chunk_frames ? nf : c->chunk_frames;
   if ((rc = ensure(&c->is16, (size_t)cf * 4 * 576 * 2))) return rc;
   if ((rc = ensure(&c->count1, (size_t)cf * 4 * 4))) return rc;
@@ -161,32 +191,42 @@ extern "C" int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes
     if (span > maxg) maxg = span;
   }
   c->k1_smem_words = (uint32_t)((512 + maxg + 16 + 3) / 4 + 3) & ~3u;   /* multiple of 16 bytes: the staging areas behind it hold uint4 */
-  if ((size_t)c->k1_smem_words * 4 + sizeof(((p3_tables *)0)->hlut) > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
-  CK(cudaMemcpyAsync(c->raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->frames.p, b->frames, (size_t)nf * sizeof(p3_frame), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->gcs.p, b->gcs, (size_t)nf * 4 * sizeof(p3_gc), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d_tail, c->h_tail, 512, cudaMemcpyHostToDevice, c->stream));
+  if ((size_t)c->k1_smem_words * 4 + sizeof(((p3_tables *)0)->hlut) + 24 * K1_THREADS * 4 > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
+  memcpy(sl->h_tail, c->h_tail, 512);
+  CK(cudaMemcpyAsync(sl->raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(sl->frames.p, b->frames, (size_t)nf * sizeof(p3_frame), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(sl->gcs.p, b->gcs, (size_t)nf * 4 * sizeof(p3_gc), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(sl->d_tail, sl->h_tail, 512, cudaMemcpyHostToDevice, st));
   compute_tail(raw, b, c->h_tail, c->next_tail); c->have_next_tail = 1;
   return P3_OK;
 }
 
-/* Launch K1..K4 over frames [f0,f1) of the uploaded batch.  ev != NULL: record stage events. */
-static int run_chunk(p3_ctx *c, int64_t f0, int64_t f1, cudaEvent_t *ev)
+extern "C" int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *b)
 {
-  const p3_frame *fr = (const p3_frame *)c->frames.p; const p3_gc *gc = (const p3_gc *)c->gcs.p;
+  if (!c || !raw || !b) return fail(P3_EINVAL, "null argument");
+  CK(cudaSetDevice(c->device));
+  p3_slot *sl = &c->slot[c->cur_slot];
+  slot_release(sl);
+  return stage_batch(c, sl, raw, raw_bytes, b, c->stream);
+}
+
+/* Launch K1..K4 over frames [f0,f1) of the batch staged in `sl`.  ev != NULL: record stage events. */
+static int run_chunk(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, cudaEvent_t *ev)
+{
+  const p3_frame *fr = (const p3_frame *)sl->frames.p; const p3_gc *gc = (const p3_gc *)sl->gcs.p;
   const int64_t nf = f1 - f0;
   p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
   CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));   /* fields a launch does not rewrite carry over */
   if (ev) CK(cudaEventRecord(ev[0], c->stream));
   size_t smem1 = (size_t)c->k1_smem_words * 4 + (8 + 16) * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
   k_huffman<<<(unsigned)((nf + K1_FPB - 1) / K1_FPB), K1_THREADS, smem1, c->stream>>>(
-      (const uint8_t *)c->raw.p, fr, gc, c->d_tables, c->d_tail, f0, f1, c->k1_smem_words,
+      (const uint8_t *)sl->raw.p, fr, gc, c->d_tables, sl->d_tail, f0, f1, c->k1_smem_words,
       (int16_t *)c->is16.p, (int32_t *)c->count1.p, (uint8_t *)c->scf.p);
   if (ev) CK(cudaEventRecord(ev[1], c->stream));
   if (c->mode == P3_MODE_FAST) {
     /* K2+K3+K4 fused (p3_fused.cu) */
     k_synth_fast<<<(unsigned)((nf + c->fpc - 1) / c->fpc), 128, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
-        (const int16_t *)c->is16.p, (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so, (int16_t *)c->pcm.p,
+        (const int16_t *)c->is16.p, (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so, (int16_t *)sl->pcm.p,
         c->taps ? (float *)c->xr.p : NULL, c->taps ? (float *)c->y.p : NULL);
     if (ev) { CK(cudaEventRecord(ev[2], c->stream)); CK(cudaEventRecord(ev[3], c->stream)); CK(cudaEventRecord(ev[4], c->stream)); }
     CK(cudaGetLastError());
@@ -200,7 +240,7 @@ static int run_chunk(p3_ctx *c, int64_t f0, int64_t f1, cudaEvent_t *ev)
   if (ev) CK(cudaEventRecord(ev[3], c->stream));
   size_t smem4 = (size_t)(2048 + 512 + 2 * (15 + K4_SLOTS) * 96) * 4;
   k_polyphase<<<(unsigned)((2 * nf + K4_GRAN - 1) / K4_GRAN), K4_THREADS, smem4, c->stream>>>(fr, c->d_tables, f0, f1,
-      (const float *)c->y.p, si, so, (int16_t *)c->pcm.p);
+      (const float *)c->y.p, si, so, (int16_t *)sl->pcm.p);
   if (ev) CK(cudaEventRecord(ev[4], c->stream));
   CK(cudaGetLastError());
   c->cur ^= 1;
@@ -208,39 +248,46 @@ static int run_chunk(p3_ctx *c, int64_t f0, int64_t f1, cudaEvent_t *ev)
   return P3_OK;
 }
 
+static int run_all(p3_ctx *c, p3_slot *sl)
+{
+  c->launches = 0;
+  for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames) {
+    int64_t f1 = f0 + c->chunk_frames < c->n_frames ? f0 + c->chunk_frames : c->n_frames;
+    int rc = run_chunk(c, sl, f0, f1, NULL);
+    if (rc) return rc;
+  }
+  return P3_OK;
+}
+
 extern "C" int p3_batch_run(p3_ctx *c)
 {
   if (!c) return fail(P3_EINVAL, "null ctx");
   CK(cudaSetDevice(c->device));
-  c->launches = 0;
-  for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames) {
-    int64_t f1 = f0 + c->chunk_frames < c->n_frames ? f0 + c->chunk_frames : c->n_frames;
-    int rc = run_chunk(c, f0, f1, NULL);
-    if (rc) return rc;
-  }
-  return P3_OK;
+  return run_all(c, &c->slot[c->cur_slot]);
 }
 
 extern "C" int p3_batch_sync(p3_ctx *c)
 {
   if (!c) return fail(P3_EINVAL, "null ctx");
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->s_h2d)); CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->s_d2h));
+  for (int i = 0; i < 2; i++) slot_release(&c->slot[i]);
   return P3_OK;
 }
 
 extern "C" void *p3_batch_pcm_device(p3_ctx *c, uint64_t *bytes)
 {
   if (bytes) *bytes = (uint64_t)c->n_pcm_frames * 1152 * c->nch * sizeof(int16_t);
-  return c->pcm.p;
+  return c->slot[c->cur_slot].pcm.p;
 }
 
 extern "C" int p3_batch_download(p3_ctx *c, int16_t *pcm, const p3_taps *t)
 {
   if (!c) return fail(P3_EINVAL, "null ctx");
   CK(cudaSetDevice(c->device));
+  p3_slot *sl = &c->slot[c->cur_slot];
   if (pcm && c->n_pcm_frames)
-    CK(cudaMemcpyAsync(pcm, c->pcm.p, (size_t)c->n_pcm_frames * 1152 * c->nch * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(pcm, sl->pcm.p, (size_t)c->n_pcm_frames * 1152 * c->nch * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
   if (t) {
     if (c->n_frames > c->chunk_frames) return fail(P3_EINVAL, "taps need the batch to fit one chunk (%lld frames)", (long long)c->chunk_frames);
     size_t ngc = (size_t)c->n_frames * 4;
@@ -259,10 +306,41 @@ extern "C" int p3_decode_batch(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes
   int rc;
   if (!c) return fail(P3_EINVAL, "null ctx");
   c->taps = t != NULL;
+  if ((rc = p3_batch_sync(c))) return rc;                 /* drain anything still in flight from the async path */
   if ((rc = p3_batch_upload(c, raw, raw_bytes, b))) return rc;
   if ((rc = p3_batch_run(c))) return rc;
   if ((rc = p3_batch_download(c, pcm, t))) return rc;
   if (c->have_next_tail) { memcpy(c->h_tail, c->next_tail, 512); c->have_next_tail = 0; }   /* reservoir for the next batch */
+  return P3_OK;
+}
+
+/* Asynchronous batch: uploads on the H2D stream, kernels on the kernel stream, the PCM download on
+ * the D2H stream, chained by events; returns as soon as everything is enqueued.  Alternating between
+ * two slots overlaps the transfer of one batch with the kernels of the other.  Takes ownership of
+ * `b` (freed once its upload has completed).  `raw` and `pcm` must stay valid until p3_batch_sync(). */
+extern "C" int p3_decode_batch_async(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, p3_parsed *b, int16_t *pcm)
+{
+  if (!c || !raw || !b) return fail(P3_EINVAL, "null argument");
+  CK(cudaSetDevice(c->device));
+  c->taps = 0;
+  c->cur_slot ^= 1;
+  p3_slot *sl = &c->slot[c->cur_slot];
+  slot_release(sl);                                        /* wait for the batch that used this slot two calls ago */
+  int rc = stage_batch(c, sl, raw, raw_bytes, b, c->s_h2d);
+  if (rc) return rc;
+  sl->keep = *b; sl->have_keep = 1; b->frames = NULL; b->gcs = NULL;
+  CK(cudaEventRecord(sl->h2d_done, c->s_h2d));
+  CK(cudaStreamWaitEvent(c->stream, sl->h2d_done, 0));
+  if ((rc = run_all(c, sl))) return rc;
+  CK(cudaEventRecord(sl->compute_done, c->stream));
+  CK(cudaStreamWaitEvent(c->s_d2h, sl->compute_done, 0));
+  if (pcm && c->n_pcm_frames)
+    CK(cudaMemcpyAsync(pcm, sl->pcm.p, (size_t)c->n_pcm_frames * 1152 * c->nch * sizeof(int16_t), cudaMemcpyDeviceToHost, c->s_d2h));
+  CK(cudaEventRecord(sl->d2h_done, c->s_d2h));
+  /* the other slot's kernels must not start before this download has its data: ordering on c->stream is implicit;
+   * its next stage_batch() waits for d2h_done through slot_release() */
+  sl->busy = 1;
+  if (c->have_next_tail) { memcpy(c->h_tail, c->next_tail, 512); c->have_next_tail = 0; }
   return P3_OK;
 }
 
@@ -282,7 +360,7 @@ extern "C" int p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_st
     for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames) {
       int64_t f1 = f0 + c->chunk_frames < c->n_frames ? f0 + c->chunk_frames : c->n_frames;
       bool single = c->n_frames <= c->chunk_frames;
-      int rc = run_chunk(c, f0, f1, single ? c->ev : NULL);
+      int rc = run_chunk(c, &c->slot[c->cur_slot], f0, f1, single ? c->ev : NULL);
       if (rc) { cudaFree(save); return rc; }
     }
     CK(cudaEventRecord(c->ev[9], c->stream));

@@ -38,16 +38,15 @@ struct k1_bits {
     hi = __funnelshift_l(b, a, sh); lo = b << sh; nb = 64 - sh;
   }
   __device__ __forceinline__ uint32_t pos() const { return widx * 32 - nb; }      /* absolute bit position */
-  __device__ __forceinline__ void skip(uint32_t n)                                /* n <= 32 */
+  __device__ __forceinline__ void skip(uint32_t n)                                /* n < 32 */
   {
-    hi = __funnelshift_l(lo, hi, n); lo = n >= 32 ? 0u : lo << n; nb -= n;
-    if (nb <= 32) {                                                               /* one whole word fits */
-      const uint32_t w = sw[widx++];
-      hi |= nb == 32 ? 0u : (nb == 0 ? w : w >> nb);
-      lo = nb == 0 ? 0u : w << (32 - nb);
-      if (nb == 32) lo = w;
-      nb += 32;
-    }
+    hi = __funnelshift_l(lo, hi, n); lo <<= n; nb -= n;
+    /* branch-free refill: when at most 32 valid bits are left, the next whole word is appended */
+    const uint32_t w = sw[widx];
+    const bool need = nb <= 32;
+    const uint32_t ah = __funnelshift_rc(w, 0u, nb), al = __funnelshift_rc(0u, w, nb);   /* (w:0) >> nb, nb in 0..32 */
+    hi |= need ? ah : 0u; lo |= need ? al : 0u;
+    nb += need ? 32u : 0u; widx += need ? 1u : 0u;
   }
 };
 
