@@ -90,10 +90,13 @@ typedef struct {
   p3_gc    *gcs;             /* malloc'd [n_frames*4] */
   uint64_t consumed;         /* bytes of `data` used up to the end of the last parsed frame      */
   int64_t  n_pcm_frames;     /* frames holding a PCM slot                                        */
+  int32_t  external;         /* arrays belong to the caller (p3_parse_into) */
   int32_t  stop;             /* 0: ran out of data, 1: max_frames, 2: no sync within 1152 bytes (pdmp3.c:1337), 3: channel count / sample rate changes at `consumed` */
 } p3_parsed;
 
 int  p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *opts, p3_parse_state *state, p3_parsed *out);
+int  p3_parse_into(const uint8_t *data, uint64_t n, const p3_parse_opts *opts, p3_parse_state *state, p3_parsed *out,
+                   p3_frame *frames_buf, p3_gc *gcs_buf, int64_t buf_cap);   /* caller-owned (e.g. page-locked) descriptor arrays */
 void p3_parsed_free(p3_parsed *p);
 int  p3_find_header(const uint8_t *data, uint64_t n, int *nch, int *sfreq);   /* 1 found, 0 need more, -1 none within 1152 B */
 

@@ -35,7 +35,7 @@ class P3ParseOpts(C.Structure):
 
 class P3Parsed(C.Structure):
     _fields_ = [("n_frames", C.c_int64), ("frames", C.POINTER(P3Frame)), ("gcs", C.POINTER(P3Gc)),
-                ("consumed", C.c_uint64), ("n_pcm_frames", C.c_int64), ("stop", C.c_int32)]
+                ("consumed", C.c_uint64), ("n_pcm_frames", C.c_int64), ("external", C.c_int32), ("stop", C.c_int32)]
 
 
 class P3Taps(C.Structure):

@@ -36,6 +36,7 @@ struct pdmp3_handle {
   int16_t *pcm;                                     /* one frame: the partially delivered frame */
   size_t pend_pos, pend_end;                        /* undelivered PCM bytes of it: [pend_pos,pend_end) */
   int in_pinned;
+  p3_frame *dfr[3]; p3_gc *dgc[3]; int dnext;       /* page-locked descriptor arrays, rotated over the in-flight batches */
   p3_ctx *ctx; int device; int ctx_failed; int mode;
   p3_parse_state ps;
   int new_header;                                   /* 0 none yet, 1 seen, -1 reported (pdmp3.c:1318,2470,2531) */
@@ -69,6 +70,7 @@ void pdmp3_delete(pdmp3_handle *id)
   if (!id) return;
   if (id->ctx) p3_ctx_destroy(id->ctx);
   if (id->in_pinned) p3_host_free(id->in); else free(id->in);
+  for (int k = 0; k < 3; k++) { p3_host_free(id->dfr[k]); p3_host_free(id->dgc[k]); }
   free(id->pcm); free(id);
 }
 
@@ -153,7 +155,13 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
     p3_parse_opts po = {want, 2 * 576, want >= 8192 ? 4 : 1, 0};
     p3_parse_state ps = id->ps;
     p3_parsed pb;
-    if (p3_parse(id->in + id->istart, in_filled(id), &po, &ps, &pb) != P3_OK) { res = PDMP3_ERR; break; }
+    p3_frame *dfr = NULL; p3_gc *dgc = NULL;
+    if (direct && want >= 1024) {                                             /* big batches: descriptors in page-locked memory, no allocation */
+      const int k = id->dnext; id->dnext = (k + 1) % 3;
+      if (!id->dfr[k]) { id->dfr[k] = (p3_frame *)p3_host_alloc(sizeof(p3_frame) * P3_API_CHUNK); id->dgc[k] = (p3_gc *)p3_host_alloc(sizeof(p3_gc) * 4 * P3_API_CHUNK); }
+      if (id->dfr[k] && id->dgc[k]) { dfr = id->dfr[k]; dgc = id->dgc[k]; }
+    }
+    if (p3_parse_into(id->in + id->istart, in_filled(id), &po, &ps, &pb, dfr, dgc, P3_API_CHUNK) != P3_OK) { res = PDMP3_ERR; break; }
     if (pb.n_frames == 0) {
       int stop = pb.stop;
       p3_parsed_free(&pb);

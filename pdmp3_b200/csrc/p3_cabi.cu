@@ -328,7 +328,7 @@ extern "C" int p3_decode_batch_async(p3_ctx *c, const uint8_t *raw, uint64_t raw
   slot_release(sl);                                        /* wait for the batch that used this slot two calls ago */
   int rc = stage_batch(c, sl, raw, raw_bytes, b, c->s_h2d);
   if (rc) return rc;
-  sl->keep = *b; sl->have_keep = 1; b->frames = NULL; b->gcs = NULL;
+  if (!b->external) { sl->keep = *b; sl->have_keep = 1; b->frames = NULL; b->gcs = NULL; }   /* caller-owned arrays: the caller rotates them */
   CK(cudaEventRecord(sl->h2d_done, c->s_h2d));
   CK(cudaStreamWaitEvent(c->stream, sl->h2d_done, 0));
   if ((rc = run_all(c, sl))) return rc;

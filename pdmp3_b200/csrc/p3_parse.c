@@ -103,6 +103,14 @@ static void *worker(void *arg)
 
 int p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_parse_state *st, p3_parsed *out)
 {
+  return p3_parse_into(data, n, o, st, out, NULL, NULL, 0);
+}
+
+/* Same, writing into caller-owned descriptor arrays (e.g. page-locked) of `cap` frames; the result is
+ * then not freed by p3_parsed_free(). */
+int p3_parse_into(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_parse_state *st, p3_parsed *out,
+                  p3_frame *frames_buf, p3_gc *gcs_buf, int64_t buf_cap)
+{
   p3_parse_opts od = {0, 0, 0, 0};
   p3_parse_state sd = {0, 0, 0, -1, -1};
   if (!data || !out) return P3_EINVAL;
@@ -113,12 +121,14 @@ int p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_parse_s
   /* ---- phase 1: sequential header hop ---- */
   int64_t cap = o->max_frames > 0 ? o->max_frames : (int64_t)(n / 96 + 16), nf = 0;
   if (cap > (int64_t)(n / 96 + 16)) cap = (int64_t)(n / 96 + 16);
-  p3_frame *fr = (p3_frame *)malloc((size_t)(cap > 0 ? cap : 1) * sizeof *fr);
+  const int ext = frames_buf && gcs_buf;
+  if (ext && cap > buf_cap) cap = buf_cap;
+  p3_frame *fr = ext ? frames_buf : (p3_frame *)malloc((size_t)(cap > 0 ? cap : 1) * sizeof *fr);
   if (!fr) return P3_ENOMEM;
   uint64_t pos = 0;
   int stop = 0;
   while (1) {
-    if (o->max_frames > 0 && nf >= o->max_frames) { stop = 1; break; }
+    if ((o->max_frames > 0 && nf >= o->max_frames) || nf >= cap) { stop = 1; break; }
     if (n - pos < (o->lookahead ? o->lookahead : 4)) break;
     uint64_t p = pos, lim = pos + 1153 < n - 3 ? pos + 1153 : n - 3;   /* resync window (pdmp3.c:1337) */
     while (p < lim && !header_ok(data + p)) p++;
@@ -131,6 +141,9 @@ int p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_parse_s
     unsigned fsize = 144u * k_bitrate[br] * 1000u / k_sfreq[sf] + pad;            /* pdmp3.c:1135-1138 */
     unsigned hdr = 4 + (prot ? 0 : 2);
     if (fsize < hdr + silen || p + fsize > n) break;                              /* incomplete frame */
+    /* the hop is one cache miss per frame; fetch the headers a few frames ahead assuming a similar
+     * frame length (exact for CBR, harmless for VBR) */
+    if (p + 8 * (uint64_t)fsize + 64 < n) { __builtin_prefetch(data + p + 6 * (uint64_t)fsize); __builtin_prefetch(data + p + 6 * (uint64_t)fsize + 64); __builtin_prefetch(data + p + 8 * (uint64_t)fsize); }
     p3_frame *f = &fr[nf];
     f->main_off = p + hdr + silen;
     f->main_size = (uint16_t)(fsize - hdr - silen);
@@ -150,7 +163,8 @@ int p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_parse_s
     nf++;
   }
   out->consumed = pos; out->n_frames = nf; out->frames = fr; out->stop = stop;
-  out->gcs = (p3_gc *)malloc((size_t)(nf > 0 ? nf : 1) * 4 * sizeof(p3_gc));
+  out->external = ext;
+  out->gcs = ext ? gcs_buf : (p3_gc *)malloc((size_t)(nf > 0 ? nf : 1) * 4 * sizeof(p3_gc));
   if (!out->gcs) { free(fr); return P3_ENOMEM; }
 
   /* ---- phase 2: side info, in parallel ---- */
@@ -181,4 +195,4 @@ int p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_parse_s
   return P3_OK;
 }
 
-void p3_parsed_free(p3_parsed *p) { if (p) { free(p->frames); free(p->gcs); p->frames = NULL; p->gcs = NULL; } }
+void p3_parsed_free(p3_parsed *p) { if (p) { if (!p->external) { free(p->frames); free(p->gcs); } p->frames = NULL; p->gcs = NULL; } }
