@@ -221,14 +221,19 @@ def main():
     peak, peak_src = peaks()
     frame_bytes = len(stream) / parsed.n_frames
     alg_bytes = (frame_bytes + 4608.0) * n_frames
-    names = ["k_huffman", "k_requant", "k_imdct", "k_polyphase"]
+    names = ["k_huffman", "k_synth_fast", "-", "-"] if a.mode == "fast" else ["k_huffman", "k_requant", "k_imdct", "k_polyphase"]
     dom = int(np.argmax(ms_stage)) if sum(ms_stage) > 0 else 0
     dom_ms = ms_stage[dom] if sum(ms_stage) > 0 else ms
+    traffic = None
+    tj = os.path.join(ROOT, "profiles", "traffic.json")       # dram__bytes_read+write per frame of each kernel, from the committed ncu captures
+    if os.path.exists(tj):
+        tr = json.load(open(tj)).get(names[dom])
+        if tr: traffic = tr["dram_bytes_per_frame"] * n_frames
     roof = {"bound": "hbm", "kernel": names[dom], "achieved": alg_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": alg_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+            "frac": alg_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
             "algorithmic_bytes_per_frame": frame_bytes + 4608.0,
             "whole_path": {"achieved": alg_bytes / (ms * 1e-3) / 1e9, "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak},
-            "stage_ms": dict(zip(names, ms_stage))}
+            "stage_ms": {k: v for k, v in zip(names, ms_stage) if k != "-"}}
     cpu = None
     if not a.no_cpu and world == 1:
         r = ref_cpu_throughput(BLOCK, ncores, 4096)

@@ -65,3 +65,46 @@ def test_exact_batches_with_carried_state(gpu_ctx):
     assert np.array_equal(a, np.concatenate(parts))
     o = H.oracle_decode(s, lookahead=0)
     assert np.array_equal(a, o["pcm"])
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+def test_shards_with_halo_bit_identical(mode):
+    """the concatenated PCM of an N-way frame-sharded decode (each shard primed by its warm-up
+    frames) is bit-identical to the single-pass decode -- the multi-GPU correctness check, run here as
+    three shards on one GPU with a fresh decoder state per shard."""
+    import pdmp3_b200
+    from pdmp3_b200 import shard
+    ctx = pdmp3_b200.Context(0, pdmp3_b200.MODE_FAST if mode == "fast" else pdmp3_b200.MODE_EXACT)
+    s, _ = H.synth(300, seed=23, **H.CONFIGS["cfg4_vbr_mixed"])
+    whole = ctx.decode(s, lookahead=0)
+    fr = pdmp3_b200.parse_stream(s, lookahead=0).frames()
+    parts = []
+    for p in shard.plan_shards(fr, 3):
+        ctx.reset()
+        parts.append(ctx.decode(s[p["byte_lo"]:p["byte_hi"]], lookahead=0, warmup=p["warmup"]))
+        assert parts[-1].shape[0] == p["last"] - p["first"]
+    assert np.array_equal(np.concatenate(parts), whole)
+    ctx.close()
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] size (65 536 frames) through size-independent properties: the stream is a
+    4096-frame block tiled 16 times, so (a) encode->decode round trip: the Huffman stage returns exactly
+    the encoded spectra for every tile, (b) PCM of tiles 2..16 is identical (same input, same carried
+    state), (c) decoding twice gives the same bits (no races), (d) a tile decoded alone from zero state
+    differs from a mid-stream tile only in its first frame (halo = 1 frame of filter state)."""
+    import pdmp3_b200
+    blk, iso = H.synth(4096, want_is=True, seed=77, **H.CONFIGS["cfg3_320k_js_ms"])
+    s = np.tile(blk, 16)
+    ctx = pdmp3_b200.Context(0, pdmp3_b200.MODE_EXACT)
+    pcm, t = ctx.decode(s, lookahead=0, taps=True)
+    assert pcm.shape[0] == 65536
+    ih = t["is_huff"].reshape(16, 4096, 2, 2, 576)
+    assert all(np.array_equal(ih[k], iso) for k in range(16))
+    tiles = pcm.reshape(16, 4096, 1152, 2)
+    assert all(np.array_equal(tiles[k], tiles[1]) for k in range(2, 16))
+    ctx.reset(); again = ctx.decode(s, lookahead=0)
+    assert np.array_equal(pcm, again)
+    ctx.reset(); alone = ctx.decode(blk, lookahead=0)
+    assert np.array_equal(alone[1:], tiles[1][1:]) and not np.array_equal(alone[0], tiles[1][0])
+    ctx.close()
