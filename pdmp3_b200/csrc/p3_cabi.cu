@@ -18,6 +18,7 @@ static int fail(int code, const char *fmt, ...) { va_list ap; va_start(ap, fmt);
 extern "C" const char *p3_last_error(void) { return g_err; }
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(P3_ECUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
+#define P3_PP_CHUNK 8192            /* frames per ping-pong step: 2 x 38 MB of spectra stay inside the 126 MB L2 */
 struct dbuf { void *p; size_t cap; };
 static int ensure(dbuf *b, size_t n)
 {
@@ -49,7 +50,9 @@ struct p3_ctx {
   p3_state *d_state[2]; int cur;          /* double-buffered carried state: kernels read [cur], write [cur^1] */
   uint8_t h_tail[512];                    /* last 512 main-data bytes before the next batch */
   p3_slot slot[2]; int cur_slot;
-  dbuf is16, count1, scf, xr, y;          /* intermediates, only touched by the kernel stream */
+  dbuf is16, count1, scf, xr, y;          /* intermediates, only touched by the kernel streams */
+  dbuf is16b, count1b, scfb;              /* FAST mode ping-pong partner (L2-resident hand-over K1 -> fused kernel) */
+  cudaStream_t s_k1; cudaEvent_t k1_done[2], syn_done[2], fork; int pingpong;
   /* current (most recently uploaded) batch */
   int64_t n_frames, n_pcm_frames; uint32_t nch; uint64_t raw_bytes;
   uint32_t k1_smem_words; int64_t chunk_frames;
@@ -76,6 +79,10 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->s_k1, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&c->k1_done[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->syn_done[i], cudaEventDisableTiming)); }
+  CK(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
+  c->pingpong = 0; { const char *e = getenv("P3_PINGPONG"); if (e) c->pingpong = atoi(e); }   /* experiment, off: small launches underfill the GPU (profiles/README.md) */
   for (int i = 0; i < 2; i++) {
     p3_slot *sl = &c->slot[i];
     CK(cudaEventCreateWithFlags(&sl->h2d_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sl->compute_done, cudaEventDisableTiming));
@@ -118,8 +125,10 @@ extern "C" void p3_ctx_destroy(p3_ctx *c)
     cudaFree(sl->d_tail); cudaFreeHost(sl->h_tail);
     cudaEventDestroy(sl->h2d_done); cudaEventDestroy(sl->compute_done); cudaEventDestroy(sl->d2h_done);
   }
-  dbuf *bs[] = {&c->is16, &c->count1, &c->scf, &c->xr, &c->y};
+  dbuf *bs[] = {&c->is16, &c->count1, &c->scf, &c->xr, &c->y, &c->is16b, &c->count1b, &c->scfb};
   for (dbuf *b : bs) if (b->p) cudaFree(b->p);
+  cudaStreamDestroy(c->s_k1); cudaEventDestroy(c->fork);
+  for (int i = 0; i < 2; i++) { cudaEventDestroy(c->k1_done[i]); cudaEventDestroy(c->syn_done[i]); }
   cudaFree(c->d_tables); cudaFree(c->d_state[0]); cudaFree(c->d_state[1]);
   for (int i = 0; i < 10; i++) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
@@ -141,7 +150,8 @@ extern "C" int p3_ctx_set_mode(p3_ctx *c, int mode)
   if (!c || (mode != P3_MODE_EXACT && mode != P3_MODE_FAST)) return fail(P3_EINVAL, "bad mode");
   c->mode = mode;
   /* frames per kernel-sequence launch: EXACT keeps fp32 intermediates of every stage in HBM (28 KB/frame), FAST only the int16 spectra */
-  c->chunk_frames = mode == P3_MODE_FAST ? (1 << 21) : (1 << 18);
+  c->chunk_frames = mode == P3_MODE_FAST ? (c->pingpong ? P3_PP_CHUNK : (1 << 21)) : (1 << 18);
+  { const char *e = getenv("P3_CHUNK"); if (e && atoi(e) >= 64) c->chunk_frames = atoi(e); }
   return P3_OK;
 }
 extern "C" int p3_ctx_set_taps(p3_ctx *c, int on) { if (!c) return P3_EINVAL; c->taps = on; return P3_OK; }
@@ -179,6 +189,11 @@ static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_
   if ((rc = ensure(&c->is16, (size_t)cf * 4 * 576 * 2))) return rc;
   if ((rc = ensure(&c->count1, (size_t)cf * 4 * 4))) return rc;
   if ((rc = ensure(&c->scf, (size_t)cf * 4 * P3_SCF_STRIDE))) return rc;
+  if (c->mode == P3_MODE_FAST && c->pingpong && !c->taps) {
+    if ((rc = ensure(&c->is16b, (size_t)cf * 4 * 576 * 2))) return rc;
+    if ((rc = ensure(&c->count1b, (size_t)cf * 4 * 4))) return rc;
+    if ((rc = ensure(&c->scfb, (size_t)cf * 4 * P3_SCF_STRIDE))) return rc;
+  }
   if (c->mode == P3_MODE_EXACT || c->taps) {
     if ((rc = ensure(&c->xr, (size_t)cf * 4 * 576 * 4))) return rc;
     if ((rc = ensure(&c->y, (size_t)cf * 4 * 576 * 4))) return rc;
@@ -248,9 +263,41 @@ static int run_chunk(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, cudaEvent_t
   return P3_OK;
 }
 
+/* FAST mode, two streams: K1 of step k+1 runs beside the fused kernel of step k, and the spectra of a
+ * step (38 MB) are consumed straight out of the 126 MB L2 and overwritten in place two steps later,
+ * so most of them never travel to HBM. */
+static int run_pingpong(p3_ctx *c, p3_slot *sl)
+{
+  const p3_frame *fr = (const p3_frame *)sl->frames.p; const p3_gc *gc = (const p3_gc *)sl->gcs.p;
+  size_t smem1 = (size_t)c->k1_smem_words * 4 + (8 + 16) * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
+  CK(cudaEventRecord(c->fork, c->stream));                 /* everything queued on the kernel stream so far (uploads) comes first */
+  CK(cudaStreamWaitEvent(c->s_k1, c->fork, 0));
+  int step = 0;
+  for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames, step++) {
+    int64_t f1 = f0 + c->chunk_frames < c->n_frames ? f0 + c->chunk_frames : c->n_frames, nf = f1 - f0;
+    const int b = step & 1;
+    int16_t *is16 = (int16_t *)(b ? c->is16b.p : c->is16.p); int32_t *c1 = (int32_t *)(b ? c->count1b.p : c->count1.p);
+    uint8_t *scf = (uint8_t *)(b ? c->scfb.p : c->scf.p);
+    if (step >= 2) CK(cudaStreamWaitEvent(c->s_k1, c->syn_done[b], 0));     /* buffer b is free again */
+    k_huffman<<<(unsigned)((nf + K1_FPB - 1) / K1_FPB), K1_THREADS, smem1, c->s_k1>>>((const uint8_t *)sl->raw.p, fr, gc, c->d_tables,
+        sl->d_tail, f0, f1, c->k1_smem_words, is16, c1, scf);
+    CK(cudaEventRecord(c->k1_done[b], c->s_k1));
+    CK(cudaStreamWaitEvent(c->stream, c->k1_done[b], 0));
+    p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
+    CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
+    k_synth_fast<<<(unsigned)((nf + c->fpc - 1) / c->fpc), 128, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc, is16, c1, scf,
+        si, so, (int16_t *)sl->pcm.p, NULL, NULL);
+    CK(cudaEventRecord(c->syn_done[b], c->stream));
+    c->cur ^= 1; c->launches += 2;
+  }
+  CK(cudaGetLastError());
+  return P3_OK;
+}
+
 static int run_all(p3_ctx *c, p3_slot *sl)
 {
   c->launches = 0;
+  if (c->mode == P3_MODE_FAST && c->pingpong && !c->taps && c->n_frames > c->chunk_frames) return run_pingpong(c, sl);
   for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames) {
     int64_t f1 = f0 + c->chunk_frames < c->n_frames ? f0 + c->chunk_frames : c->n_frames;
     int rc = run_chunk(c, sl, f0, f1, NULL);
@@ -357,12 +404,8 @@ extern "C" int p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_st
     CK(cudaMemcpyAsync(c->d_state[c->cur], save, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
     c->launches = 0;
     CK(cudaEventRecord(c->ev[8], c->stream));
-    for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames) {
-      int64_t f1 = f0 + c->chunk_frames < c->n_frames ? f0 + c->chunk_frames : c->n_frames;
-      bool single = c->n_frames <= c->chunk_frames;
-      int rc = run_chunk(c, &c->slot[c->cur_slot], f0, f1, single ? c->ev : NULL);
-      if (rc) { cudaFree(save); return rc; }
-    }
+    if (c->n_frames <= c->chunk_frames) { int rc = run_chunk(c, &c->slot[c->cur_slot], 0, c->n_frames, c->ev); if (rc) { cudaFree(save); return rc; } }
+    else { int rc = run_all(c, &c->slot[c->cur_slot]); if (rc) { cudaFree(save); return rc; } }
     CK(cudaEventRecord(c->ev[9], c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms; CK(cudaEventElapsedTime(&ms, c->ev[8], c->ev[9])); tot += ms;

@@ -25,28 +25,25 @@
  * stream into shared memory as big-endian words -- the "bit reservoir" of Get_Main_Data
  * (pdmp3.c:1096-1122) for the whole group at once; header and side-info bytes never reach smem.
  * ============================================================================================= */
-/* MSB-first bit buffer in two registers over the big-endian words in shared memory.  `hi:lo` hold
- * the next `nb` bits left-aligned and always end on a word boundary, so a refill is one aligned
- * word load that is off the critical path of the symbol chain (pdmp3.c:1489-1527 does a byte
- * access per BIT). */
+/* MSB-first bit reader over the big-endian words in shared memory: two consecutive words in registers
+ * plus a bit offset, so a 32-bit look-ahead is ONE funnel shift and advancing is branch-free (the next
+ * word is loaded unconditionally, off the critical path).  The reference does a byte access per BIT
+ * (pdmp3.c:1489-1527). */
 struct k1_bits {
-  const uint32_t *sw; uint32_t hi, lo, nb, widx;
+  const uint32_t *sw; uint32_t cur, nxt, off, widx;       /* cur = sw[widx], nxt = sw[widx+1], off in 0..31 */
   __device__ __forceinline__ void init(const uint32_t *s, uint32_t bitpos)
   {
-    sw = s; widx = (bitpos >> 5) + 2;
-    const uint32_t a = s[bitpos >> 5], b = s[(bitpos >> 5) + 1], sh = bitpos & 31;
-    hi = __funnelshift_l(b, a, sh); lo = b << sh; nb = 64 - sh;
+    sw = s; widx = bitpos >> 5; off = bitpos & 31; cur = s[widx]; nxt = s[widx + 1];
   }
-  __device__ __forceinline__ uint32_t pos() const { return widx * 32 - nb; }      /* absolute bit position */
-  __device__ __forceinline__ void skip(uint32_t n)                                /* n < 32 */
+  __device__ __forceinline__ uint32_t pos() const { return widx * 32 + off; }
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, off); }   /* next 32 bits */
+  __device__ __forceinline__ void skip(uint32_t n)                                              /* n <= 32 */
   {
-    hi = __funnelshift_l(lo, hi, n); lo <<= n; nb -= n;
-    /* branch-free refill: when at most 32 valid bits are left, the next whole word is appended */
-    const uint32_t w = sw[widx];
-    const bool need = nb <= 32;
-    const uint32_t ah = __funnelshift_rc(w, 0u, nb), al = __funnelshift_rc(0u, w, nb);   /* (w:0) >> nb, nb in 0..32 */
-    hi |= need ? ah : 0u; lo |= need ? al : 0u;
-    nb += need ? 32u : 0u; widx += need ? 1u : 0u;
+    const uint32_t w = sw[widx + 2];
+    off += n;
+    const bool adv = off >= 32;
+    cur = adv ? nxt : cur; nxt = adv ? w : nxt;
+    widx += adv ? 1u : 0u; off &= 31u;
   }
 };
 
@@ -54,23 +51,28 @@ struct k1_bits {
 __device__ __forceinline__ uint32_t k1_pair(k1_bits &bb, const uint16_t *lut, uint32_t tb)
 {
   const uint32_t base = tb & 0xffffu, linbits = (tb >> 24) & 31u;
-  uint32_t w = bb.hi;                                   /* >= 33 valid bits: the longest code has 19 */
+  const uint32_t w0 = bb.peek();
   uint32_t cw = (tb >> 16) & 31u, used = 0;
-  uint32_t e = lut[base + (w >> (32 - cw))];
+  uint32_t e = lut[base + (w0 >> (32 - cw))];
   while (e & 0x8000u) {                                 /* next LUT level (codes longer than 8 bits) */
     used += cw; cw = (e >> 10) & 7;
-    e = lut[base + (e & 1023u) + ((w << used) >> (32 - cw))];
+    e = lut[base + (e & 1023u) + ((w0 << used) >> (32 - cw))];
   }
   used += (e >> 8) & 31;
   int x = (e >> 4) & 15, y = e & 15;
-  bb.skip(used);
-  w = bb.hi;                                            /* >= 33 valid bits: 2 x (13 linbits + sign) = 28 */
-  uint32_t u2 = 0;
-  if (linbits && x == 15) { x += (int)(w >> (32 - linbits)); w <<= linbits; u2 += linbits; }
-  if (x) { if (w >> 31) x = -x; w <<= 1; u2++; }
-  if (linbits && y == 15) { y += (int)(w >> (32 - linbits)); w <<= linbits; u2 += linbits; }
-  if (y) { if (w >> 31) y = -y; u2++; }
-  bb.skip(u2);
+  /* bits after the code word: x linbits, x sign, y linbits, y sign (pdmp3.c:1637-1640).  If code + worst-case
+   * escapes cannot fit the 32-bit window (only tables with >= 8 linbits), re-read after the code word. */
+  uint32_t w = w0 << used, total = used;
+  if (used + 2 * linbits + 2 > 32) { bb.skip(used); w = bb.peek(); total = 0; }
+  const uint32_t ex = x == 15 ? linbits : 0u;
+  x += (int)((w >> 1) >> (31 - ex)); w <<= ex;
+  const uint32_t sx = x != 0;
+  x = (sx & (w >> 31)) ? -x : x; w <<= sx;
+  const uint32_t ey = y == 15 ? linbits : 0u;
+  y += (int)((w >> 1) >> (31 - ey)); w <<= ey;
+  const uint32_t sy = y != 0;
+  y = (sy & (w >> 31)) ? -y : y;
+  bb.skip(total + ex + sx + ey + sy);
   return (uint32_t)(x & 0xffff) | ((uint32_t)y << 16);
 }
 
@@ -235,7 +237,7 @@ k_huffman(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames, 
       const uint32_t qbase = T->book_base[T->table_book[32]], qbits = T->book_pbits[T->table_book[32]];
       pos = bb.pos();
       while (is_pos <= 572 && pos <= bit_pos_end) {
-        uint32_t w = bb.hi, used = 0, leaf = 3;
+        uint32_t w = bb.peek(), used = 0, leaf = 3;
         if (!tabB) { uint32_t e = lut[qbase + (w >> (32 - qbits))]; used = (e >> 8) & 31; leaf = e & 15; w <<= used; }
         int v = (leaf >> 3) & 1, ww = (leaf >> 2) & 1, x = (leaf >> 1) & 1, y = leaf & 1;
         if (v) { if (w >> 31) v = -1; w <<= 1; used++; }
