@@ -10,6 +10,10 @@
 #include <math.h>
 
 extern "C" int p3_fused_upload_consts(const p3_tables *T, const float *dct4);
+extern "C" size_t p3_fused_smem_bytes(uint32_t k1_words, uint32_t hlut_used);
+extern "C" int p3_fused_group_frames(void);
+extern "C" __global__ void k_decode_fused(const uint8_t *raw, const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, const uint8_t *tail, int64_t f_first, int64_t f_end,
+    uint32_t k1_words, int16_t *scratch, const p3_state *st_in, p3_state *st_out, int16_t *pcm);
 extern "C" __global__ void k_synth_fast(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_cta,
     const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, float *xr_tap, float *y_tap);
 
@@ -53,6 +57,7 @@ struct p3_ctx {
   dbuf is16, count1, scf, xr, y;          /* intermediates, only touched by the kernel streams */
   dbuf is16b, count1b, scfb;              /* FAST mode ping-pong partner (L2-resident hand-over K1 -> fused kernel) */
   cudaStream_t s_k1; cudaEvent_t k1_done[2], syn_done[2], fork; int pingpong;
+  dbuf scratch; uint32_t kf_words; int persist; int n_sm;   /* k_decode_fused: private spectra rows of the resident CTAs */
   /* current (most recently uploaded) batch */
   int64_t n_frames, n_pcm_frames; uint32_t nch; uint64_t raw_bytes;
   uint32_t k1_smem_words; int64_t chunk_frames;
@@ -82,6 +87,9 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
   CK(cudaStreamCreateWithFlags(&c->s_k1, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&c->k1_done[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->syn_done[i], cudaEventDisableTiming)); }
   CK(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
+  c->persist = 0; { const char *e = getenv("P3_PERSIST"); if (e) c->persist = atoi(e); }   /* one persistent kernel: HBM traffic = algorithmic bytes, but 14 % slower than K1 + k_synth_fast (profiles/README.md) */
+  c->n_sm = prop.multiProcessorCount;
+  CK(cudaFuncSetAttribute(k_decode_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   c->pingpong = 0; { const char *e = getenv("P3_PINGPONG"); if (e) c->pingpong = atoi(e); }   /* experiment, off: small launches underfill the GPU (profiles/README.md) */
   for (int i = 0; i < 2; i++) {
     p3_slot *sl = &c->slot[i];
@@ -125,7 +133,7 @@ extern "C" void p3_ctx_destroy(p3_ctx *c)
     cudaFree(sl->d_tail); cudaFreeHost(sl->h_tail);
     cudaEventDestroy(sl->h2d_done); cudaEventDestroy(sl->compute_done); cudaEventDestroy(sl->d2h_done);
   }
-  dbuf *bs[] = {&c->is16, &c->count1, &c->scf, &c->xr, &c->y, &c->is16b, &c->count1b, &c->scfb};
+  dbuf *bs[] = {&c->is16, &c->count1, &c->scf, &c->xr, &c->y, &c->is16b, &c->count1b, &c->scfb, &c->scratch};
   for (dbuf *b : bs) if (b->p) cudaFree(b->p);
   cudaStreamDestroy(c->s_k1); cudaEventDestroy(c->fork);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(c->k1_done[i]); cudaEventDestroy(c->syn_done[i]); }
@@ -185,7 +193,22 @@ static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_
   if ((rc = ensure(&sl->frames, (size_t)nf * sizeof(p3_frame)))) return rc;
   if ((rc = ensure(&sl->gcs, (size_t)nf * 4 * sizeof(p3_gc)))) return rc;
   if ((rc = ensure(&sl->pcm, (size_t)(b->n_pcm_frames ? b->n_pcm_frames : 1) * 1152 * c->nch * sizeof(int16_t)))) return rc;
+  const int use_persist = c->mode == P3_MODE_FAST && c->persist && !c->taps;
   int64_t cf = nf < c->chunk_frames ? nf : c->chunk_frames;
+  if (use_persist) {
+    const int FGn = p3_fused_group_frames();
+    uint64_t mg = 0;
+    for (int64_t f0 = 0; f0 < nf; f0++) {                    /* any FG consecutive frames can form a group */
+      int64_t f1 = f0 + FGn < nf ? f0 + FGn : nf;
+      uint64_t span = b->frames[f1 - 1].main_pos + b->frames[f1 - 1].main_size - b->frames[f0].main_pos;
+      if (span > mg) mg = span;
+    }
+    c->kf_words = (uint32_t)((512 + mg + 16 + 3) / 4 + 3) & ~3u;
+    if (p3_fused_smem_bytes(c->kf_words, p3_tables_get()->hlut_used) > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
+    if ((rc = ensure(&c->scratch, (size_t)c->n_sm * 4 * FGn * 4 * 576 * 2))) return rc;
+    cf = 0;
+  }
+  if (cf) {
   if ((rc = ensure(&c->is16, (size_t)cf * 4 * 576 * 2))) return rc;
   if ((rc = ensure(&c->count1, (size_t)cf * 4 * 4))) return rc;
   if ((rc = ensure(&c->scf, (size_t)cf * 4 * P3_SCF_STRIDE))) return rc;
@@ -197,6 +220,7 @@ static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_
   if (c->mode == P3_MODE_EXACT || c->taps) {
     if ((rc = ensure(&c->xr, (size_t)cf * 4 * 576 * 4))) return rc;
     if ((rc = ensure(&c->y, (size_t)cf * 4 * 576 * 4))) return rc;
+  }
   }
   /* K1 shared-memory window: 512 reservoir bytes + the largest group of K1_FPB frames */
   uint64_t maxg = 0;
@@ -294,9 +318,29 @@ static int run_pingpong(p3_ctx *c, p3_slot *sl)
   return P3_OK;
 }
 
+/* FAST mode default: the whole batch in one persistent launch (p3_fused.cu, k_decode_fused) */
+static int run_persist(p3_ctx *c, p3_slot *sl)
+{
+  const int64_t nf = c->n_frames;
+  if (nf == 0) return P3_OK;
+  p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
+  CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
+  int64_t grid = (int64_t)c->n_sm * 4;
+  const int FGn = p3_fused_group_frames();
+  if (grid > (nf + 2 * FGn - 1) / (2 * FGn)) grid = (nf + 2 * FGn - 1) / (2 * FGn);     /* at least two groups per run */
+  if (grid < 1) grid = 1;
+  size_t smem = p3_fused_smem_bytes(c->kf_words, p3_tables_get()->hlut_used);
+  k_decode_fused<<<(unsigned)grid, 128, smem, c->stream>>>((const uint8_t *)sl->raw.p, (const p3_frame *)sl->frames.p, (const p3_gc *)sl->gcs.p,
+      c->d_tables, sl->d_tail, 0, nf, c->kf_words, (int16_t *)c->scratch.p, si, so, (int16_t *)sl->pcm.p);
+  CK(cudaGetLastError());
+  c->cur ^= 1; c->launches += 1;
+  return P3_OK;
+}
+
 static int run_all(p3_ctx *c, p3_slot *sl)
 {
   c->launches = 0;
+  if (c->mode == P3_MODE_FAST && c->persist && !c->taps) return run_persist(c, sl);
   if (c->mode == P3_MODE_FAST && c->pingpong && !c->taps && c->n_frames > c->chunk_frames) return run_pingpong(c, sl);
   for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames) {
     int64_t f1 = f0 + c->chunk_frames < c->n_frames ? f0 + c->chunk_frames : c->n_frames;
@@ -404,12 +448,13 @@ extern "C" int p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_st
     CK(cudaMemcpyAsync(c->d_state[c->cur], save, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
     c->launches = 0;
     CK(cudaEventRecord(c->ev[8], c->stream));
-    if (c->n_frames <= c->chunk_frames) { int rc = run_chunk(c, &c->slot[c->cur_slot], 0, c->n_frames, c->ev); if (rc) { cudaFree(save); return rc; } }
+    if (c->mode == P3_MODE_FAST && c->persist && !c->taps) { int rc = run_all(c, &c->slot[c->cur_slot]); if (rc) { cudaFree(save); return rc; } }
+    else if (c->n_frames <= c->chunk_frames) { int rc = run_chunk(c, &c->slot[c->cur_slot], 0, c->n_frames, c->ev); if (rc) { cudaFree(save); return rc; } }
     else { int rc = run_all(c, &c->slot[c->cur_slot]); if (rc) { cudaFree(save); return rc; } }
     CK(cudaEventRecord(c->ev[9], c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms; CK(cudaEventElapsedTime(&ms, c->ev[8], c->ev[9])); tot += ms;
-    if (c->n_frames <= c->chunk_frames)
+    if (c->n_frames <= c->chunk_frames && !(c->mode == P3_MODE_FAST && c->persist && !c->taps))
       for (int k = 0; k < 4; k++) { CK(cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1])); st[k] += ms; }
   }
   cudaFree(save);

@@ -17,6 +17,7 @@
  */
 #include "p3_device.cuh"
 #include "p3_kernels.h"
+#include "p3_k1.cuh"
 #include "p3_lee.inc"
 
 struct p3_fconst {
@@ -122,70 +123,36 @@ __device__ __forceinline__ float fq_requant(const float *__restrict__ pow43, int
   return __fmul_rn(scale, t3);
 }
 
-extern "C" __global__ void __launch_bounds__(FT, 5)
-k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
-             int64_t f_first, int64_t f_end, int frames_per_cta,
-             const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf,
-             const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm,
-             float *__restrict__ xr_tap, float *__restrict__ y_tap)
+/* shared-memory working set of the synthesis stages (one frame = 4 granule-channels at a time) */
+struct synth_sm {
+  float (*xs)[576];                  /* [4] spectra -> subband samples, in place */
+  float (*tails)[2][576];            /* [3] IMDCT second halves: [0] granule 0, [1]/[2] granule 1 of odd/even frames */
+  float (*xring)[XSLOTS][XPITCH];    /* [2] 32-point DCT of 15 history + 36 new time slots per channel */
+  int16_t (*isbuf)[576];             /* [4] Huffman output of the current frame */
+  uint8_t *sfb_l, *sfbw_s; uint16_t *reo;   /* per-line helper tables of the current sample rate */
+  gcpar *par; float (*scale)[40]; int32_t *c1; uint32_t *sfreq;
+  float (*t01)[2][576]; float (*t2)[576];   /* fused kernel: tails[0..1] in phase-local memory, tails[2] persistent */
+  __device__ __forceinline__ float *tail(int idx, int ch) const
+  {
+    if (tails) return &tails[idx][ch][0];
+    return idx == 2 ? &t2[ch][0] : &t01[idx][ch][0];
+  }
+};
+
+/* One frame through stages A..F.  n: frame counter of this CTA (selects the tail buffer), scf4: the frame's
+ * 4 x 64 scalefactor bytes in shared memory, S.c1[4]: effective count1, pre[9]: this thread's share of the
+ * frame's spectra (fetched one frame ahead), next_is: words of the next frame's spectra or NULL. */
+template <bool SCRATCH>
+__device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &fr, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
+    int64_t f, int n, uint32_t nch, const uint8_t (*scf4)[P3_SCF_STRIDE], uint32_t (&pre)[9], const uint32_t *next_is, bool emit,
+    int16_t *__restrict__ pcm, const float (&ce)[8], const float (&co)[8], int ia, int ib, float *xr_tap, float *y_tap)
 {
-  __shared__ float xs[4][576];
-  __shared__ float tails[3][2][576];
-  __shared__ float xring[2][XSLOTS][XPITCH];
-  __shared__ __align__(16) int16_t isbuf[4][576];
-  __shared__ uint8_t s_sfb_l[576], s_sfbw_s[576];
-  __shared__ uint16_t s_reo[576];
-  __shared__ __align__(16) uint8_t s_scf[4][P3_SCF_STRIDE];
-  __shared__ gcpar s_par[4];
-  __shared__ float s_scale[4][40];                       /* fl(t1*t2) per scalefactor band: long sfb 0..21, short 3*sfb+win */
-  __shared__ uint32_t s_sfreq;
-
   const int tid = threadIdx.x;
-  const int64_t c0 = f_first + (int64_t)blockIdx.x * frames_per_cta;
-  const int64_t c1 = min(c0 + (int64_t)frames_per_cta, f_end);
-  const int warm = blockIdx.x > 0 ? 1 : 0;
-  const uint32_t nch = frames[c0].nch;
-
-  /* window coefficients of this thread's output column j, signs of the V<->X symmetry folded in */
   const int j = tid & 31, wgr = (tid >> 5) & 1, wch = tid >> 6;
-  float ce[8], co[8]; int ia, ib;
-  {
-    /* even k: V[j]:   j<16 -> +X[16+j];  j==16 -> 0;  j>16 -> -X[48-j]
-       odd  k: V[32+j]: j<16 -> -X[16-j]; j>=16 -> -X[j-16]                       (see tools/proto/fast_transforms.py) */
-    float se = j < 16 ? 1.0f : (j == 16 ? 0.0f : -1.0f);
-    ia = j < 16 ? 16 + j : (j == 16 ? 0 : 48 - j);
-    ib = j < 16 ? 16 - j : j - 16;
-    #pragma unroll
-    for (int k = 0; k < 8; k++) { ce[k] = se * T->synth_d[64 * k + j] * 32767.0f; co[k] = -T->synth_d[64 * k + 32 + j] * 32767.0f; }
-  }
-
-  /* carried state */
-  for (int i = tid; i < 2 * 576; i += FT) {
-    (&tails[2][0][0])[i] = warm ? 0.0f : st_in->store[i / 576][i % 576];
-    (&tails[0][0][0])[i] = 0.0f; (&tails[1][0][0])[i] = 0.0f;
-  }
-  for (int i = tid; i < 2 * XSLOTS * XPITCH; i += FT) (&xring[0][0][0])[i] = 0.0f;
-  __syncthreads();
-  if (!warm)
-    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, s = r / 32, k = r % 32; xring[ch][36 + s][k] = st_in->xhist[ch][14 - s][k]; }
-  if (tid == 0) s_sfreq = 0xffffffffu;
-
-  /* software pipeline: the spectra of frame n+1 are fetched into registers while frame n is processed */
-  uint32_t pre[9]; uint32_t pre_scf = 0;
-  const uint32_t *isw = reinterpret_cast<const uint32_t *>(is_in);
-  {
-    const int64_t o0 = (c0 - warm - f_first) * 4;
-    #pragma unroll
-    for (int k = 0; k < 9; k++) pre[k] = __ldg(isw + o0 * 288 + tid + FT * k);
-    if (tid < 64) pre_scf = __ldg(reinterpret_cast<const uint32_t *>(scf + o0 * P3_SCF_STRIDE) + tid);
-  }
-  __syncthreads();
-
-  int n = 0;                                              /* frame iteration within this CTA */
-  for (int64_t f = c0 - warm; f < c1; f++, n++) {
-    const p3_frame fr = frames[f];
-    const int64_t o0 = (f - f_first) * 4;
-    const bool emit = !(warm && n == 0) && (fr.flags & P3_FRAME_DECODE);
+  float (*xs)[576] = S.xs; float (*xring)[XSLOTS][XPITCH] = S.xring; int16_t (*isbuf)[576] = S.isbuf;
+  uint8_t *s_sfb_l = S.sfb_l, *s_sfbw_s = S.sfbw_s; uint16_t *s_reo = S.reo; gcpar *s_par = S.par; float (*s_scale)[40] = S.scale;
+  int32_t *s_c1 = S.c1;
+#define s_sfreq (*S.sfreq)
     if (s_sfreq != fr.sfreq) {                            /* per-line helper tables of this sample rate */
       __syncthreads();
       for (int i = tid; i < 576; i += FT) { s_sfb_l[i] = T->line_sfb_l[fr.sfreq][i]; s_sfbw_s[i] = T->line_sfbw_s[fr.sfreq][i]; s_reo[i] = T->reorder_src[fr.sfreq][i]; }
@@ -194,30 +161,22 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
     /* the last 15 slots of the previous frame become the history of this one (stage F of that frame must be done) */
     __syncthreads();
     for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, sl = r >> 5, k = r & 31; xring[ch][sl][k] = xring[ch][36 + sl][k]; }
-    /* land the prefetched spectra / scalefactors in shared memory, start the next fetch */
+    /* land the prefetched spectra in shared memory, start the next fetch */
     {
       uint32_t *ib32 = reinterpret_cast<uint32_t *>(&isbuf[0][0]);
       #pragma unroll
       for (int k = 0; k < 9; k++) ib32[tid + FT * k] = pre[k];
-      if (tid < 64) reinterpret_cast<uint32_t *>(&s_scf[0][0])[tid] = pre_scf;
-      if (f + 1 < c1) {
+      if (next_is) {
         #pragma unroll
-        for (int k = 0; k < 9; k++) pre[k] = __ldg(isw + (o0 + 4) * 288 + tid + FT * k);
-        if (tid < 64) pre_scf = __ldg(reinterpret_cast<const uint32_t *>(scf + (o0 + 4) * P3_SCF_STRIDE) + tid);
+        for (int k = 0; k < 9; k++) pre[k] = SCRATCH ? __ldcg(next_is + tid + FT * k) : __ldg(next_is + tid + FT * k);
       }
     }
     if (tid < 4) {                                        /* unpack the side info of this granule-channel once */
       const uint32_t gr = tid >> 1, ch = tid & 1;
       const p3_gc g = gcs[4 * f + tid];
       gcpar p;
-      int32_t c = 0;
-      if (ch < nch) {                                     /* effective count1 (Q6), as in k_requant */
-        const uint32_t back = g.w3;
-        if (back == 0) c = count1[o0 + tid];
-        else if ((int64_t)back <= f - f_first) c = count1[o0 + tid - 4 * (int64_t)back];
-        else c = st_in->count1[gr][ch];
-      }
-      if (f == f_end - 1) st_out->count1[gr][ch] = c;
+      const int32_t c = s_c1[tid];                        /* effective count1 (Q6), resolved by the caller */
+      (void)gr;
       const bool is_short = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
       p.c1 = c; p.gg = (int)P3_GC_GAIN(g) - 210;
       p.first_short = is_short ? (P3_GC_MIXED(g) ? 36 : 0) : 576;
@@ -237,11 +196,11 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       if (p.live) {
         const bool longband = p.first_short == 576 ? b < 22 : (p.first_short == 36 && b < 8);
         if (longband) {
-          const uint32_t sc = b < 21 ? s_scf[gcl][b] + p.pre * (uint32_t)FC.pretab[b] : 0u;
+          const uint32_t sc = b < 21 ? scf4[gcl][b] + p.pre * (uint32_t)FC.pretab[b] : 0u;
           v = __fmul_rn(FC.t1h[p.mult * sc], FC.t2[p.gg + P3_T2_BIAS]);
         } else if (p.first_short < 576 && b < 39) {
           const int sfb = b / 3, win = b % 3;
-          const uint32_t sc = sfb < 12 ? s_scf[gcl][P3_SCF_S_OFF + 3 * sfb + win] : 0u;
+          const uint32_t sc = sfb < 12 ? scf4[gcl][P3_SCF_S_OFF + 3 * sfb + win] : 0u;
           v = __fmul_rn(FC.t1h[p.mult * sc], FC.t2[p.gg - (int)p.sbg8[win] + P3_T2_BIAS]);
         }
       }
@@ -293,14 +252,14 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
           } else if (is_on) {
             if (i >= first_short0) {
               const uint32_t sw = s_sfbw_s[i], sfb = sw & 15u, win = sw >> 4;
-              if (sfb < 12 && 3u * T->sfb_s[fr.sfreq][sfb] >= c1r && s_scf[2 * gr][P3_SCF_S_OFF + 3 * sfb + win] != 7) {
+              if (sfb < 12 && 3u * T->sfb_s[fr.sfreq][sfb] >= c1r && scf4[2 * gr][P3_SCF_S_OFF + 3 * sfb + win] != 7) {
                 float x = (float)(unsigned)(long long)l;                               /* Q4 */
                 xs[2 * gr][i] = x; xs[2 * gr + 1][i] = x;
               }
             } else {
               const uint32_t sfb = s_sfb_l[i], lim = sh0 ? 8u : 21u;
               if (sfb < lim && T->sfb_l[fr.sfreq][sfb] >= c1r) {
-                const uint32_t pp = s_scf[2 * gr][sfb];
+                const uint32_t pp = scf4[2 * gr][sfb];
                 if (pp != 7) { xs[2 * gr][i] = __fmul_rn(FC.is_l[pp & 7], l); xs[2 * gr + 1][i] = __fmul_rn(FC.is_r[pp & 7], l); }
               }
             }
@@ -326,7 +285,7 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       }
     }
     __syncthreads();
-    if (xr_tap) for (int e = tid; e < 4 * 576; e += FT) xr_tap[o0 * 576 + e] = (&xs[0][0])[e];
+    if (xr_tap) for (int e = tid; e < 4 * 576; e += FT) xr_tap[e] = (&xs[0][0])[e];
 
     /* ---- D: IMDCT + window; first half in place, second half to the tail buffer ---- */
     {
@@ -335,7 +294,7 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       if (p.live) {
         const uint32_t bt = (p.ws && p.mixed && sb < 2) ? 0u : p.bt;
         float *x = &xs[gcl][18 * sb];
-        float *tl = &tails[gr == 0 ? 0 : 1 + (n & 1)][ch][18 * sb];
+        float *tl = S.tail(gr == 0 ? 0 : 1 + (n & 1), ch) + 18 * sb;
         float in[18];
         #pragma unroll
         for (int m = 0; m < 18; m++) in[m] = x[m];
@@ -373,7 +332,7 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       const uint32_t gr = tid / 36, r = tid % 36, ch = r / 18, ss = r % 18;
       if (ch < nch) {
         const float *cur = &xs[2 * gr + ch][0];
-        const float *prv = gr == 0 ? &tails[2 - (n & 1)][ch][0] : &tails[0][ch][0];
+        const float *prv = gr == 0 ? S.tail(2 - (n & 1), ch) : S.tail(0, ch);
         float s[32];
         #pragma unroll
         for (int sb = 0; sb < 32; sb++) {
@@ -382,7 +341,7 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
         }
         if (y_tap) {
           #pragma unroll
-          for (int sb = 0; sb < 32; sb++) y_tap[(o0 + 2 * gr + ch) * 576 + ss * 32 + sb] = s[sb];
+          for (int sb = 0; sb < 32; sb++) y_tap[(2 * gr + ch) * 576 + ss * 32 + sb] = s[sb];
         }
         dct2<32>(s);
         float *X = &xring[ch][15 + gr * 18 + ss][0];
@@ -409,16 +368,261 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
           /* (int32)(sum*32767.0) with the scale folded into the window; x86 gives INT_MIN out of range */
           int32_t s = fabsf(sum) < 2147483648.0f ? __float2int_rz(sum) : (int32_t)0x80000000;
           s = max(-32767, min(32767, s));
-          pcm[base + (int64_t)(9 * h + s9) * 32 * nch] = (int16_t)s;
+          __stcs(pcm + base + (int64_t)(9 * h + s9) * 32 * nch, (int16_t)s);       /* streaming: do not displace the L2-resident spectra */
         }
       }
     }
+#undef s_sfreq
+}
+
+/* window coefficients of this thread's output column j, signs of the V<->X symmetry and the 32767 scale folded in:
+ *   even k: V[j]:   j<16 -> +X[16+j];  j==16 -> 0;  j>16 -> -X[48-j]
+ *   odd  k: V[32+j]: j<16 -> -X[16-j]; j>=16 -> -X[j-16]                       (see tools/proto/fast_transforms.py) */
+__device__ __forceinline__ void synth_window_coeffs(const p3_tables *__restrict__ T, float (&ce)[8], float (&co)[8], int &ia, int &ib)
+{
+  const int j = threadIdx.x & 31;
+  const float se = j < 16 ? 1.0f : (j == 16 ? 0.0f : -1.0f);
+  ia = j < 16 ? 16 + j : (j == 16 ? 0 : 48 - j);
+  ib = j < 16 ? 16 - j : j - 16;
+  #pragma unroll
+  for (int k = 0; k < 8; k++) { ce[k] = se * T->synth_d[64 * k + j] * 32767.0f; co[k] = -T->synth_d[64 * k + 32 + j] * 32767.0f; }
+}
+
+/* carried state -> shared memory (st == NULL: zero state, used when a run is primed by a warm-up frame) */
+__device__ __forceinline__ void synth_load_state(const synth_sm &S, const p3_state *__restrict__ st)
+{
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * 576; i += FT) {
+    S.tail(2, i / 576)[i % 576] = st ? st->store[i / 576][i % 576] : 0.0f;
+    S.tail(0, i / 576)[i % 576] = 0.0f; S.tail(1, i / 576)[i % 576] = 0.0f;
+  }
+  for (int i = tid; i < 2 * XSLOTS * XPITCH; i += FT) (&S.xring[0][0][0])[i] = 0.0f;
+  __syncthreads();
+  if (st)
+    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, s = r / 32, k = r % 32; S.xring[ch][36 + s][k] = st->xhist[ch][14 - s][k]; }
+  if (tid == 0) *S.sfreq = 0xffffffffu;
+  __syncthreads();
+}
+
+/* shared memory -> carried state, after the last frame (iteration index `last`) of a launch */
+__device__ __forceinline__ void synth_store_state(const synth_sm &S, int last, p3_state *__restrict__ st)
+{
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * 576; i += FT) st->store[i / 576][i % 576] = S.tail(1 + (last & 1), i / 576)[i % 576];
+  for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, age = r / 32, k = r % 32; st->xhist[ch][age][k] = S.xring[ch][50 - age][k]; }
+}
+
+extern "C" __global__ void __launch_bounds__(FT, 5)
+k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
+             int64_t f_first, int64_t f_end, int frames_per_cta,
+             const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf,
+             const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm,
+             float *__restrict__ xr_tap, float *__restrict__ y_tap)
+{
+  __shared__ float xs[4][576];
+  __shared__ float tails[3][2][576];
+  __shared__ float xring[2][XSLOTS][XPITCH];
+  __shared__ __align__(16) int16_t isbuf[4][576];
+  __shared__ uint8_t s_sfb_l[576], s_sfbw_s[576];
+  __shared__ uint16_t s_reo[576];
+  __shared__ __align__(16) uint8_t s_scf[4][P3_SCF_STRIDE];
+  __shared__ gcpar s_par[4];
+  __shared__ float s_scale[4][40];                       /* fl(t1*t2) per scalefactor band: long sfb 0..21, short 3*sfb+win */
+  __shared__ int32_t s_c1[4];
+  __shared__ uint32_t s_sfreq;
+  synth_sm S = {xs, tails, xring, isbuf, s_sfb_l, s_sfbw_s, s_reo, s_par, s_scale, s_c1, &s_sfreq, NULL, NULL};
+
+  const int tid = threadIdx.x;
+  const int64_t c0 = f_first + (int64_t)blockIdx.x * frames_per_cta;
+  const int64_t c1 = min(c0 + (int64_t)frames_per_cta, f_end);
+  const int warm = blockIdx.x > 0 ? 1 : 0;
+  const uint32_t nch = frames[c0].nch;
+
+  float ce[8], co[8]; int ia, ib;
+  synth_window_coeffs(T, ce, co, ia, ib);
+  synth_load_state(S, warm ? NULL : st_in);
+
+  /* software pipeline: the spectra of frame n+1 are fetched into registers while frame n is processed */
+  uint32_t pre[9], pre_scf = 0;
+  const uint32_t *isw = reinterpret_cast<const uint32_t *>(is_in);
+  {
+    const int64_t o0 = (c0 - warm - f_first) * 4;
+    #pragma unroll
+    for (int k = 0; k < 9; k++) pre[k] = __ldg(isw + o0 * 288 + tid + FT * k);
+    if (tid < 64) pre_scf = __ldg(reinterpret_cast<const uint32_t *>(scf + o0 * P3_SCF_STRIDE) + tid);
   }
   __syncthreads();
-  if (c1 == f_end) {                                       /* leave the state for the next launch */
-    const int last = n - 1;
-    for (int i = tid; i < 2 * 576; i += FT) st_out->store[i / 576][i % 576] = tails[1 + (last & 1)][i / 576][i % 576];
-    (void)last;
-    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, age = r / 32, k = r % 32; st_out->xhist[ch][age][k] = xring[ch][50 - age][k]; }
+
+  int n = 0;                                              /* frame iteration within this CTA */
+  for (int64_t f = c0 - warm; f < c1; f++, n++) {
+    const p3_frame fr = frames[f];
+    const int64_t o0 = (f - f_first) * 4;
+    const bool emit = !(warm && n == 0) && (fr.flags & P3_FRAME_DECODE);
+    __syncthreads();                                      /* previous frame completely done (stage F reads, s_scf, s_c1) */
+    if (tid < 64) {
+      reinterpret_cast<uint32_t *>(&s_scf[0][0])[tid] = pre_scf;
+      if (f + 1 < c1) pre_scf = __ldg(reinterpret_cast<const uint32_t *>(scf + (o0 + 4) * P3_SCF_STRIDE) + tid);
+    }
+    if (tid < 4) {                                        /* effective count1 (Q6), as in k_requant */
+      const uint32_t gr = tid >> 1, ch = tid & 1;
+      int32_t c = 0;
+      if (ch < nch) {
+        const uint32_t back = gcs[4 * f + tid].w3;
+        if (back == 0) c = count1[o0 + tid];
+        else if ((int64_t)back <= f - f_first) c = count1[o0 + tid - 4 * (int64_t)back];
+        else c = st_in->count1[gr][ch];
+      }
+      s_c1[tid] = c;
+      if (f == f_end - 1) st_out->count1[gr][ch] = c;
+    }
+    synth_frame<false>(S, fr, gcs, T, f, n, nch, s_scf, pre, f + 1 < c1 ? isw + (o0 + 4) * 288 : NULL, emit, pcm, ce, co, ia, ib,
+                       xr_tap ? xr_tap + o0 * 576 : NULL, y_tap ? y_tap + o0 * 576 : NULL);
+  }
+  __syncthreads();
+  if (c1 == f_end) synth_store_state(S, n - 1, st_out);
+}
+
+/* =============================================================================================
+ * k_decode_fused -- the whole path in ONE persistent kernel (FAST mode, default).
+ *
+ * Each CTA owns a contiguous run of frames and alternates two phases over groups of FG frames:
+ *   H  (Huffman, K1): gather the group's main data into the shared-memory bit reservoir, one thread per
+ *      granule-channel decodes scalefactors + spectra; the spectra go to a PRIVATE scratch row block in
+ *      global memory that the same CTA re-reads a few microseconds later and overwrites for its next
+ *      group -- with ~600 resident CTAs x 74 KB the scratch lives in the 126 MB L2 and practically never
+ *      reaches HBM; scalefactors and count1 stay in shared memory.
+ *   S  (synthesis, stages A..F of synth_frame): requantize .. PCM for the group's frames, filter state
+ *      (IMDCT tail, DCT history) carried in shared memory from group to group.
+ * HBM traffic is therefore the compressed stream + descriptors in and PCM out: the algorithmic bytes.
+ * CTAs drift apart in phase, so the latency-bound Huffman phase of one CTA overlaps the FMA-bound
+ * synthesis of the others on the same SM.
+ * Run boundaries are placed (identically by both neighbours) at the first frame at or after the even
+ * split point whose own and preceding frame have no zero-length part, so the stale-count1 chain (Q6)
+ * never reaches across a boundary; each run but the first is primed by the frame in front of it.
+ * ============================================================================================= */
+#define FG 16                      /* frames per group: 64 Huffman threads, 74 KB of scratch */
+
+__device__ __forceinline__ bool frame_clean(const p3_gc *__restrict__ gcs, int64_t f)
+{
+  return (gcs[4 * f].w3 | gcs[4 * f + 1].w3 | gcs[4 * f + 2].w3 | gcs[4 * f + 3].w3) == 0;
+}
+/* first frame of run k of B over frames [f_first, f_end) */
+__device__ __forceinline__ int64_t run_start(const p3_gc *__restrict__ gcs, int64_t f_first, int64_t f_end, int64_t k, int64_t B)
+{
+  if (k <= 0) return f_first;
+  if (k >= B) return f_end;
+  const int64_t nf = f_end - f_first;
+  int64_t f = f_first + nf * k / B;
+  const int64_t lim = f_first + nf * (k + 1) / B;
+  for (int64_t g = f; g < lim && g < f + 256; g++)
+    if (g > f_first && frame_clean(gcs, g - 1) && frame_clean(gcs, g)) return g;
+  return f;                                                /* no clean frame nearby: keep the even split */
+}
+
+extern "C" __global__ void __launch_bounds__(FT, 4)
+k_decode_fused(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
+               const p3_tables *__restrict__ T, const uint8_t *__restrict__ tail, int64_t f_first, int64_t f_end,
+               uint32_t k1_words, int16_t *__restrict__ scratch, const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out,
+               int16_t *__restrict__ pcm)
+{
+  extern __shared__ __align__(16) uint8_t dsm[];
+  /* ---- persistent part ---- */
+  float (*xring)[XSLOTS][XPITCH] = reinterpret_cast<float (*)[XSLOTS][XPITCH]>(dsm);
+  float (*tail2)[576] = reinterpret_cast<float (*)[576]>(dsm + sizeof(float) * 2 * XSLOTS * XPITCH);          /* tails[2]: carried IMDCT tail */
+  uint8_t *p = reinterpret_cast<uint8_t *>(tail2) + sizeof(float) * 2 * 576;
+  uint8_t (*scfg)[P3_SCF_STRIDE] = reinterpret_cast<uint8_t (*)[P3_SCF_STRIDE]>(p); p += FG * 4 * P3_SCF_STRIDE;   /* scalefactors of the group */
+  int32_t *c1g = reinterpret_cast<int32_t *>(p); p += FG * 4 * 4;                                                /* count1 of the group, made effective in place */
+  float (*s_scale)[40] = reinterpret_cast<float (*)[40]>(p); p += 4 * 40 * 4;
+  gcpar *s_par = reinterpret_cast<gcpar *>(p); p += 4 * sizeof(gcpar);
+  uint16_t *s_reo = reinterpret_cast<uint16_t *>(p); p += 576 * 2;
+  uint8_t *s_sfb_l = p; p += 576; uint8_t *s_sfbw_s = p; p += 576;
+  int32_t *s_c1 = reinterpret_cast<int32_t *>(p); p += 16; int32_t *s_eff = reinterpret_cast<int32_t *>(p); p += 16;
+  uint32_t *s_sfreq = reinterpret_cast<uint32_t *>(p); p += 8;
+  p = dsm + ((p - dsm + 15) & ~(size_t)15);
+  int64_t *s_fb = reinterpret_cast<int64_t *>(p); p += 16;
+  /* ---- phase-local part: synthesis buffers and the Huffman buffers share the same bytes ---- */
+  uint8_t *u = p;
+  float (*xs)[576] = reinterpret_cast<float (*)[576]>(u);                       /* [4] */
+  float (*tails01)[2][576] = reinterpret_cast<float (*)[2][576]>(u + 4 * 576 * 4);   /* tails[0], tails[1] */
+  int16_t (*isbuf)[576] = reinterpret_cast<int16_t (*)[576]>(u + 8 * 576 * 4);  /* [4] */
+  uint32_t *sw = reinterpret_cast<uint32_t *>(u);                               /* bit reservoir */
+  uint32_t *ring = sw + k1_words;                                               /* [8][FG*4] output staging */
+  uint16_t *lut = reinterpret_cast<uint16_t *>(ring + 8 * FG * 4);
+
+  const int tid = threadIdx.x;
+  const int64_t B = gridDim.x;
+  const int64_t r0 = run_start(gcs, f_first, f_end, blockIdx.x, B), r1 = run_start(gcs, f_first, f_end, blockIdx.x + 1, B);
+  if (r0 >= r1) return;
+  const int warm = r0 > f_first ? 1 : 0;
+  const uint32_t nch = frames[r0].nch;
+  int16_t *my = scratch + (size_t)blockIdx.x * FG * 4 * 576;
+
+  synth_sm S = {xs, NULL, xring, isbuf, s_sfb_l, s_sfbw_s, s_reo, s_par, s_scale, s_c1, s_sfreq, tails01, tail2};
+  float ce[8], co[8]; int ia, ib;
+  synth_window_coeffs(T, ce, co, ia, ib);
+  synth_load_state(S, warm ? NULL : st_in);
+  if (tid < 4) s_eff[tid] = warm ? 0 : st_in->count1[tid >> 1][tid & 1];
+  __syncthreads();
+
+  int n = 0;
+  for (int64_t F0 = r0 - warm; F0 < r1; F0 += FG) {
+    const int64_t F1 = min(F0 + (int64_t)FG, r1);
+    const int ngc = (int)(F1 - F0) * 4;
+    /* ================= phase H ================= */
+    for (uint32_t i = tid; i < (T->hlut_used + 1) / 2; i += FT) reinterpret_cast<uint32_t *>(lut)[i] = reinterpret_cast<const uint32_t *>(T->hlut)[i];
+    for (uint32_t i = tid; i < k1_words; i += FT) sw[i] = 0;
+    for (uint32_t i = tid; i < FG * 4 * P3_SCF_STRIDE / 4; i += FT) reinterpret_cast<uint32_t *>(&scfg[0][0])[i] = 0;
+    k1_gather(raw, frames, tail, F0, F1, sw, s_fb);
+    if (tid < ngc) {
+      const int64_t f = F0 + (tid >> 2);
+      const uint32_t gr = (tid >> 1) & 1, ch = tid & 1;
+      const p3_frame fr = frames[f]; const p3_gc g = gcs[4 * f + 2 * gr + ch];
+      k1_out ob; ob.ring = ring + tid; ob.stride = FG * 4; ob.pw = 0; ob.dst = reinterpret_cast<uint4 *>(my + (size_t)tid * 576);
+      const int32_t c = (int32_t)k1_decode_gc(sw, lut, T, gcs, fr, g, f, gr, ch, frames[F0].main_pos, ob, scfg[tid]);
+      /* bit 30: this part overwrites the slot's count1 (non-empty, or a flagged frame decoded as silence) */
+      const bool own = ch < fr.nch && (P3_GC_P23L(g) != 0 || (fr.flags & (P3_FRAME_NODATA | P3_FRAME_BAD)));
+      c1g[tid] = ch < fr.nch ? (c | (own ? 0x40000000 : 0)) : 0x40000000;
+    }
+    __syncthreads();
+    if (tid < 4) {                                        /* stale count1 chain (Q6): an empty part keeps the slot's previous value */
+      int32_t e = s_eff[tid];
+      for (int k = 0; k < ngc / 4; k++) {
+        const int32_t v = c1g[4 * k + tid];
+        e = (v & 0x40000000) ? (v & 0x3fffffff) : e;
+        c1g[4 * k + tid] = e;
+      }
+      s_eff[tid] = e;
+    }
+    /* ================= phase S ================= */
+    uint32_t pre[9];
+    const uint32_t *isw = reinterpret_cast<const uint32_t *>(my);
+    #pragma unroll
+    for (int k = 0; k < 9; k++) pre[k] = __ldcg(isw + tid + FT * k);
+    __syncthreads();
+    for (int64_t f = F0; f < F1; f++, n++) {
+      const p3_frame fr = frames[f];
+      const int k = (int)(f - F0);
+      const bool emit = !(warm && n == 0) && (fr.flags & P3_FRAME_DECODE);
+      __syncthreads();
+      if (tid < 4) s_c1[tid] = c1g[4 * k + tid];
+      synth_frame<true>(S, fr, gcs, T, f, n, nch, scfg + 4 * k, pre, f + 1 < F1 ? isw + (size_t)(k + 1) * 4 * 288 : NULL, emit, pcm, ce, co, ia, ib, NULL, NULL);
+    }
+    __syncthreads();
+  }
+  if (r1 == f_end) {
+    synth_store_state(S, n - 1, st_out);
+    if (tid < 4) st_out->count1[tid >> 1][tid & 1] = s_eff[tid];
   }
 }
+
+/* bytes of dynamic shared memory k_decode_fused needs for a K1 window of `k1_words` words */
+extern "C" size_t p3_fused_smem_bytes(uint32_t k1_words, uint32_t hlut_used)
+{
+  size_t pers = sizeof(float) * 2 * XSLOTS * XPITCH + sizeof(float) * 2 * 576 + FG * 4 * P3_SCF_STRIDE + FG * 4 * 4 + 4 * 40 * 4 + 4 * sizeof(gcpar)
+              + 576 * 2 + 576 + 576 + 16 + 16 + 8;
+  pers = (pers + 15) & ~(size_t)15; pers += 16;
+  size_t syn = 8 * 576 * 4 + 4 * 576 * 2;
+  size_t huf = (size_t)k1_words * 4 + 8 * FG * 4 * 4 + (size_t)hlut_used * 2 + 16;
+  return pers + (syn > huf ? syn : huf);
+}
+extern "C" int p3_fused_group_frames(void) { return FG; }

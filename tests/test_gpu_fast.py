@@ -55,3 +55,13 @@ def test_fast_partition_independent(fast_ctx):
         parts.append(fast_ctx.decode_parsed(p)); pos += p.consumed
     c = np.concatenate(parts)
     assert np.array_equal(a, c)
+
+
+@pytest.mark.parametrize("name", ["cfg3", "cfg4", "mono", "lowrate", "c1b"])
+def test_persistent_kernel_equals_two_kernel_path(fast_ctx, name):
+    """k_decode_fused (one persistent launch, spectra through L2-resident scratch) must give the same
+    bits as K1 + k_synth_fast (the path used when stage taps are requested)."""
+    s, _ = H.synth(700, seed=5, **VARIANTS[name])
+    fast_ctx.reset(); a = fast_ctx.decode(s, lookahead=0)                  # persistent kernel
+    fast_ctx.reset(); b, _ = fast_ctx.decode(s, lookahead=0, taps=True)    # two kernels
+    assert np.array_equal(a, b)
