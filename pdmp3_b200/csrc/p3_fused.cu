@@ -144,7 +144,7 @@ struct synth_sm {
  * frame's spectra (fetched one frame ahead), next_is: words of the next frame's spectra or NULL. */
 template <bool SCRATCH>
 __device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &fr, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
-    int64_t f, int n, uint32_t nch, const uint8_t (*scf4)[P3_SCF_STRIDE], uint32_t (&pre)[9], const uint32_t *next_is, bool emit,
+    int64_t f, int n, uint32_t nch, const uint8_t (*scf4)[P3_SCF_STRIDE], uint32_t (&pre)[9], const uint32_t *next_is, bool emit, const p3_gc &gmine,
     int16_t *__restrict__ pcm, const float (&ce)[8], const float (&co)[8], int ia, int ib, float *xr_tap, float *y_tap)
 {
   const int tid = threadIdx.x;
@@ -158,8 +158,8 @@ __device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &f
       for (int i = tid; i < 576; i += FT) { s_sfb_l[i] = T->line_sfb_l[fr.sfreq][i]; s_sfbw_s[i] = T->line_sfbw_s[fr.sfreq][i]; s_reo[i] = T->reorder_src[fr.sfreq][i]; }
       if (tid == 0) s_sfreq = fr.sfreq;
     }
-    /* the last 15 slots of the previous frame become the history of this one (stage F of that frame must be done) */
-    __syncthreads();
+    /* the last 15 slots of the previous frame become the history of this one (the caller's barrier has ended
+     * stage F of that frame) */
     for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, sl = r >> 5, k = r & 31; xring[ch][sl][k] = xring[ch][36 + sl][k]; }
     /* land the prefetched spectra in shared memory, start the next fetch */
     {
@@ -173,7 +173,7 @@ __device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &f
     }
     if (tid < 4) {                                        /* unpack the side info of this granule-channel once */
       const uint32_t gr = tid >> 1, ch = tid & 1;
-      const p3_gc g = gcs[4 * f + tid];
+      const p3_gc g = gmine;                               /* descriptor of granule-channel `tid`, fetched a frame ahead */
       gcpar p;
       const int32_t c = s_c1[tid];                        /* effective count1 (Q6), resolved by the caller */
       (void)gr;
@@ -368,7 +368,9 @@ __device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &f
           /* (int32)(sum*32767.0) with the scale folded into the window; x86 gives INT_MIN out of range */
           int32_t s = fabsf(sum) < 2147483648.0f ? __float2int_rz(sum) : (int32_t)0x80000000;
           s = max(-32767, min(32767, s));
-          __stcs(pcm + base + (int64_t)(9 * h + s9) * 32 * nch, (int16_t)s);       /* streaming: do not displace the L2-resident spectra */
+          int16_t *dst = pcm + base + (int64_t)(9 * h + s9) * 32 * nch;
+          if (SCRATCH) __stcs(dst, (int16_t)s);                                /* persistent kernel: do not displace the L2-resident spectra */
+          else *dst = (int16_t)s;                                              /* the two channels of a sector meet in L2 */
         }
       }
     }
@@ -451,11 +453,17 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
     for (int k = 0; k < 9; k++) pre[k] = __ldg(isw + o0 * 288 + tid + FT * k);
     if (tid < 64) pre_scf = __ldg(reinterpret_cast<const uint32_t *>(scf + o0 * P3_SCF_STRIDE) + tid);
   }
+  /* second half of the p3_frame record (nch, mode, mode_ext, sfreq, scfsi, flags, pcm_index), one frame ahead */
+  uint4 frn = __ldg(reinterpret_cast<const uint4 *>(frames + (c0 - warm)) + 1);
+  p3_gc gnext = {0, 0, 0, 0}; int32_t cnext = 0;        /* threads 0..3: side info and count1 of their granule-channel, one frame ahead */
+  if (tid < 4) { gnext = gcs[4 * (c0 - warm) + tid]; cnext = count1[(c0 - warm - f_first) * 4 + tid]; }
   __syncthreads();
 
   int n = 0;                                              /* frame iteration within this CTA */
   for (int64_t f = c0 - warm; f < c1; f++, n++) {
-    const p3_frame fr = frames[f];
+    p3_frame fr;
+    *(reinterpret_cast<uint4 *>(&fr) + 1) = frn;
+    if (f + 1 < c1) frn = __ldg(reinterpret_cast<const uint4 *>(frames + f + 1) + 1);
     const int64_t o0 = (f - f_first) * 4;
     const bool emit = !(warm && n == 0) && (fr.flags & P3_FRAME_DECODE);
     __syncthreads();                                      /* previous frame completely done (stage F reads, s_scf, s_c1) */
@@ -463,19 +471,21 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       reinterpret_cast<uint32_t *>(&s_scf[0][0])[tid] = pre_scf;
       if (f + 1 < c1) pre_scf = __ldg(reinterpret_cast<const uint32_t *>(scf + (o0 + 4) * P3_SCF_STRIDE) + tid);
     }
+    const p3_gc gcur = gnext;
     if (tid < 4) {                                        /* effective count1 (Q6), as in k_requant */
       const uint32_t gr = tid >> 1, ch = tid & 1;
       int32_t c = 0;
       if (ch < nch) {
-        const uint32_t back = gcs[4 * f + tid].w3;
-        if (back == 0) c = count1[o0 + tid];
+        const uint32_t back = gcur.w3;
+        if (back == 0) c = cnext;
         else if ((int64_t)back <= f - f_first) c = count1[o0 + tid - 4 * (int64_t)back];
         else c = st_in->count1[gr][ch];
       }
       s_c1[tid] = c;
       if (f == f_end - 1) st_out->count1[gr][ch] = c;
+      if (f + 1 < c1) { gnext = gcs[4 * (f + 1) + tid]; cnext = count1[o0 + 4 + tid]; }
     }
-    synth_frame<false>(S, fr, gcs, T, f, n, nch, s_scf, pre, f + 1 < c1 ? isw + (o0 + 4) * 288 : NULL, emit, pcm, ce, co, ia, ib,
+    synth_frame<false>(S, fr, gcs, T, f, n, nch, s_scf, pre, f + 1 < c1 ? isw + (o0 + 4) * 288 : NULL, emit, gcur, pcm, ce, co, ia, ib,
                        xr_tap ? xr_tap + o0 * 576 : NULL, y_tap ? y_tap + o0 * 576 : NULL);
   }
   __syncthreads();
@@ -604,8 +614,9 @@ k_decode_fused(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ fra
       const int k = (int)(f - F0);
       const bool emit = !(warm && n == 0) && (fr.flags & P3_FRAME_DECODE);
       __syncthreads();
-      if (tid < 4) s_c1[tid] = c1g[4 * k + tid];
-      synth_frame<true>(S, fr, gcs, T, f, n, nch, scfg + 4 * k, pre, f + 1 < F1 ? isw + (size_t)(k + 1) * 4 * 288 : NULL, emit, pcm, ce, co, ia, ib, NULL, NULL);
+      p3_gc gcur = {0, 0, 0, 0};
+      if (tid < 4) { s_c1[tid] = c1g[4 * k + tid]; gcur = gcs[4 * f + tid]; }
+      synth_frame<true>(S, fr, gcs, T, f, n, nch, scfg + 4 * k, pre, f + 1 < F1 ? isw + (size_t)(k + 1) * 4 * 288 : NULL, emit, gcur, pcm, ce, co, ia, ib, NULL, NULL);
     }
     __syncthreads();
   }
