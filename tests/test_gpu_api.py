@@ -105,3 +105,18 @@ def test_api_codes_and_options():
     assert rc == P.PDMP3_NEW_FORMAT
     assert d2.getformat()[1:3] == (44100, 2)
     d2.close(); d.close()
+
+
+def test_cli_entry_writes_raw_file(tmp_path):
+    """pdmp3(char*const*) (pdmp3.c:2540-2589): decodes files to <file>.raw with the reference's read/feed loop."""
+    import pdmp3_b200
+    s, _ = H.synth(50, seed=9, **H.CONFIGS["cfg1_128k_stereo_long"])
+    f = tmp_path / "a.mp3"; f.write_bytes(s.tobytes())
+    L = pdmp3_b200.lib()
+    argv = (C.c_char_p * 2)(str(f).encode(), None)
+    L.pdmp3.argtypes = [C.POINTER(C.c_char_p)]; L.pdmp3.restype = None
+    L.pdmp3(argv)
+    raw = np.fromfile(str(f) + ".raw", dtype=np.int16)
+    o = H.oracle_decode(s, lookahead=1152, taps=False)["pcm"]
+    assert raw.size == o.size
+    assert np.abs(raw.astype(np.int32) - o.reshape(-1).astype(np.int32)).max() <= 1      # default FAST mode

@@ -65,3 +65,24 @@ def test_persistent_kernel_equals_two_kernel_path(fast_ctx, name):
     fast_ctx.reset(); a = fast_ctx.decode(s, lookahead=0)                  # persistent kernel
     fast_ctx.reset(); b, _ = fast_ctx.decode(s, lookahead=0, taps=True)    # two kernels
     assert np.array_equal(a, b)
+
+
+def test_one_million_frames_properties(fast_ctx):
+    """BASELINE configs[2] at full size (1 000 000 frames = 15 625-frame block x 64, 4.6 GB of PCM): tiles 2..64
+    decode to identical PCM (same input, same carried state -> no dependence on position, CTA or chunk), and
+    tile 2 is within 1 LSB of the bit-exact decode of the same data."""
+    import pdmp3_b200
+    blk, _ = H.synth(15625, seed=1, **H.CONFIGS["cfg3_320k_js_ms"])
+    s = np.tile(blk, 64)
+    fast_ctx.reset()
+    pcm = fast_ctx.decode(s, lookahead=0)
+    assert pcm.shape == (1000000, 1152, 2)
+    tiles = pcm.reshape(64, 15625, 1152, 2)
+    ref = tiles[1]
+    for k in range(2, 64):
+        assert np.array_equal(tiles[k], ref), "tile %d" % k
+    ex = pdmp3_b200.Context(0, pdmp3_b200.MODE_EXACT)
+    two = ex.decode(np.tile(blk, 2), lookahead=0)[15625:]
+    ex.close()
+    d = np.abs(two.astype(np.int32) - ref.astype(np.int32))
+    assert d.max() <= 1 and (d == 0).mean() > 0.9
