@@ -286,7 +286,7 @@ int p3o_decode(const uint8_t *raw, const p3_frame *fr, const p3_gc *gc, int64_t 
   ostate *S = calloc(1, sizeof *S);
   /* header-stripped main-data stream == what Get_Main_Data assembles frame by frame (1096-1122) */
   uint64_t total = n_frames ? fr[n_frames - 1].main_pos + fr[n_frames - 1].main_size - fr[0].main_pos : 0, base = n_frames ? fr[0].main_pos : 0;
-  uint8_t *ms = calloc(total + 16, 1);
+  uint8_t *ms = calloc(total + 4096, 1);   /* slack: a corrupt part may be read far past its end */
   for (int64_t f = 0; f < n_frames; f++) memcpy(ms + (fr[f].main_pos - base), raw + fr[f].main_off, fr[f].main_size);
   float (*is)[2][576] = malloc(sizeof(float) * 4 * 576);
   for (int64_t f = 0; f < n_frames; f++) {
