@@ -230,7 +230,7 @@ static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_
     if (span > maxg) maxg = span;
   }
   c->k1_smem_words = (uint32_t)((512 + maxg + 16 + 3) / 4 + 3) & ~3u;   /* multiple of 16 bytes: the staging areas behind it hold uint4 */
-  if ((size_t)c->k1_smem_words * 4 + sizeof(((p3_tables *)0)->hlut) + 24 * K1_THREADS * 4 > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
+  if ((size_t)c->k1_smem_words * 4 + sizeof(((p3_tables *)0)->hlut) + 4 * K1_THREADS * 4 > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
   memcpy(sl->h_tail, c->h_tail, 512);
   CK(cudaMemcpyAsync(sl->raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(sl->frames.p, b->frames, (size_t)nf * sizeof(p3_frame), cudaMemcpyHostToDevice, st));
@@ -257,7 +257,7 @@ static int run_chunk(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, cudaEvent_t
   p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
   CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));   /* fields a launch does not rewrite carry over */
   if (ev) CK(cudaEventRecord(ev[0], c->stream));
-  size_t smem1 = (size_t)c->k1_smem_words * 4 + (8 + 16) * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
+  size_t smem1 = (size_t)c->k1_smem_words * 4 + 4 * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
   k_huffman<<<(unsigned)((nf + K1_FPB - 1) / K1_FPB), K1_THREADS, smem1, c->stream>>>(
       (const uint8_t *)sl->raw.p, fr, gc, c->d_tables, sl->d_tail, f0, f1, c->k1_smem_words,
       (int16_t *)c->is16.p, (int32_t *)c->count1.p, (uint8_t *)c->scf.p);
@@ -293,7 +293,7 @@ static int run_chunk(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, cudaEvent_t
 static int run_pingpong(p3_ctx *c, p3_slot *sl)
 {
   const p3_frame *fr = (const p3_frame *)sl->frames.p; const p3_gc *gc = (const p3_gc *)sl->gcs.p;
-  size_t smem1 = (size_t)c->k1_smem_words * 4 + (8 + 16) * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
+  size_t smem1 = (size_t)c->k1_smem_words * 4 + 4 * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
   CK(cudaEventRecord(c->fork, c->stream));                 /* everything queued on the kernel stream so far (uploads) comes first */
   CK(cudaStreamWaitEvent(c->s_k1, c->fork, 0));
   int step = 0;

@@ -556,8 +556,8 @@ k_decode_fused(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ fra
   float (*tails01)[2][576] = reinterpret_cast<float (*)[2][576]>(u + 4 * 576 * 4);   /* tails[0], tails[1] */
   int16_t (*isbuf)[576] = reinterpret_cast<int16_t (*)[576]>(u + 8 * 576 * 4);  /* [4] */
   uint32_t *sw = reinterpret_cast<uint32_t *>(u);                               /* bit reservoir */
-  uint32_t *ring = sw + k1_words;                                               /* [8][FG*4] output staging */
-  uint16_t *lut = reinterpret_cast<uint16_t *>(ring + 8 * FG * 4);
+  uint32_t *ring = sw + k1_words;                                               /* [4][FG*4] output staging */
+  uint16_t *lut = reinterpret_cast<uint16_t *>(ring + 4 * FG * 4);
 
   const int tid = threadIdx.x;
   const int64_t B = gridDim.x;
@@ -633,7 +633,7 @@ extern "C" size_t p3_fused_smem_bytes(uint32_t k1_words, uint32_t hlut_used)
               + 576 * 2 + 576 + 576 + 16 + 16 + 8;
   pers = (pers + 15) & ~(size_t)15; pers += 16;
   size_t syn = 8 * 576 * 4 + 4 * 576 * 2;
-  size_t huf = (size_t)k1_words * 4 + 8 * FG * 4 * 4 + (size_t)hlut_used * 2 + 16;
+  size_t huf = (size_t)k1_words * 4 + 4 * FG * 4 * 4 + (size_t)hlut_used * 2 + 16;
   return pers + (syn > huf ? syn : huf);
 }
 extern "C" int p3_fused_group_frames(void) { return FG; }

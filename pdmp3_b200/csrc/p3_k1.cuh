@@ -55,25 +55,25 @@ __device__ __forceinline__ uint32_t k1_pair(k1_bits &bb, const uint16_t *lut, ui
   return (uint32_t)(x & 0xffff) | ((uint32_t)y << 16);
 }
 
-/* Per-thread output staging: 8 words (16 spectral values = one 32-byte sector) are collected in
+/* Per-thread output staging: 8 words (16 spectral values = half a 32-byte sector) are collected in
  * shared memory, transposed [word][thread] so that neither the word writes nor the flush conflict,
- * and leave as two 16-byte stores -- every DRAM sector of the spectra is written exactly once. */
+ * and leave as one 16-byte store; the two halves of a sector meet in L2, so every DRAM sector of the
+ * spectra is written once. */
 struct k1_out {
   uint32_t *ring;                 /* &ring[0][tid] */
   uint32_t stride;                /* threads sharing the staging area */
   uint4 *dst;                     /* this granule-channel's 1152-byte row */
   uint32_t pw;                    /* words emitted so far */
-  __device__ __forceinline__ void flush(uint32_t sector)
+  __device__ __forceinline__ void flush(uint32_t q)          /* q: index of the 16-byte quarter-row chunk */
   {
-    uint4 a, b;
+    uint4 a;
     a.x = ring[0]; a.y = ring[stride]; a.z = ring[2 * stride]; a.w = ring[3 * stride];
-    b.x = ring[4 * stride]; b.y = ring[5 * stride]; b.z = ring[6 * stride]; b.w = ring[7 * stride];
-    dst[2 * sector] = a; dst[2 * sector + 1] = b;
+    dst[q] = a;
   }
   __device__ __forceinline__ void put(uint32_t word)
   {
-    ring[(pw & 7u) * stride] = word;
-    if ((pw & 7u) == 7u) flush(pw >> 3);
+    ring[(pw & 3u) * stride] = word;
+    if ((pw & 3u) == 3u) flush(pw >> 2);
     pw++;
   }
 };
@@ -219,24 +219,23 @@ __device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw, const uint1
       if (pos > bit_pos_end + 1) is_pos = is_pos >= 4 ? is_pos - 4 : 0;    /* pdmp3.c:2105-2106 */
       c1 = is_pos;
     }
-    /* ---- close the row: words [c1/2, 288) are the rzero region ---- */
+    /* ---- close the row: words [c1/2, 288) are the rzero region; 72 chunks of 4 words ---- */
     {
-      const uint32_t pw_hi = ob.pw, pw_new = c1 >> 1, S = pw_hi & ~7u;
-      uint32_t zs;                                        /* first sector that is entirely zero */
+      const uint32_t pw_hi = ob.pw, pw_new = c1 >> 1, S = pw_hi & ~3u;
+      uint32_t zs;                                        /* first chunk that is entirely zero */
       if (pw_new >= S) {
         if (S < 288) {
-          for (uint32_t k = pw_new & 7u; k < 8; k++) ob.ring[k * ob.stride] = 0;
-          if (pw_new == S) { for (uint32_t k = 0; k < 8; k++) ob.ring[k * ob.stride] = 0; }
-          ob.flush(S >> 3);
+          for (uint32_t k = pw_new & 3u; k < 4; k++) ob.ring[k * ob.stride] = 0;
+          ob.flush(S >> 2);
         }
-        zs = (S >> 3) + 1;
-      } else {                                            /* rolled back into a sector that already left */
+        zs = (S >> 2) + 1;
+      } else {                                            /* rolled back into a chunk that already left */
         uint32_t *dw = reinterpret_cast<uint32_t *>(ob.dst);
         for (uint32_t k = pw_new; k < S; k++) dw[k] = 0;
-        zs = S >> 3;
+        zs = S >> 2;
       }
       const uint4 z = make_uint4(0, 0, 0, 0);
-      for (uint32_t sct = zs; sct < 36; sct++) { ob.dst[2 * sct] = z; ob.dst[2 * sct + 1] = z; }
+      for (uint32_t q = zs; q < 72; q++) ob.dst[q] = z;
     }
   }
   return c1;

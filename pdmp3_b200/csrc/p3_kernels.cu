@@ -35,9 +35,8 @@ k_huffman(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames, 
 {
   extern __shared__ uint32_t sm[];
   uint32_t *sw = sm;                                     /* main-data words, big-endian */
-  uint32_t *ring = sm + smem_words;                      /* [8][K1_THREADS] output staging */
-  uint32_t *scfw = ring + 8 * K1_THREADS;                /* [K1_THREADS][16] scalefactor bytes */
-  uint16_t *lut = reinterpret_cast<uint16_t *>(scfw + 16 * K1_THREADS);
+  uint32_t *ring = sm + smem_words;                      /* [4][K1_THREADS] output staging */
+  uint16_t *lut = reinterpret_cast<uint16_t *>(ring + 4 * K1_THREADS);
   __shared__ int64_t s_fb;
 
   const int64_t F0 = f_first + (int64_t)blockIdx.x * K1_FPB;
@@ -47,26 +46,41 @@ k_huffman(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames, 
   for (uint32_t i = threadIdx.x; i < (T->hlut_used + 1) / 2; i += blockDim.x)
     reinterpret_cast<uint32_t *>(lut)[i] = reinterpret_cast<const uint32_t *>(T->hlut)[i];
   for (uint32_t i = threadIdx.x; i < smem_words; i += blockDim.x) sw[i] = 0;
-  for (uint32_t i = threadIdx.x; i < 16 * K1_THREADS; i += blockDim.x) scfw[i] = 0;
   k1_gather(raw, frames, tail, F0, F1, sw, &s_fb);
 
-  const uint32_t gi = threadIdx.x;                        /* granule-channel within the group */
+  /* Lanes of a warp run in lock step, so a warp takes as long as its longest part.  Parts are therefore
+   * handed out sorted by big_values (bitonic sort of the group's 128 keys in shared memory): each warp
+   * gets parts of similar length.  Outputs are addressed by part, so nothing downstream changes. */
+  __shared__ uint32_t s_key[K1_THREADS];
+  {
+    const int64_t fk = F0 + (threadIdx.x >> 2);
+    uint32_t bv = 0;
+    if (fk < F1) bv = P3_GC_BIGV(gcs[4 * fk + (threadIdx.x & 3)]);
+    s_key[threadIdx.x] = ((511u - bv) << 8) | threadIdx.x;          /* descending big_values, part index in the low byte */
+    __syncthreads();
+    for (uint32_t k = 2; k <= K1_THREADS; k <<= 1)
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        const uint32_t i = threadIdx.x, l = i ^ j;
+        if (l > i) {
+          const uint32_t a = s_key[i], b = s_key[l];
+          if (((i & k) == 0) == (a > b)) { s_key[i] = b; s_key[l] = a; }
+        }
+        __syncthreads();
+      }
+  }
+  const uint32_t gi = s_key[threadIdx.x] & 0xffu;         /* granule-channel within the group handled by this thread */
   const int64_t f = F0 + (gi >> 2);
   const int64_t o_cta = (F0 - f_first) * 4;
   if (f < F1) {
     const uint32_t gr = (gi >> 1) & 1, ch = gi & 1;
     const int64_t o = o_cta + gi;
     const p3_frame fr = frames[f]; const p3_gc g = gcs[4 * f + 2 * gr + ch];
-    k1_out ob; ob.ring = ring + gi; ob.stride = K1_THREADS; ob.pw = 0; ob.dst = reinterpret_cast<uint4 *>(is_out + o * 576);
-    count1_out[o] = (int32_t)k1_decode_gc(sw, lut, T, gcs, fr, g, f, gr, ch, base0, ob, reinterpret_cast<uint8_t *>(scfw + 16 * gi));
-  }
-  __syncthreads();
-  /* scalefactors of the whole group, coalesced */
-  {
-    const int64_t ngc = (F1 - F0) * 4;
-    uint4 *dst = reinterpret_cast<uint4 *>(scf_out + o_cta * P3_SCF_STRIDE);
-    const uint4 *srcv = reinterpret_cast<const uint4 *>(scfw);
-    for (int64_t i = threadIdx.x; i < ngc * 4; i += blockDim.x) dst[i] = srcv[i];
+    k1_out ob; ob.ring = ring + threadIdx.x; ob.stride = K1_THREADS; ob.pw = 0; ob.dst = reinterpret_cast<uint4 *>(is_out + o * 576);
+    /* scalefactor bytes go straight to this part's 64-byte row (byte stores merge in L2): staging them
+     * in shared memory would cost 8 KB per CTA, i.e. one resident CTA per SM */
+    uint8_t *scf = scf_out + o * P3_SCF_STRIDE;
+    for (int q = 0; q < P3_SCF_STRIDE / 16; q++) reinterpret_cast<uint4 *>(scf)[q] = make_uint4(0, 0, 0, 0);
+    count1_out[o] = (int32_t)k1_decode_gc(sw, lut, T, gcs, fr, g, f, gr, ch, base0, ob, scf);
   }
 }
 
