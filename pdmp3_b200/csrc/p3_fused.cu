@@ -208,86 +208,83 @@ __device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &f
     }
     __syncthreads();
 
-    /* ---- A: requantize + reorder (exact arithmetic of pdmp3.c:2121-2152) ---- */
-    #pragma unroll 1
-    for (int gcl = 0; gcl < 4; gcl++) {
-      const gcpar p = s_par[gcl];
-      if (!p.live) { for (int d = tid; d < 576; d += FT) xs[gcl][d] = 0.0f; continue; }
-      const int16_t *isp = isbuf[gcl];
-      const float *scl = s_scale[gcl];
-      #pragma unroll
-      for (int it = 0; it < 5; it++) {
-        const int d = tid + FT * it;
-        if (d < 576) {
-          float r;
-          if (d >= p.first_short) {
-            const uint32_t s = s_reo[d], sw = s_sfbw_s[s];
-            r = fq_requant(T->pow43, isp[s], scl[3 * (sw & 15u) + (sw >> 4)]);
-          } else r = fq_requant(T->pow43, isp[d], scl[s_sfb_l[d]]);
-          xs[gcl][d] = r;
+    /* ---- A+B: requantize + reorder (exact arithmetic of pdmp3.c:2121-2152) and stereo (pdmp3.c:1916-1971):
+     *      a thread requantizes line d of BOTH channels of a granule and couples them in registers ---- */
+    {
+      const bool st_on = nch == 2 && fr.mode == 1 && fr.mode_ext != 0;
+      const bool is_on = st_on && (fr.mode_ext & 1);
+      #pragma unroll 1
+      for (int gr = 0; gr < 2; gr++) {
+        const gcpar p0 = s_par[2 * gr], p1 = s_par[2 * gr + 1];
+        const int16_t *is0 = isbuf[2 * gr], *is1 = isbuf[2 * gr + 1];
+        const float *sc0 = s_scale[2 * gr], *sc1 = s_scale[2 * gr + 1];
+        const uint32_t cl = (uint32_t)p0.c1, c1r = (uint32_t)p1.c1;
+        const uint32_t msn = (st_on && (fr.mode_ext & 2)) ? (cl > c1r ? c1r : cl) : 0u;     /* min(count1), sic (pdmp3.c:1920) */
+        const uint32_t first_short0 = p0.first_short;
+        const bool sh0 = first_short0 < 576;
+        #pragma unroll
+        for (int it = 0; it < 5; it++) {
+          const uint32_t d = tid + FT * it;
+          if (d >= 576) break;
+          float l = 0.0f, r = 0.0f;
+          if (p0.live) {
+            if (d >= p0.first_short) { const uint32_t s = s_reo[d], sw = s_sfbw_s[s]; l = fq_requant(T->pow43, is0[s], sc0[3 * (sw & 15u) + (sw >> 4)]); }
+            else l = fq_requant(T->pow43, is0[d], sc0[s_sfb_l[d]]);
+          }
+          if (p1.live) {
+            if (d >= p1.first_short) { const uint32_t s = s_reo[d], sw = s_sfbw_s[s]; r = fq_requant(T->pow43, is1[s], sc1[3 * (sw & 15u) + (sw >> 4)]); }
+            else r = fq_requant(T->pow43, is1[d], sc1[s_sfb_l[d]]);
+          }
+          if (d < msn) {
+            /* float sum times a double constant, rounded once to float (pdmp3.c:168,1923-1926) */
+            const float a = __fadd_rn(l, r), b = __fsub_rn(l, r);
+            l = __double2float_rn(__dmul_rn((double)a, 0.70710678118654752440));
+            r = __double2float_rn(__dmul_rn((double)b, 0.70710678118654752440));
+          } else if (is_on) {
+            if (d >= first_short0) {
+              /* short-block intensity (pdmp3.c:2190-2220) in reordered position; Q4: assignment through an `unsigned` */
+              const uint32_t sw = s_sfbw_s[d], sfb = sw & 15u, win = sw >> 4;
+              if (sfb < 12 && 3u * T->sfb_s[fr.sfreq][sfb] >= c1r && scf4[2 * gr][P3_SCF_S_OFF + 3 * sfb + win] != 7) {
+                const float x = (float)(unsigned)(long long)l; l = x; r = x;
+              }
+            } else {
+              const uint32_t sfb = s_sfb_l[d], lim = sh0 ? 8u : 21u;                     /* mixed: long sfb 0..7 only (pdmp3.c:1944) */
+              if (sfb < lim && T->sfb_l[fr.sfreq][sfb] >= c1r) {
+                const uint32_t pp = scf4[2 * gr][sfb];                                   /* channel-0 scalefactor, sic (pdmp3.c:2163) */
+                if (pp != 7) { const float x = l; l = __fmul_rn(FC.is_l[pp & 7], x); r = __fmul_rn(FC.is_r[pp & 7], x); }
+              }
+            }
+          }
+          xs[2 * gr][d] = l; xs[2 * gr + 1][d] = r;
         }
       }
     }
     __syncthreads();
 
-    /* ---- B: stereo (pdmp3.c:1916-1971), both granules ---- */
-    if (nch == 2 && fr.mode == 1 && fr.mode_ext != 0) {
+    /* ---- C: antialias (pdmp3.c:1706-1732).  Normally folded into stage D (below); as a separate pass only
+     *      when the post-antialias spectra are tapped for the stage-level parity tests ---- */
+    if (xr_tap) {
       #pragma unroll 1
-      for (int gr = 0; gr < 2; gr++) {
-        const uint32_t cl = (uint32_t)s_par[2 * gr].c1, c1r = (uint32_t)s_par[2 * gr + 1].c1;
-        const uint32_t msn = (fr.mode_ext & 2) ? (cl > c1r ? c1r : cl) : 0u;
-        const uint32_t first_short0 = s_par[2 * gr].first_short;
-        const bool sh0 = first_short0 < 576;
-        const bool is_on = fr.mode_ext & 1;
+      for (int gcl = 0; gcl < 4; gcl++) {
+        const uint32_t sblim = s_par[gcl].live ? s_par[gcl].sblim : 0;
         #pragma unroll
-        for (int it = 0; it < 5; it++) {
-          const uint32_t i = tid + FT * it;
-          if (i >= 576) break;
-          float l = xs[2 * gr][i], r = xs[2 * gr + 1][i];
-          if (i < msn) {
-            float a = __fadd_rn(l, r), b = __fsub_rn(l, r);
-            l = __double2float_rn(__dmul_rn((double)a, 0.70710678118654752440));
-            r = __double2float_rn(__dmul_rn((double)b, 0.70710678118654752440));
-            xs[2 * gr][i] = l; xs[2 * gr + 1][i] = r;
-          } else if (is_on) {
-            if (i >= first_short0) {
-              const uint32_t sw = s_sfbw_s[i], sfb = sw & 15u, win = sw >> 4;
-              if (sfb < 12 && 3u * T->sfb_s[fr.sfreq][sfb] >= c1r && scf4[2 * gr][P3_SCF_S_OFF + 3 * sfb + win] != 7) {
-                float x = (float)(unsigned)(long long)l;                               /* Q4 */
-                xs[2 * gr][i] = x; xs[2 * gr + 1][i] = x;
-              }
-            } else {
-              const uint32_t sfb = s_sfb_l[i], lim = sh0 ? 8u : 21u;
-              if (sfb < lim && T->sfb_l[fr.sfreq][sfb] >= c1r) {
-                const uint32_t pp = scf4[2 * gr][sfb];
-                if (pp != 7) { xs[2 * gr][i] = __fmul_rn(FC.is_l[pp & 7], l); xs[2 * gr + 1][i] = __fmul_rn(FC.is_r[pp & 7], l); }
-              }
-            }
+        for (int it = 0; it < 2; it++) {
+          const uint32_t t = tid + FT * it, sb = 1 + (t >> 3), i = t & 7;
+          if (sb < sblim) {
+            const uint32_t li = 18 * sb - 1 - i, ui = 18 * sb + i;
+            const float a = xs[gcl][li], b = xs[gcl][ui];
+            xs[gcl][li] = __fsub_rn(__fmul_rn(a, FC.cs[i]), __fmul_rn(b, FC.ca[i]));
+            xs[gcl][ui] = __fadd_rn(__fmul_rn(b, FC.cs[i]), __fmul_rn(a, FC.ca[i]));
           }
         }
       }
       __syncthreads();
+      for (int e = tid; e < 4 * 576; e += FT) xr_tap[e] = (&xs[0][0])[e];
     }
 
-    /* ---- C: antialias (pdmp3.c:1706-1732): 31 boundaries x 8 butterflies per granule-channel ---- */
-    #pragma unroll 1
-    for (int gcl = 0; gcl < 4; gcl++) {
-      const uint32_t sblim = s_par[gcl].live ? s_par[gcl].sblim : 0;
-      #pragma unroll
-      for (int it = 0; it < 2; it++) {
-        const uint32_t t = tid + FT * it, sb = 1 + (t >> 3), i = t & 7;
-        if (sb < sblim) {
-          const uint32_t li = 18 * sb - 1 - i, ui = 18 * sb + i;
-          const float a = xs[gcl][li], b = xs[gcl][ui];
-          xs[gcl][li] = __fsub_rn(__fmul_rn(a, FC.cs[i]), __fmul_rn(b, FC.ca[i]));
-          xs[gcl][ui] = __fadd_rn(__fmul_rn(b, FC.cs[i]), __fmul_rn(a, FC.ca[i]));
-        }
-      }
-    }
-    __syncthreads();
-    if (xr_tap) for (int e = tid; e < 4 * 576; e += FT) xr_tap[e] = (&xs[0][0])[e];
-
-    /* ---- D: IMDCT + window; first half in place, second half to the tail buffer ---- */
+    /* ---- D: antialias + IMDCT + window; first half in place, second half to the tail buffer.
+     *      One warp = the 32 subbands of one granule-channel, so the butterflies across subband boundaries
+     *      only need the neighbour lanes' lines: read, __syncwarp(), then write in place. ---- */
     {
       const uint32_t gcl = tid >> 5, sb = tid & 31, gr = gcl >> 1, ch = gcl & 1;
       const gcpar p = s_par[gcl];
@@ -298,6 +295,18 @@ __device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &f
         float in[18];
         #pragma unroll
         for (int m = 0; m < 18; m++) in[m] = x[m];
+        if (!xr_tap) {
+          /* boundary below (with subband sb-1) turns lines 0..7, boundary above (with sb+1) lines 17..10 */
+          const bool lo = sb >= 1 && sb < p.sblim, hi = sb + 1 < p.sblim;
+          #pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const float below = lo ? x[-1 - i] : 0.0f, above = hi ? x[18 + i] : 0.0f;
+            const float u = in[i], l = in[17 - i];
+            if (lo) in[i] = __fadd_rn(__fmul_rn(u, FC.cs[i]), __fmul_rn(below, FC.ca[i]));       /* ub (pdmp3.c:1726) */
+            if (hi) in[17 - i] = __fsub_rn(__fmul_rn(l, FC.cs[i]), __fmul_rn(above, FC.ca[i]));   /* lb (pdmp3.c:1725) */
+          }
+        }
+        __syncwarp();
         if (bt != 2) {
           float t[18];
           dct4_18(in, t);
