@@ -44,7 +44,7 @@ def build_product(force=False, verbose=False):
         objs.append(o)
     for s in srcs_cu:
         o = os.path.join(bdir, s + ".o")
-        log = _run([nvcc] + NVCC_ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xptxas", "-v", "-Xcompiler", "-fPIC",
+        log = _run([nvcc] + NVCC_ARCH + ["-O3", "-lineinfo", "-std=c++17", "-diag-suppress", "550", "-Xptxas", "-v", "-Xcompiler", "-fPIC",
                     "-I", os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, s), "-o", o])
         if verbose:
             print(log)

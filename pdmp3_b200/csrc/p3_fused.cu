@@ -123,14 +123,16 @@ __device__ __forceinline__ float fq_requant(const float *__restrict__ pow43, int
   return __fmul_rn(scale, t3);
 }
 
-/* shared-memory working set of the synthesis stages (one frame = 4 granule-channels at a time) */
+/* shared-memory working set of the synthesis stages (one frame = 4 granule-channels at a time).
+ * Side info, scalefactors and band scales are double buffered (slot = frame parity) so that a frame's
+ * tables can be prepared while the previous frame is still in its transforms. */
 struct synth_sm {
   float (*xs)[576];                  /* [4] spectra -> subband samples, in place */
   float (*tails)[2][576];            /* [3] IMDCT second halves: [0] granule 0, [1]/[2] granule 1 of odd/even frames */
   float (*xring)[XSLOTS][XPITCH];    /* [2] 32-point DCT of 15 history + 36 new time slots per channel */
-  int16_t (*isbuf)[576];             /* [4] Huffman output of the current frame */
-  uint8_t *sfb_l, *sfbw_s; uint16_t *reo;   /* per-line helper tables of the current sample rate */
-  gcpar *par; float (*scale)[40]; int32_t *c1; uint32_t *sfreq;
+  int16_t (*isbuf)[576];             /* [4] Huffman output of the frame about to be requantized */
+  uint8_t *sfb_l, *sfbw_s; uint16_t *reo;   /* per-line helper tables of the batch's sample rate */
+  gcpar (*par)[4]; float (*scale)[4][40]; uint8_t (*scf)[4][P3_SCF_STRIDE];   /* [2] slots */
   float (*t01)[2][576]; float (*t2)[576];   /* fused kernel: tails[0..1] in phase-local memory, tails[2] persistent */
   __device__ __forceinline__ float *tail(int idx, int ch) const
   {
@@ -139,54 +141,45 @@ struct synth_sm {
   }
 };
 
-/* One frame through stages A..F.  n: frame counter of this CTA (selects the tail buffer), scf4: the frame's
- * 4 x 64 scalefactor bytes in shared memory, S.c1[4]: effective count1, pre[9]: this thread's share of the
- * frame's spectra (fetched one frame ahead), next_is: words of the next frame's spectra or NULL. */
-template <bool SCRATCH>
-__device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &fr, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
-    int64_t f, int n, uint32_t nch, const uint8_t (*scf4)[P3_SCF_STRIDE], uint32_t (&pre)[9], const uint32_t *next_is, bool emit, const p3_gc &gmine,
-    int16_t *__restrict__ pcm, const float (&ce)[8], const float (&co)[8], int ia, int ib, float *xr_tap, float *y_tap)
+#define SF_LOCALS \
+  const int tid = threadIdx.x; (void)tid; \
+  float (*xs)[576] = S.xs; float (*xring)[XSLOTS][XPITCH] = S.xring; int16_t (*isbuf)[576] = S.isbuf; \
+  uint8_t *s_sfb_l = S.sfb_l, *s_sfbw_s = S.sfbw_s; uint16_t *s_reo = S.reo; gcpar *s_par = S.par[slot]; \
+  float (*s_scale)[40] = S.scale[slot]; const uint8_t (*scf4)[P3_SCF_STRIDE] = S.scf[slot]; \
+  (void)xs; (void)xring; (void)isbuf; (void)s_sfb_l; (void)s_sfbw_s; (void)s_reo; (void)s_par; (void)s_scale; (void)scf4;
+
+/* per-line helper tables of sample rate `sf` (once per launch: a batch never mixes sample rates) */
+__device__ __forceinline__ void sf_load_luts(const synth_sm &S, const p3_tables *__restrict__ T, uint32_t sf)
+{
+  for (int i = threadIdx.x; i < 576; i += FT) { S.sfb_l[i] = T->line_sfb_l[sf][i]; S.sfbw_s[i] = T->line_sfbw_s[sf][i]; S.reo[i] = T->reorder_src[sf][i]; }
+}
+
+/* Land one frame's inputs in shared memory slot `slot`: spectra (from the registers they were prefetched into),
+ * scalefactor words, and the unpacked side info of the 4 granule-channels (threads 0..3; c1eff = effective count1, Q6). */
+__device__ __forceinline__ void sf_land(const synth_sm &S, int slot, const uint32_t (&pre)[9], uint32_t scfword, const p3_gc &g, int32_t c1eff, uint32_t nch)
 {
   const int tid = threadIdx.x;
-  const int j = tid & 31, wgr = (tid >> 5) & 1, wch = tid >> 6;
-  float (*xs)[576] = S.xs; float (*xring)[XSLOTS][XPITCH] = S.xring; int16_t (*isbuf)[576] = S.isbuf;
-  uint8_t *s_sfb_l = S.sfb_l, *s_sfbw_s = S.sfbw_s; uint16_t *s_reo = S.reo; gcpar *s_par = S.par; float (*s_scale)[40] = S.scale;
-  int32_t *s_c1 = S.c1;
-#define s_sfreq (*S.sfreq)
-    if (s_sfreq != fr.sfreq) {                            /* per-line helper tables of this sample rate */
-      __syncthreads();
-      for (int i = tid; i < 576; i += FT) { s_sfb_l[i] = T->line_sfb_l[fr.sfreq][i]; s_sfbw_s[i] = T->line_sfbw_s[fr.sfreq][i]; s_reo[i] = T->reorder_src[fr.sfreq][i]; }
-      if (tid == 0) s_sfreq = fr.sfreq;
-    }
-    /* the last 15 slots of the previous frame become the history of this one (the caller's barrier has ended
-     * stage F of that frame) */
-    for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, sl = r >> 5, k = r & 31; xring[ch][sl][k] = xring[ch][36 + sl][k]; }
-    /* land the prefetched spectra in shared memory, start the next fetch */
-    {
-      uint32_t *ib32 = reinterpret_cast<uint32_t *>(&isbuf[0][0]);
-      #pragma unroll
-      for (int k = 0; k < 9; k++) ib32[tid + FT * k] = pre[k];
-      if (next_is) {
-        #pragma unroll
-        for (int k = 0; k < 9; k++) pre[k] = SCRATCH ? __ldcg(next_is + tid + FT * k) : __ldg(next_is + tid + FT * k);
-      }
-    }
-    if (tid < 4) {                                        /* unpack the side info of this granule-channel once */
-      const uint32_t gr = tid >> 1, ch = tid & 1;
-      const p3_gc g = gmine;                               /* descriptor of granule-channel `tid`, fetched a frame ahead */
-      gcpar p;
-      const int32_t c = s_c1[tid];                        /* effective count1 (Q6), resolved by the caller */
-      (void)gr;
-      const bool is_short = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
-      p.c1 = c; p.gg = (int)P3_GC_GAIN(g) - 210;
-      p.first_short = is_short ? (P3_GC_MIXED(g) ? 36 : 0) : 576;
-      p.mult = P3_GC_SCALE(g) ? 2 : 1; p.pre = P3_GC_PREF(g); p.bt = P3_GC_BTYPE(g); p.mixed = P3_GC_MIXED(g); p.ws = P3_GC_WINSW(g);
-      p.live = ch < nch;
-      p.sbg8[0] = 8 * P3_GC_SBG(g, 0); p.sbg8[1] = 8 * P3_GC_SBG(g, 1); p.sbg8[2] = 8 * P3_GC_SBG(g, 2);
-      p.sblim = is_short ? (P3_GC_MIXED(g) ? 2 : 1) : 32;
-      s_par[tid] = p;
-    }
-    __syncthreads();
+  uint32_t *ib32 = reinterpret_cast<uint32_t *>(&S.isbuf[0][0]);
+  #pragma unroll
+  for (int k = 0; k < 9; k++) ib32[tid + FT * k] = pre[k];
+  if (tid < 64) reinterpret_cast<uint32_t *>(&S.scf[slot][0][0])[tid] = scfword;
+  if (tid < 4) {
+    const uint32_t ch = tid & 1;
+    gcpar p;
+    const bool is_short = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
+    p.c1 = c1eff; p.gg = (int)P3_GC_GAIN(g) - 210;
+    p.first_short = is_short ? (P3_GC_MIXED(g) ? 36 : 0) : 576;
+    p.mult = P3_GC_SCALE(g) ? 2 : 1; p.pre = P3_GC_PREF(g); p.bt = P3_GC_BTYPE(g); p.mixed = P3_GC_MIXED(g); p.ws = P3_GC_WINSW(g);
+    p.live = ch < nch;
+    p.sbg8[0] = 8 * P3_GC_SBG(g, 0); p.sbg8[1] = 8 * P3_GC_SBG(g, 1); p.sbg8[2] = 8 * P3_GC_SBG(g, 2);
+    p.sblim = is_short ? (P3_GC_MIXED(g) ? 2 : 1) : 32;
+    S.par[slot][tid] = p;
+  }
+}
+
+__device__ __forceinline__ void sf_scale(const synth_sm &S, int slot)
+{
+  SF_LOCALS
     /* band scales fl(t1*t2): 2^(-(scale?1:0.5)*(scalefac+preflag*pretab)) * 2^((gain-210-8*sbg)/4) (pdmp3.c:2127-2128,2144-2146).
      * long blocks: index = sfb (0..21); short: 3*sfb+win; mixed: long bands 0..7 sit in the unused short slots 0..7 */
     for (int e = tid; e < 4 * 40; e += FT) {
@@ -206,8 +199,12 @@ __device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &f
       }
       s_scale[gcl][b] = v;
     }
-    __syncthreads();
+}
 
+template <int DUMMY>
+__device__ __forceinline__ void sf_stageAB(const synth_sm &S, int slot, const p3_frame &fr, const p3_tables *__restrict__ T, uint32_t nch)
+{
+  SF_LOCALS
     /* ---- A+B: requantize + reorder (exact arithmetic of pdmp3.c:2121-2152) and stereo (pdmp3.c:1916-1971):
      *      a thread requantizes line d of BOTH channels of a granule and couples them in registers ---- */
     {
@@ -259,8 +256,17 @@ __device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &f
         }
       }
     }
-    __syncthreads();
+}
 
+/* the last 15 slots of the previous frame become the history of the next one (stage F of that frame must be over) */
+__device__ __forceinline__ void sf_hist(const synth_sm &S)
+{
+  for (int i = threadIdx.x; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, sl = r >> 5, k = r & 31; S.xring[ch][sl][k] = S.xring[ch][36 + sl][k]; }
+}
+
+__device__ __forceinline__ void sf_tapC(const synth_sm &S, int slot, float *xr_tap)
+{
+  SF_LOCALS
     /* ---- C: antialias (pdmp3.c:1706-1732).  Normally folded into stage D (below); as a separate pass only
      *      when the post-antialias spectra are tapped for the stage-level parity tests ---- */
     if (xr_tap) {
@@ -282,6 +288,11 @@ __device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &f
       for (int e = tid; e < 4 * 576; e += FT) xr_tap[e] = (&xs[0][0])[e];
     }
 
+}
+
+__device__ __forceinline__ void sf_stageD(const synth_sm &S, int slot, int n, const float *xr_tap)
+{
+  SF_LOCALS
     /* ---- D: antialias + IMDCT + window; first half in place, second half to the tail buffer.
      *      One warp = the 32 subbands of one granule-channel, so the butterflies across subband boundaries
      *      only need the neighbour lanes' lines: read, __syncwarp(), then write in place. ---- */
@@ -334,8 +345,11 @@ __device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &f
         }
       }
     }
-    __syncthreads();
+}
 
+__device__ __forceinline__ void sf_stageE(const synth_sm &S, int n, uint32_t nch, float *y_tap)
+{
+  const int slot = 0; SF_LOCALS
     /* ---- E: overlap-add + frequency inversion + 32-point DCT per time slot -> X ring ---- */
     if (tid < 72) {
       const uint32_t gr = tid / 36, r = tid % 36, ch = r / 18, ss = r % 18;
@@ -358,8 +372,14 @@ __device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &f
         for (int k = 0; k < 32; k++) X[k] = s[k];
       }
     }
-    __syncthreads();
+}
 
+template <bool SCRATCH>
+__device__ __forceinline__ void sf_stageF(const synth_sm &S, const p3_frame &fr, uint32_t nch, bool emit, int16_t *__restrict__ pcm,
+                                          const float (&ce)[8], const float (&co)[8], int ia, int ib)
+{
+  const int slot = 0; SF_LOCALS
+  const int j = tid & 31, wgr = (tid >> 5) & 1, wch = tid >> 6;
     /* ---- F: 512-tap window from registers + PCM ---- */
     if (wch < (int)nch && emit) {
       const int64_t base = ((int64_t)fr.pcm_index * 1152 + wgr * 576 + j) * nch + wch;
@@ -383,7 +403,6 @@ __device__ __forceinline__ void synth_frame(const synth_sm &S, const p3_frame &f
         }
       }
     }
-#undef s_sfreq
 }
 
 /* window coefficients of this thread's output column j, signs of the V<->X symmetry and the 32767 scale folded in:
@@ -411,7 +430,6 @@ __device__ __forceinline__ void synth_load_state(const synth_sm &S, const p3_sta
   __syncthreads();
   if (st)
     for (int i = tid; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, s = r / 32, k = r % 32; S.xring[ch][36 + s][k] = st->xhist[ch][14 - s][k]; }
-  if (tid == 0) *S.sfreq = 0xffffffffu;
   __syncthreads();
 }
 
@@ -436,66 +454,81 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   __shared__ __align__(16) int16_t isbuf[4][576];
   __shared__ uint8_t s_sfb_l[576], s_sfbw_s[576];
   __shared__ uint16_t s_reo[576];
-  __shared__ __align__(16) uint8_t s_scf[4][P3_SCF_STRIDE];
-  __shared__ gcpar s_par[4];
-  __shared__ float s_scale[4][40];                       /* fl(t1*t2) per scalefactor band: long sfb 0..21, short 3*sfb+win */
-  __shared__ int32_t s_c1[4];
-  __shared__ uint32_t s_sfreq;
-  synth_sm S = {xs, tails, xring, isbuf, s_sfb_l, s_sfbw_s, s_reo, s_par, s_scale, s_c1, &s_sfreq, NULL, NULL};
+  __shared__ __align__(16) uint8_t s_scf[2][4][P3_SCF_STRIDE];
+  __shared__ gcpar s_par[2][4];
+  __shared__ float s_scale[2][4][40];                    /* fl(t1*t2) per scalefactor band: long sfb 0..21, short 3*sfb+win */
+  synth_sm S = {xs, tails, xring, isbuf, s_sfb_l, s_sfbw_s, s_reo, s_par, s_scale, s_scf, NULL, NULL};
 
   const int tid = threadIdx.x;
   const int64_t c0 = f_first + (int64_t)blockIdx.x * frames_per_cta;
   const int64_t c1 = min(c0 + (int64_t)frames_per_cta, f_end);
   const int warm = blockIdx.x > 0 ? 1 : 0;
   const uint32_t nch = frames[c0].nch;
+  const uint32_t *isw = reinterpret_cast<const uint32_t *>(is_in);
 
   float ce[8], co[8]; int ia, ib;
   synth_window_coeffs(T, ce, co, ia, ib);
+  sf_load_luts(S, T, frames[c0].sfreq);
   synth_load_state(S, warm ? NULL : st_in);
 
-  /* software pipeline: the spectra of frame n+1 are fetched into registers while frame n is processed */
-  uint32_t pre[9], pre_scf = 0;
-  const uint32_t *isw = reinterpret_cast<const uint32_t *>(is_in);
-  {
-    const int64_t o0 = (c0 - warm - f_first) * 4;
+  /* Everything a frame needs from global memory is fetched one frame ahead into registers:
+   *   pre[9]   this thread's share of the frame's spectra      pscf  its word of the scalefactors (threads 0..63)
+   *   gq       side info of granule-channel `tid` (threads 0..3)    cq  its count1      frq  second half of p3_frame */
+  uint32_t pre[9], pscf = 0; p3_gc gq = {0, 0, 0, 0}; int32_t cq = 0; uint4 frq;
+  auto fetch = [&](int64_t f) {
+    const int64_t o = (f - f_first) * 4;
     #pragma unroll
-    for (int k = 0; k < 9; k++) pre[k] = __ldg(isw + o0 * 288 + tid + FT * k);
-    if (tid < 64) pre_scf = __ldg(reinterpret_cast<const uint32_t *>(scf + o0 * P3_SCF_STRIDE) + tid);
-  }
-  /* second half of the p3_frame record (nch, mode, mode_ext, sfreq, scfsi, flags, pcm_index), one frame ahead */
-  uint4 frn = __ldg(reinterpret_cast<const uint4 *>(frames + (c0 - warm)) + 1);
-  p3_gc gnext = {0, 0, 0, 0}; int32_t cnext = 0;        /* threads 0..3: side info and count1 of their granule-channel, one frame ahead */
-  if (tid < 4) { gnext = gcs[4 * (c0 - warm) + tid]; cnext = count1[(c0 - warm - f_first) * 4 + tid]; }
+    for (int k = 0; k < 9; k++) pre[k] = __ldg(isw + o * 288 + tid + FT * k);
+    if (tid < 64) pscf = __ldg(reinterpret_cast<const uint32_t *>(scf + o * P3_SCF_STRIDE) + tid);
+    if (tid < 4) { gq = gcs[4 * f + tid]; cq = count1[o + tid]; }
+    frq = __ldg(reinterpret_cast<const uint4 *>(frames + f) + 1);
+  };
+  /* effective count1 of granule-channel `tid` of frame f (Q6: an empty part keeps the slot's previous value) */
+  auto eff_c1 = [&](int64_t f) -> int32_t {
+    int32_t c = 0;
+    if (tid < 4 && (uint32_t)(tid & 1) < nch) {
+      const uint32_t back = gq.w3;
+      if (back == 0) c = cq;
+      else if ((int64_t)back <= f - f_first) c = count1[(f - f_first) * 4 + tid - 4 * (int64_t)back];
+      else c = st_in->count1[tid >> 1][tid & 1];
+    }
+    if (tid < 4 && f == f_end - 1) st_out->count1[tid >> 1][tid & 1] = c;
+    return c;
+  };
+
+  const int64_t fs = c0 - warm;
+  fetch(fs);
+  sf_land(S, 0, pre, pscf, gq, eff_c1(fs), nch);
+  p3_frame fr; *(reinterpret_cast<uint4 *>(&fr) + 1) = frq;
+  if (fs + 1 < c1) fetch(fs + 1);
+  __syncthreads();
+  sf_scale(S, 0);
   __syncthreads();
 
-  int n = 0;                                              /* frame iteration within this CTA */
-  for (int64_t f = c0 - warm; f < c1; f++, n++) {
-    p3_frame fr;
-    *(reinterpret_cast<uint4 *>(&fr) + 1) = frn;
-    if (f + 1 < c1) frn = __ldg(reinterpret_cast<const uint4 *>(frames + f + 1) + 1);
-    const int64_t o0 = (f - f_first) * 4;
+  /* Three barriers per frame.  While frame n is in its transforms, frame n+1 is landed in the other table
+   * slot (after stage A+B has consumed the spectra buffer) and its band scales are computed (before stage E). */
+  int n = 0;
+  for (int64_t f = fs; f < c1; f++, n++) {
+    const int slot = n & 1;
     const bool emit = !(warm && n == 0) && (fr.flags & P3_FRAME_DECODE);
-    __syncthreads();                                      /* previous frame completely done (stage F reads, s_scf, s_c1) */
-    if (tid < 64) {
-      reinterpret_cast<uint32_t *>(&s_scf[0][0])[tid] = pre_scf;
-      if (f + 1 < c1) pre_scf = __ldg(reinterpret_cast<const uint32_t *>(scf + (o0 + 4) * P3_SCF_STRIDE) + tid);
+    const int64_t o0 = (f - f_first) * 4;
+    sf_stageAB<0>(S, slot, fr, T, nch);
+    __syncthreads();
+    if (xr_tap) sf_tapC(S, slot, xr_tap + o0 * 576);       /* tests only: separate antialias pass + tap (has its own barrier) */
+    sf_hist(S);
+    p3_frame frn = fr;
+    if (f + 1 < c1) {
+      sf_land(S, slot ^ 1, pre, pscf, gq, eff_c1(f + 1), nch);
+      *(reinterpret_cast<uint4 *>(&frn) + 1) = frq;
+      if (f + 2 < c1) fetch(f + 2);
     }
-    const p3_gc gcur = gnext;
-    if (tid < 4) {                                        /* effective count1 (Q6), as in k_requant */
-      const uint32_t gr = tid >> 1, ch = tid & 1;
-      int32_t c = 0;
-      if (ch < nch) {
-        const uint32_t back = gcur.w3;
-        if (back == 0) c = cnext;
-        else if ((int64_t)back <= f - f_first) c = count1[o0 + tid - 4 * (int64_t)back];
-        else c = st_in->count1[gr][ch];
-      }
-      s_c1[tid] = c;
-      if (f == f_end - 1) st_out->count1[gr][ch] = c;
-      if (f + 1 < c1) { gnext = gcs[4 * (f + 1) + tid]; cnext = count1[o0 + 4 + tid]; }
-    }
-    synth_frame<false>(S, fr, gcs, T, f, n, nch, s_scf, pre, f + 1 < c1 ? isw + (o0 + 4) * 288 : NULL, emit, gcur, pcm, ce, co, ia, ib,
-                       xr_tap ? xr_tap + o0 * 576 : NULL, y_tap ? y_tap + o0 * 576 : NULL);
+    sf_stageD(S, slot, n, xr_tap);
+    __syncthreads();
+    if (f + 1 < c1) sf_scale(S, slot ^ 1);
+    sf_stageE(S, n, nch, y_tap ? y_tap + o0 * 576 : NULL);
+    __syncthreads();
+    sf_stageF<false>(S, fr, nch, emit, pcm, ce, co, ia, ib);
+    fr = frn;
   }
   __syncthreads();
   if (c1 == f_end) synth_store_state(S, n - 1, st_out);
@@ -551,12 +584,12 @@ k_decode_fused(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ fra
   uint8_t *p = reinterpret_cast<uint8_t *>(tail2) + sizeof(float) * 2 * 576;
   uint8_t (*scfg)[P3_SCF_STRIDE] = reinterpret_cast<uint8_t (*)[P3_SCF_STRIDE]>(p); p += FG * 4 * P3_SCF_STRIDE;   /* scalefactors of the group */
   int32_t *c1g = reinterpret_cast<int32_t *>(p); p += FG * 4 * 4;                                                /* count1 of the group, made effective in place */
-  float (*s_scale)[40] = reinterpret_cast<float (*)[40]>(p); p += 4 * 40 * 4;
-  gcpar *s_par = reinterpret_cast<gcpar *>(p); p += 4 * sizeof(gcpar);
+  float (*s_scale)[4][40] = reinterpret_cast<float (*)[4][40]>(p); p += 2 * 4 * 40 * 4;
+  gcpar (*s_par)[4] = reinterpret_cast<gcpar (*)[4]>(p); p += 2 * 4 * sizeof(gcpar);
+  uint8_t (*s_scf2)[4][P3_SCF_STRIDE] = reinterpret_cast<uint8_t (*)[4][P3_SCF_STRIDE]>(p); p += 2 * 4 * P3_SCF_STRIDE;
   uint16_t *s_reo = reinterpret_cast<uint16_t *>(p); p += 576 * 2;
   uint8_t *s_sfb_l = p; p += 576; uint8_t *s_sfbw_s = p; p += 576;
-  int32_t *s_c1 = reinterpret_cast<int32_t *>(p); p += 16; int32_t *s_eff = reinterpret_cast<int32_t *>(p); p += 16;
-  uint32_t *s_sfreq = reinterpret_cast<uint32_t *>(p); p += 8;
+  int32_t *s_eff = reinterpret_cast<int32_t *>(p); p += 16;
   p = dsm + ((p - dsm + 15) & ~(size_t)15);
   int64_t *s_fb = reinterpret_cast<int64_t *>(p); p += 16;
   /* ---- phase-local part: synthesis buffers and the Huffman buffers share the same bytes ---- */
@@ -576,9 +609,10 @@ k_decode_fused(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ fra
   const uint32_t nch = frames[r0].nch;
   int16_t *my = scratch + (size_t)blockIdx.x * FG * 4 * 576;
 
-  synth_sm S = {xs, NULL, xring, isbuf, s_sfb_l, s_sfbw_s, s_reo, s_par, s_scale, s_c1, s_sfreq, tails01, tail2};
+  synth_sm S = {xs, NULL, xring, isbuf, s_sfb_l, s_sfbw_s, s_reo, s_par, s_scale, s_scf2, tails01, tail2};
   float ce[8], co[8]; int ia, ib;
   synth_window_coeffs(T, ce, co, ia, ib);
+  sf_load_luts(S, T, frames[r0].sfreq);
   synth_load_state(S, warm ? NULL : st_in);
   if (tid < 4) s_eff[tid] = warm ? 0 : st_in->count1[tid >> 1][tid & 1];
   __syncthreads();
@@ -622,10 +656,29 @@ k_decode_fused(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ fra
       const p3_frame fr = frames[f];
       const int k = (int)(f - F0);
       const bool emit = !(warm && n == 0) && (fr.flags & P3_FRAME_DECODE);
+      __syncthreads();                                    /* previous frame completely done */
+      {
+        p3_gc gcur = {0, 0, 0, 0}; int32_t cc = 0;
+        if (tid < 4) { cc = c1g[4 * k + tid]; gcur = gcs[4 * f + tid]; }
+        const uint32_t w = tid < 64 ? reinterpret_cast<const uint32_t *>(&scfg[4 * k][0])[tid] : 0u;
+        sf_hist(S);
+        sf_land(S, 0, pre, w, gcur, cc, nch);
+        if (f + 1 < F1) {
+          const uint32_t *nx = isw + (size_t)(k + 1) * 4 * 288;
+          #pragma unroll
+          for (int q = 0; q < 9; q++) pre[q] = __ldcg(nx + tid + FT * q);
+        }
+      }
       __syncthreads();
-      p3_gc gcur = {0, 0, 0, 0};
-      if (tid < 4) { s_c1[tid] = c1g[4 * k + tid]; gcur = gcs[4 * f + tid]; }
-      synth_frame<true>(S, fr, gcs, T, f, n, nch, scfg + 4 * k, pre, f + 1 < F1 ? isw + (size_t)(k + 1) * 4 * 288 : NULL, emit, gcur, pcm, ce, co, ia, ib, NULL, NULL);
+      sf_scale(S, 0);
+      __syncthreads();
+      sf_stageAB<0>(S, 0, fr, T, nch);
+      __syncthreads();
+      sf_stageD(S, 0, n, NULL);
+      __syncthreads();
+      sf_stageE(S, n, nch, NULL);
+      __syncthreads();
+      sf_stageF<true>(S, fr, nch, emit, pcm, ce, co, ia, ib);
     }
     __syncthreads();
   }
@@ -638,8 +691,8 @@ k_decode_fused(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ fra
 /* bytes of dynamic shared memory k_decode_fused needs for a K1 window of `k1_words` words */
 extern "C" size_t p3_fused_smem_bytes(uint32_t k1_words, uint32_t hlut_used)
 {
-  size_t pers = sizeof(float) * 2 * XSLOTS * XPITCH + sizeof(float) * 2 * 576 + FG * 4 * P3_SCF_STRIDE + FG * 4 * 4 + 4 * 40 * 4 + 4 * sizeof(gcpar)
-              + 576 * 2 + 576 + 576 + 16 + 16 + 8;
+  size_t pers = sizeof(float) * 2 * XSLOTS * XPITCH + sizeof(float) * 2 * 576 + FG * 4 * P3_SCF_STRIDE + FG * 4 * 4 + 2 * 4 * 40 * 4 + 2 * 4 * sizeof(gcpar)
+              + 2 * 4 * P3_SCF_STRIDE + 576 * 2 + 576 + 576 + 16;
   pers = (pers + 15) & ~(size_t)15; pers += 16;
   size_t syn = 8 * 576 * 4 + 4 * 576 * 2;
   size_t huf = (size_t)k1_words * 4 + 4 * FG * 4 * 4 + (size_t)hlut_used * 2 + 16;
