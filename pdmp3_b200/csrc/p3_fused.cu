@@ -261,7 +261,12 @@ __device__ __forceinline__ void sf_stageAB(const synth_sm &S, int slot, const p3
 /* the last 15 slots of the previous frame become the history of the next one (stage F of that frame must be over) */
 __device__ __forceinline__ void sf_hist(const synth_sm &S)
 {
-  for (int i = threadIdx.x; i < 2 * 15 * 32; i += FT) { int ch = i / 480, r = i % 480, sl = r >> 5, k = r & 31; S.xring[ch][sl][k] = S.xring[ch][36 + sl][k]; }
+  const int lane = threadIdx.x & 31;
+  #pragma unroll
+  for (int it = 0; it < 8; it++) {                          /* 30 rows of 32 floats over 4 warps */
+    const int r = (threadIdx.x >> 5) + 4 * it;
+    if (r < 30) { const int ch = r >= 15, sl = r - 15 * ch; S.xring[ch][sl][lane] = S.xring[ch][36 + sl][lane]; }
+  }
 }
 
 __device__ __forceinline__ void sf_tapC(const synth_sm &S, int slot, float *xr_tap)
