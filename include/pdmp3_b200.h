@@ -115,7 +115,8 @@ void p3_ctx_destroy(p3_ctx *c);
 int  p3_ctx_reset(p3_ctx *c);                 /* zero overlap / FIFO / reservoir state (pdmp3_open_feed, pdmp3.c:2377-2379) */
 int  p3_ctx_set_mode(p3_ctx *c, int mode);
 int  p3_ctx_set_taps(p3_ctx *c, int on);              /* keep stage taps of the next batches on the device */
-int  p3_ctx_set_frames_per_cta(p3_ctx *c, int n);     /* FAST mode: frames each CTA walks (default 32) */
+int  p3_ctx_set_frames_per_cta(p3_ctx *c, int n);     /* FAST mode: frames each CTA (k_synth_fast) / warp (k_synth_warp) walks (default 32) */
+int  p3_ctx_set_synth_kernel(p3_ctx *c, int which);   /* FAST mode: 0 = k_synth_warp for stereo batches (default), 1 = always k_synth_fast */
 const char *p3_last_error(void);
 
 /* Tap buffers (device side, optional; for stage-level parity tests). NULL = not captured. */

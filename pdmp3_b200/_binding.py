@@ -66,6 +66,7 @@ def lib():
     L.p3_ctx_set_mode.argtypes = [C.c_void_p, C.c_int]
     L.p3_ctx_set_taps.argtypes = [C.c_void_p, C.c_int]
     L.p3_ctx_set_frames_per_cta.argtypes = [C.c_void_p, C.c_int]
+    L.p3_ctx_set_synth_kernel.argtypes = [C.c_void_p, C.c_int]
     L.p3_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3Parsed), C.c_void_p, C.POINTER(P3Taps)]
     L.p3_batch_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3Parsed)]
     L.p3_batch_run.argtypes = [C.c_void_p]
@@ -149,6 +150,10 @@ class Context:
 
     def set_frames_per_cta(self, n):
         _check(lib().p3_ctx_set_frames_per_cta(self.h, n), "p3_ctx_set_frames_per_cta")
+
+    def set_synth_kernel(self, which):
+        """FAST mode: 0 = k_synth_warp for stereo batches (default), 1 = always k_synth_fast."""
+        _check(lib().p3_ctx_set_synth_kernel(self.h, which), "p3_ctx_set_synth_kernel")
 
     def reset(self):
         _check(lib().p3_ctx_reset(self.h), "p3_ctx_reset")

@@ -14,6 +14,10 @@ extern "C" size_t p3_fused_smem_bytes(uint32_t k1_words, uint32_t hlut_used);
 extern "C" int p3_fused_group_frames(void);
 extern "C" __global__ void k_decode_fused(const uint8_t *raw, const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, const uint8_t *tail, int64_t f_first, int64_t f_end,
     uint32_t k1_words, int16_t *scratch, const p3_state *st_in, p3_state *st_out, int16_t *pcm);
+extern "C" size_t p3_synthw_smem_bytes(void);
+extern "C" int p3_synthw_warps_per_cta(void);
+extern "C" __global__ void k_synth_warp(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_warp,
+    const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, const float *pow43s);
 extern "C" __global__ void k_synth_fast(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_cta,
     const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, float *xr_tap, float *y_tap);
 
@@ -62,6 +66,7 @@ struct p3_ctx {
   int64_t n_frames, n_pcm_frames; uint32_t nch; uint64_t raw_bytes;
   uint32_t k1_smem_words; int64_t chunk_frames;
   int launches; int taps; int fpc;
+  float *d_pow43s; int synth_kernel;      /* signed |is|^(4/3) table (k_synth_warp); 0 = pick, 1 = always k_synth_fast */
   uint8_t next_tail[512]; int have_next_tail;
 };
 
@@ -105,6 +110,16 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
   CK(cudaFuncSetAttribute(k_huffman, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(k_polyphase, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   c->chunk_frames = 1 << 18; c->fpc = 32;
+  CK(cudaFuncSetAttribute(k_synth_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
+  {
+    /* pow43s[8207 + v] = sign(v) * |v|^(4/3): requantization without abs / sign fix-up (pdmp3.c:2125-2132) */
+    static float h[2 * 8207 + 1];
+    const p3_tables *T = p3_tables_get();
+    for (int v = -8207; v <= 8207; v++) h[8207 + v] = v < 0 ? -T->pow43[-v] : T->pow43[v];
+    CK(cudaMalloc(&c->d_pow43s, sizeof h));
+    CK(cudaMemcpy(c->d_pow43s, h, sizeof h, cudaMemcpyHostToDevice));
+    const char *e = getenv("P3_SYNTH"); c->synth_kernel = (e && !strcmp(e, "cta")) ? 1 : 0;
+  }
   {
     static float dct4[18 * 18];
     for (int k = 0; k < 18; k++) for (int m = 0; m < 18; m++) dct4[k * 18 + m] = (float)cos(3.14159265358979323846 / 18.0 * (k + 0.5) * (m + 0.5));
@@ -137,7 +152,7 @@ extern "C" void p3_ctx_destroy(p3_ctx *c)
   for (dbuf *b : bs) if (b->p) cudaFree(b->p);
   cudaStreamDestroy(c->s_k1); cudaEventDestroy(c->fork);
   for (int i = 0; i < 2; i++) { cudaEventDestroy(c->k1_done[i]); cudaEventDestroy(c->syn_done[i]); }
-  cudaFree(c->d_tables); cudaFree(c->d_state[0]); cudaFree(c->d_state[1]);
+  cudaFree(c->d_tables); cudaFree(c->d_state[0]); cudaFree(c->d_state[1]); cudaFree(c->d_pow43s);
   for (int i = 0; i < 10; i++) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
   free(c);
@@ -164,6 +179,7 @@ extern "C" int p3_ctx_set_mode(p3_ctx *c, int mode)
 }
 extern "C" int p3_ctx_set_taps(p3_ctx *c, int on) { if (!c) return P3_EINVAL; c->taps = on; return P3_OK; }
 extern "C" int p3_ctx_set_frames_per_cta(p3_ctx *c, int n) { if (!c || n < 1) return P3_EINVAL; c->fpc = n; return P3_OK; }
+extern "C" int p3_ctx_set_synth_kernel(p3_ctx *c, int which) { if (!c || which < 0 || which > 1) return P3_EINVAL; c->synth_kernel = which; return P3_OK; }
 extern "C" void *p3_ctx_stream(p3_ctx *c) { return c ? (void *)c->stream : NULL; }
 extern "C" int p3_kernel_launch_count(p3_ctx *c) { return c ? c->launches : 0; }
 
@@ -263,7 +279,14 @@ static int run_chunk(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, cudaEvent_t
       (int16_t *)c->is16.p, (int32_t *)c->count1.p, (uint8_t *)c->scf.p);
   if (ev) CK(cudaEventRecord(ev[1], c->stream));
   if (c->mode == P3_MODE_FAST) {
-    /* K2+K3+K4 fused (p3_fused.cu) */
+    /* K2+K3+K4 fused (p3_fused.cu): stereo batches go to the warp-autonomous packed kernel, mono batches and tapped
+     * runs to the one-channel-per-thread kernel; both give the same bits */
+    if (c->nch == 2 && !c->taps && c->synth_kernel == 0) {
+      const int wpb = p3_synthw_warps_per_cta();
+      const int64_t warps = (nf + c->fpc - 1) / c->fpc;
+      k_synth_warp<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
+          (const int16_t *)c->is16.p, (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207);
+    } else
     k_synth_fast<<<(unsigned)((nf + c->fpc - 1) / c->fpc), 128, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
         (const int16_t *)c->is16.p, (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so, (int16_t *)sl->pcm.p,
         c->taps ? (float *)c->xr.p : NULL, c->taps ? (float *)c->y.p : NULL);

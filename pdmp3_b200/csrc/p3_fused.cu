@@ -18,11 +18,12 @@
 #include "p3_device.cuh"
 #include "p3_kernels.h"
 #include "p3_k1.cuh"
-#include "p3_lee.inc"
+#include "p3_xform.cuh"
 
 struct p3_fconst {
   float dct4[18][18];              /* cos(pi/18 (k+1/2)(m+1/2)) */
   float win[4][36];
+  float swin[4][36];               /* win with the IMDCT symmetry signs folded in: -win for outputs 9..35 */
   float cos12[6][12];
   float cs[8], ca[8], is_l[8], is_r[8];
   float t1h[40];
@@ -35,70 +36,31 @@ extern "C" int p3_fused_upload_consts(const p3_tables *T, const float *dct4)
 {
   static p3_fconst h;
   memcpy(h.dct4, dct4, sizeof h.dct4);
-  memcpy(h.win, T->imdct_win, sizeof h.win); memcpy(h.cos12, T->cos12, sizeof h.cos12);
+  memcpy(h.win, T->imdct_win, sizeof h.win);
+  for (int b = 0; b < 4; b++) for (int i = 0; i < 36; i++) h.swin[b][i] = i < 9 ? T->imdct_win[b][i] : -T->imdct_win[b][i];
+  memcpy(h.cos12, T->cos12, sizeof h.cos12);
   memcpy(h.cs, T->cs, 32); memcpy(h.ca, T->ca, 32); memcpy(h.is_l, T->is_l, 32); memcpy(h.is_r, T->is_r, 32);
   memcpy(h.t1h, T->t1h, sizeof h.t1h); memcpy(h.t2, T->t2, sizeof h.t2);
   for (int i = 0; i < 24; i++) h.pretab[i] = (float)T->pretab[i];
   return (int)cudaMemcpyToSymbol(FC, &h, sizeof h);
 }
 
-/* ---- 32-point DCT-II, Lee's recursion, fully unrolled in registers ---------------------------- */
-template <int N> struct Lee { static __device__ __forceinline__ const float *k(); };
-#define LEE_TAB(N) template <> struct Lee<N> { static __device__ __forceinline__ float c(int i) { constexpr float t[N / 2] = P3_LEE##N; return t[i]; } };
-LEE_TAB(32) LEE_TAB(16) LEE_TAB(8) LEE_TAB(4) LEE_TAB(2)
+/* fast transforms (32-point DCT-II, 18-point DCT-IV), shared with the packed-stereo kernel: p3_xform.cuh */
 
-template <int N> __device__ __forceinline__ void dct2(float (&x)[N])
+/* three 12-point IMDCTs of a short block (pdmp3.c:1673-1686): raw[6w+6+p] += win2[p] * sum_m in[w+3m] cos12[m][p] */
+__device__ __forceinline__ void imdct_short(const float (&in)[18], float (&raw)[36])
 {
-  if constexpr (N == 1) return;
-  else {
-    float a[N / 2], b[N / 2];
-    #pragma unroll
-    for (int i = 0; i < N / 2; i++) { a[i] = x[i] + x[N - 1 - i]; b[i] = (x[i] - x[N - 1 - i]) * Lee<N>::c(i); }
-    dct2<N / 2>(a); dct2<N / 2>(b);
-    #pragma unroll
-    for (int i = 0; i < N / 2; i++) { x[2 * i] = a[i]; x[2 * i + 1] = (i + 1 < N / 2) ? b[i] + b[i + 1] : b[i]; }
-  }
-}
-
-
-/* ---- 18-point DCT-IV via two 9-point DCT-IIs (tools/proto/fast_transforms.py) -------------------
- * y[m] = x[m] * 2cos(pi(2m+1)/72);  Y = DCT-II-18(y) by one Lee split into two DCT-II-9;
- * t[0] = Y[0]/2, t[k] = Y[k] - t[k-1].   ~125 flops instead of 324. */
-__device__ __forceinline__ void dct9(const float (&x)[9], float (&X)[9])
-{
-  constexpr float C10 = 9.848077530e-01f, C20 = 9.396926208e-01f, C30 = 8.660254038e-01f, C40 = 7.660444431e-01f, C50 = 6.427876097e-01f, C70 = 3.420201433e-01f, C80 = 1.736481777e-01f;
-  const float s0 = x[0] + x[8], s1 = x[1] + x[7], s2 = x[2] + x[6], s3 = x[3] + x[5], x4 = x[4];
-  const float d0 = x[0] - x[8], d1 = x[1] - x[7], d2 = x[2] - x[6], d3 = x[3] - x[5];
-  const float h1 = 0.5f * s1;
-  X[0] = (s0 + s1) + (s2 + s3) + x4;
-  X[2] = fmaf(s0, C20, fmaf(-s2, C80, fmaf(-s3, C40, h1 - x4)));
-  X[4] = fmaf(s0, C40, fmaf(-s2, C20, fmaf(s3, C80, x4 - h1)));
-  X[6] = fmaf(s0 + s2 + s3, 0.5f, -(s1 + x4));
-  X[8] = fmaf(s0, C80, fmaf(s2, C40, fmaf(-s3, C20, x4 - h1)));
-  const float e1 = d1 * C30;
-  X[1] = fmaf(d0, C10, fmaf(d2, C50, fmaf(d3, C70, e1)));
-  X[3] = (d0 - d2 - d3) * C30;
-  X[5] = fmaf(d0, C50, fmaf(-d2, C70, fmaf(d3, C10, -e1)));
-  X[7] = fmaf(d0, C70, fmaf(d2, C10, fmaf(-d3, C50, -e1)));
-}
-
-__device__ __forceinline__ void dct4_18(const float (&x)[18], float (&t)[18])
-{
-  constexpr float PRE[18] = {1.998096443e+00f, 1.982889723e+00f, 1.952592014e+00f, 1.907433901e+00f, 1.847759065e+00f, 1.774021666e+00f, 1.686782892e+00f, 1.586706681e+00f, 1.474554674e+00f, 1.351180415e+00f, 1.217522858e+00f, 1.074599217e+00f, 9.234972265e-01f, 7.653668647e-01f, 6.014115990e-01f, 4.328792279e-01f, 2.610523844e-01f, 8.723877473e-02f};
-  constexpr float LEE[9] = {5.019099188e-01f, 5.176380902e-01f, 5.516889595e-01f, 6.103872944e-01f, 7.071067812e-01f, 8.717233978e-01f, 1.183100792e+00f, 1.931851653e+00f, 5.736856623e+00f};
-  float a[9], b[9], A[9], B[9];
   #pragma unroll
-  for (int m = 0; m < 9; m++) {
-    const float u = x[m] * PRE[m], v = x[17 - m] * PRE[17 - m];
-    a[m] = u + v; b[m] = (u - v) * LEE[m];
-  }
-  dct9(a, A); dct9(b, B);
-  t[0] = 0.5f * A[0];
+  for (int q = 0; q < 36; q++) raw[q] = 0.0f;
   #pragma unroll
-  for (int k = 1; k < 18; k++) {
-    const float Y = (k & 1) ? (k == 17 ? B[8] : B[k >> 1] + B[(k >> 1) + 1]) : A[k >> 1];
-    t[k] = Y - t[k - 1];
-  }
+  for (int w = 0; w < 3; w++)
+    #pragma unroll
+    for (int q = 0; q < 12; q++) {
+      float sum = 0.0f;
+      #pragma unroll
+      for (int m = 0; m < 6; m++) sum = __fmaf_rn(in[w + 3 * m], FC.cos12[m][q], sum);
+      raw[6 * w + 6 + q] = __fmaf_rn(sum, FC.win[2][q], raw[6 * w + 6 + q]);
+    }
 }
 
 #define FT 128                     /* threads per CTA */
@@ -332,19 +294,8 @@ __device__ __forceinline__ void sf_stageD(const synth_sm &S, int slot, int n, co
             x[k] = t[9 + k] * FC.win[bt][k]; x[17 - k] = -t[9 + k] * FC.win[bt][17 - k];
           }
         } else {
-          /* three 12-point transforms (pdmp3.c:1673-1686): raw[6w+6+p] += win2[p] * sum_m in[w+3m] cos12[m][p] */
           float raw[36];
-          #pragma unroll
-          for (int q = 0; q < 36; q++) raw[q] = 0.0f;
-          #pragma unroll
-          for (int w = 0; w < 3; w++)
-            #pragma unroll
-            for (int q = 0; q < 12; q++) {
-              float sum = 0.0f;
-              #pragma unroll
-              for (int m = 0; m < 6; m++) sum = fmaf(in[w + 3 * m], FC.cos12[m][q], sum);
-              raw[6 * w + 6 + q] += sum * FC.win[2][q];
-            }
+          imdct_short(in, raw);
           #pragma unroll
           for (int i = 0; i < 18; i++) { x[i] = raw[i]; tl[i] = raw[18 + i]; }
         }
@@ -371,7 +322,7 @@ __device__ __forceinline__ void sf_stageE(const synth_sm &S, int n, uint32_t nch
           #pragma unroll
           for (int sb = 0; sb < 32; sb++) y_tap[(2 * gr + ch) * 576 + ss * 32 + sb] = s[sb];
         }
-        dct2<32>(s);
+        dct2<32, float>(s);
         float *X = &xring[ch][15 + gr * 18 + ss][0];
         #pragma unroll
         for (int k = 0; k < 32; k++) X[k] = s[k];
@@ -704,3 +655,5 @@ extern "C" size_t p3_fused_smem_bytes(uint32_t k1_words, uint32_t hlut_used)
   return pers + (syn > huf ? syn : huf);
 }
 extern "C" int p3_fused_group_frames(void) { return FG; }
+
+#include "p3_synthw.cuh"

@@ -1,0 +1,440 @@
+/* p3_synthw.cuh -- k_synth_warp: FAST-mode synthesis of STEREO streams, one autonomous warp per run of frames.
+ * (included at the end of p3_fused.cu; shares its constant tables and scalar helpers)
+ *
+ * Same algorithm and operation order as k_synth_fast (requantize .. PCM of Decode_L3, pdmp3.c:1024-1060, plus
+ * Convert_Frame_S16, 2307-2345); requantize / stereo / antialias keep the reference's exact arithmetic, the
+ * transforms agree with k_synth_fast to rounding (ptxas contracts some packed mul+add pairs into FFMA2), the PCM
+ * is within 1 LSB of the reference like that kernel's.  Organised around the warp:
+ *
+ *   - both channels of a granule travel together as one packed fp32 pair (f2) and every transform runs on
+ *     Blackwell's packed FFMA2/FADD2/FMUL2: half the issue slots of the one-channel-per-thread kernel;
+ *   - lane = subband for requantize / stereo / antialias / IMDCT, so the spectrum goes from the Huffman
+ *     output to the IMDCT output in REGISTERS: the antialias butterflies reach the neighbour subbands with
+ *     warp shuffles, the IMDCT overlap (the reference's static `store`, pdmp3.c:1755) never leaves the lane's
+ *     registers; lane = time slot for the 32-point DCT and lane = output column for the 512-tap window;
+ *   - the only shared-memory traffic is the [slot][subband] transpose in front of the DCT and the DCT outputs
+ *     (a 36-slot ring: the 16-slot FIFO of the reference, pdmp3.c:1983) that the window stage slides over;
+ *   - a warp never waits for another warp: no __syncthreads() in the frame loop, only __syncwarp();
+ *   - the Huffman output of the next granules (2304 B of spectra + 128 B of scalefactors) is brought in by the
+ *     TMA engine (cp.async.bulk, completion on an mbarrier) two granules ahead, no registers involved.
+ */
+#define SW_WPB    4                 /* warps per CTA (each one independent) */
+#define SW_PITCH  33                /* f2 elements per DCT row: 66 words -> conflict-free for row-per-lane and column-per-lane access */
+#define SW_LUT_BYTES 1728           /* CTA-shared: reorder_src u16[576] | line_sfbw_s u8[576] */
+
+struct __align__(16) sw_warp_sm {
+  uint8_t isb[2][2304];             /* [buffer][ch][576] int16: Huffman output of one granule (TMA destination) */
+  uint8_t scf[2][128];              /* [buffer][ch][64]: its scalefactors (TMA destination) */
+  f2 xr[36][SW_PITCH];              /* two blocks of 18 DCT rows; the block of the granule about to be transformed doubles as scratch */
+  float scale[40][2];               /* band scales fl(t1*t2) of the current granule, [band][ch] */
+  unsigned long long mbar[2];
+};
+
+__device__ __forceinline__ uint32_t sw_s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sw_mbar_init(unsigned long long *bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(sw_s32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sw_mbar_expect(unsigned long long *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(sw_s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sw_bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(sw_s32(dst)), "l"(src), "r"(bytes), "r"(sw_s32(bar)) : "memory");
+}
+__device__ __forceinline__ void sw_mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(sw_s32(bar)), "r"(parity) : "memory");
+    if (!ok && ++spins > (1u << 24)) __trap();             /* a lost copy must not hang the device */
+  } while (!ok);
+}
+
+/* per-channel parameters of a granule, identical in every lane (plain scalars: nothing here is ever indexed) */
+struct sw_par {
+  int32_t c1, gg; uint32_t first_short, mult, pre, bt, mixed, ws, sblim, sbg;   /* sbg: 8*subblock_gain[w] in byte w */
+};
+__device__ __forceinline__ sw_par sw_unpack(const uint4 g, int32_t c1eff)
+{
+  p3_gc q; q.w0 = g.x; q.w1 = g.y; q.w2 = g.z; q.w3 = g.w;
+  sw_par p;
+  const bool is_short = P3_GC_WINSW(q) && P3_GC_BTYPE(q) == 2;
+  p.c1 = c1eff; p.gg = (int)P3_GC_GAIN(q) - 210;
+  p.first_short = is_short ? (P3_GC_MIXED(q) ? 36u : 0u) : 576u;
+  p.mult = P3_GC_SCALE(q) ? 2u : 1u; p.pre = P3_GC_PREF(q); p.bt = P3_GC_BTYPE(q); p.mixed = P3_GC_MIXED(q); p.ws = P3_GC_WINSW(q);
+  p.sbg = (8 * P3_GC_SBG(q, 0)) | (8 * P3_GC_SBG(q, 1)) << 8 | (8 * P3_GC_SBG(q, 2)) << 16;
+  p.sblim = is_short ? (P3_GC_MIXED(q) ? 2u : 1u) : 32u;
+  return p;
+}
+
+/* int16 of (int32)(sum * 32767.0), scale folded into the window, clamped to +-32767 (pdmp3.c:2028-2030): a saturating
+ * truncation to s16 and one packed max for both channels.  (Where the reference's own float->int32 conversion
+ * overflows -- |sample| >= 2^31, undefined in C -- this saturates; k_synth_fast keeps the x86 result there.) */
+__device__ __forceinline__ uint32_t sw_pcm2(f2 sum)
+{
+  int16_t l, r;
+  asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(l) : "f"(f2_x(sum)));
+  asm("cvt.rzi.s16.f32 %0, %1;" : "=h"(r) : "f"(f2_y(sum)));
+  const uint32_t v = (uint32_t)(uint16_t)l | ((uint32_t)(uint16_t)r << 16);
+  return __vmaxs2(v, 0x80018001u);
+}
+
+extern "C" __global__ void __launch_bounds__(SW_WPB * 32, 3)
+k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
+             int64_t f_first, int64_t f_end, int frames_per_warp,
+             const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf,
+             const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm,
+             const float *__restrict__ pow43s /* signed |is|^(4/3) table, indexable -8207..8207 */)
+{
+  extern __shared__ __align__(16) uint8_t sw_dsm[];
+  uint16_t *s_reo = reinterpret_cast<uint16_t *>(sw_dsm);
+  uint8_t *s_sfbw = sw_dsm + 1152;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  sw_warp_sm *W = reinterpret_cast<sw_warp_sm *>(sw_dsm + SW_LUT_BYTES) + warp;
+
+  const uint32_t sf = frames[f_first].sfreq;               /* a batch never mixes sample rates */
+  for (uint32_t i = threadIdx.x; i < 576; i += blockDim.x) { s_reo[i] = T->reorder_src[sf][i]; s_sfbw[i] = T->line_sfbw_s[sf][i]; }
+  __syncthreads();                                         /* the only CTA-wide barrier */
+
+  const int64_t gw = (int64_t)blockIdx.x * SW_WPB + warp;
+  const int64_t c0 = f_first + gw * frames_per_warp;
+  if (c0 >= f_end) return;
+  const int64_t c1 = min(c0 + (int64_t)frames_per_warp, f_end);
+  const int warm = gw > 0 ? 1 : 0;
+  const int64_t fs = c0 - warm;
+  const uint32_t sb = lane;
+
+  /* ---- per-lane constants ---- */
+  float ce[8], co[8]; int ia, ib;
+  synth_window_coeffs(T, ce, co, ia, ib);
+  uint32_t sfbp[3] = {0, 0, 0};                            /* long-block sfb of this subband's 18 lines, 5 bits each */
+  #pragma unroll
+  for (int m = 0; m < 18; m++) sfbp[m / 6] |= (uint32_t)T->line_sfb_l[sf][18 * sb + m] << (5 * (m % 6));
+
+  /* ---- carried state: IMDCT tails in registers, DCT history rows in the ring ---- */
+  f2 tail[18];
+  #pragma unroll
+  for (int i = 0; i < 18; i++) tail[i] = warm ? f2_make(0.0f, 0.0f) : f2_make(st_in->store[0][18 * sb + i], st_in->store[1][18 * sb + i]);
+  for (uint32_t i = lane; i < 36 * SW_PITCH; i += 32) (&W->xr[0][0])[i] = f2_make(0.0f, 0.0f);
+  if (lane == 0) { sw_mbar_init(&W->mbar[0], 1); sw_mbar_init(&W->mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncwarp();
+  if (!warm)
+    for (int age = 1; age <= 15; age++) W->xr[36 - age][lane] = f2_make(st_in->xhist[0][age - 1][lane], st_in->xhist[1][age - 1][lane]);
+  __syncwarp();
+
+  auto issue = [&](int64_t f, int gr, int b) {             /* TMA: spectra + scalefactors of granule (f, gr) -> buffer b */
+    if (lane == 0) {
+      const int64_t o = (f - f_first) * 4 + 2 * gr;
+      sw_mbar_expect(&W->mbar[b], 2304 + 128);
+      sw_bulk_g2s(W->isb[b], is_in + o * 576, 2304, &W->mbar[b]);
+      sw_bulk_g2s(W->scf[b], scf + o * P3_SCF_STRIDE, 128, &W->mbar[b]);
+    }
+  };
+  const int32_t rel0 = (int32_t)(fs - f_first), nfr = (int32_t)(c1 - fs);   /* first frame (relative to the launch) and frames of this warp */
+  const int32_t rel_last = (int32_t)(f_end - 1 - f_first);
+  const p3_frame *fr_l = frames + f_first; const p3_gc *gc_l = gcs + 4 * f_first;
+  issue(fs, 0, 0); issue(fs, 1, 1);
+
+  /* descriptors of a granule: side info of both channels and their count1, fetched one granule ahead */
+  uint4 ga, gb; int2 cq;
+  auto fetch_desc = [&](int32_t g /* granule index relative to the launch */) {
+    ga = __ldg(reinterpret_cast<const uint4 *>(gc_l) + 2 * g);
+    gb = __ldg(reinterpret_cast<const uint4 *>(gc_l) + 2 * g + 1);
+    cq = __ldg(reinterpret_cast<const int2 *>(count1) + g);
+  };
+  fetch_desc(2 * rel0);
+  uint4 frq = __ldg(reinterpret_cast<const uint4 *>(fr_l + rel0) + 1);
+  uint32_t mode = 0, mode_ext = 0, pcm_index = 0; bool emit = false;
+
+  double inv_sqrt2; asm volatile("mov.f64 %0, 0d3FE6A09E667F3BCD;" : "=d"(inv_sqrt2));     /* 0.70710678118654752440, kept in registers */
+  #pragma unroll 1
+  for (int32_t q = 0; q < 2 * nfr; q++) {                  /* q: granules done by this warp */
+    {
+      const int32_t gr = q & 1, rel = rel0 + (q >> 1);       /* frame relative to the launch */
+      const uint32_t b = q & 1;
+      f2 *blk = &W->xr[18 * gr][0], *prv = &W->xr[18 * (gr ^ 1)][0];
+      if (gr == 0) {
+        mode = (frq.y >> 8) & 0xffu; mode_ext = (frq.y >> 16) & 0xffu; pcm_index = frq.w;
+        emit = !(warm && q == 0) && ((frq.z >> 8) & P3_FRAME_DECODE);
+        if (q + 2 < 2 * nfr) frq = __ldg(reinterpret_cast<const uint4 *>(fr_l + rel + 1) + 1);
+      }
+      const bool st_on = mode == 1 && mode_ext != 0;
+      const bool is_on = st_on && (mode_ext & 1);
+
+      /* ---- this granule's parameters; effective count1 (Q6: an empty part keeps the slot's previous value) ---- */
+      int32_t ce0 = cq.x, ce1 = cq.y;
+      if (ga.w) ce0 = (int32_t)ga.w <= rel ? count1[(rel - (int32_t)ga.w) * 4 + 2 * gr] : st_in->count1[gr][0];
+      if (gb.w) ce1 = (int32_t)gb.w <= rel ? count1[(rel - (int32_t)gb.w) * 4 + 2 * gr + 1] : st_in->count1[gr][1];
+      if (rel == rel_last && lane == 0) { st_out->count1[gr][0] = ce0; st_out->count1[gr][1] = ce1; }
+      const sw_par p0 = sw_unpack(ga, ce0), p1 = sw_unpack(gb, ce1);
+      if (q + 1 < 2 * nfr) fetch_desc(2 * rel0 + q + 1);
+
+      sw_mbar_wait(&W->mbar[b], (q >> 1) & 1);
+      const uint8_t (*scf2)[P3_SCF_STRIDE] = reinterpret_cast<const uint8_t (*)[P3_SCF_STRIDE]>(W->scf[b]);
+
+      /* ---- band scales fl(t1*t2) (pdmp3.c:2127-2128, 2144-2146); same table layout as k_synth_fast: long blocks
+       *      index = sfb (0..21), short 3*sfb+win (0..38), mixed: long bands 0..7 sit in the unused short slots 0..7.
+       *      The scalefactor byte of short band 3*sfb+win is byte 24 + 3*sfb + win of the row. ---- */
+      #pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const uint32_t e = lane + 32 * k;
+        if (e < 80) {
+          const uint32_t c = e >= 40, bnd = e - 40 * c;
+          const uint32_t fsh = c ? p1.first_short : p0.first_short, mult = c ? p1.mult : p0.mult, pre = c ? p1.pre : p0.pre, sbg = c ? p1.sbg : p0.sbg;
+          const int32_t gg = c ? p1.gg : p0.gg;
+          const bool longband = fsh == 576 ? bnd < 22 : (fsh == 36 && bnd < 8);
+          const bool active = longband || (fsh < 576 && bnd < 39);
+          const bool has_sf = longband ? bnd < 21 : bnd < 36;
+          const uint32_t win = bnd % 3;
+          uint32_t sc = has_sf ? scf2[c][longband ? bnd : P3_SCF_S_OFF + bnd] : 0u;
+          /* pretab (pdmp3.c:2123): sfb 11..20 = 1,1,1,1,2,2,3,3,3,2, two bits each */
+          if (longband) sc += pre * ((bnd >= 11 && bnd < 21) ? (0xbfa55u >> (2 * (bnd - 11))) & 3u : 0u);
+          const int32_t qq = gg - (longband ? 0 : (int32_t)((sbg >> (8 * win)) & 0xffu));
+          const float v = __fmul_rn(FC.t1h[mult * sc], FC.t2[qq + P3_T2_BIAS]);
+          W->scale[bnd][c] = active ? v : 0.0f;
+        }
+      }
+      __syncwarp();
+
+      /* ---- A: requantize the 18 lines of subband `sb`, both channels (exact arithmetic of pdmp3.c:2121-2152) ---- */
+      f2 in[18];
+      {
+        const uint32_t *w0p = reinterpret_cast<const uint32_t *>(W->isb[b]) + 9 * sb;
+        const uint32_t *w1p = w0p + 288;
+        const float2 *scl = reinterpret_cast<const float2 *>(&W->scale[0][0]);
+        #pragma unroll
+        for (int i = 0; i < 9; i++) {
+          const uint32_t wa = w0p[i], wb = w1p[i];
+          #pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int m = 2 * i + h;
+            const float2 sc = scl[(sfbp[m / 6] >> (5 * (m % 6))) & 31u];
+            const int va = h ? (int)wa >> 16 : (int)(int16_t)(wa & 0xffffu), vb = h ? (int)wb >> 16 : (int)(int16_t)(wb & 0xffffu);
+            in[m] = f2_make(__fmul_rn(sc.x, __ldg(pow43s + va)), __fmul_rn(sc.y, __ldg(pow43s + vb)));   /* (t1*t2)*t3, t3 = sign*|is|^(4/3) */
+          }
+        }
+      }
+#ifndef SW_NOSLOW
+      if (p0.first_short < 576 || p1.first_short < 576) {          /* a short (or mixed) block in either channel: reordered gather, rare */
+        float *scr = reinterpret_cast<float *>(blk);             /* [2][576] */
+        #pragma unroll 1
+        for (int c = 0; c < 2; c++) {
+          const uint32_t fsh = c ? p1.first_short : p0.first_short;
+          const int16_t *isc = reinterpret_cast<const int16_t *>(W->isb[b]) + 576 * c;
+          #pragma unroll 1
+          for (uint32_t d = lane; d < 576; d += 32)
+            if (d >= fsh) { const uint32_t s = s_reo[d], sw = s_sfbw[s]; scr[576 * c + d] = fq_requant(T->pow43, isc[s], W->scale[3 * (sw & 15u) + (sw >> 4)][c]); }
+        }
+        __syncwarp();
+        const bool sh0 = 18 * sb >= p0.first_short, sh1 = 18 * sb >= p1.first_short;
+        #pragma unroll
+        for (int m = 0; m < 18; m++) {
+          float l = f2_x(in[m]), r = f2_y(in[m]);
+          if (sh0) l = scr[18 * sb + m];
+          if (sh1) r = scr[576 + 18 * sb + m];
+          in[m] = f2_make(l, r);
+        }
+        __syncwarp();
+      }
+#endif
+
+      /* ---- B: stereo (pdmp3.c:1916-1971) ---- */
+      const uint32_t c1r = (uint32_t)p1.c1;
+      const uint32_t msn = (st_on && (mode_ext & 2)) ? min((uint32_t)p0.c1, c1r) : 0u;      /* min(count1), sic (pdmp3.c:1920) */
+      if (18 * sb < msn) {
+        /* float sum times a double constant, rounded once to float (pdmp3.c:168,1923-1926) */
+        #pragma unroll
+        for (int m = 0; m < 18; m++) {
+          const float l = f2_x(in[m]), r = f2_y(in[m]);
+          const float a = __fadd_rn(l, r), d = __fsub_rn(l, r);
+          const float ml = __double2float_rn(__dmul_rn((double)a, inv_sqrt2)), mr = __double2float_rn(__dmul_rn((double)d, inv_sqrt2));
+          const bool on = 18 * sb + m < msn;
+          in[m] = f2_make(on ? ml : l, on ? mr : r);
+        }
+      }
+#ifndef SW_NOSLOW
+      if (is_on) {                                            /* intensity stereo: line by line through the scratch block, rare */
+        f2 *scr = blk;                                           /* [576] */
+        #pragma unroll
+        for (int m = 0; m < 18; m++) scr[18 * sb + m] = in[m];
+        __syncwarp();
+        const uint32_t first_short0 = p0.first_short;
+        const bool sh0 = first_short0 < 576;
+        #pragma unroll 1
+        for (uint32_t d = lane; d < 576; d += 32) {
+          if (d < msn) continue;
+          float l = f2_x(scr[d]), r = f2_y(scr[d]);
+          if (d >= first_short0) {
+            /* short-block intensity (pdmp3.c:2190-2220) in reordered position; Q4: assignment through an `unsigned` */
+            const uint32_t sw = s_sfbw[d], sfb = sw & 15u, win = sw >> 4;
+            if (sfb < 12 && 3u * T->sfb_s[sf][sfb] >= c1r && scf2[0][P3_SCF_S_OFF + 3 * sfb + win] != 7) {
+              const float x = (float)(unsigned)(long long)l; l = x; r = x;
+            }
+          } else {
+            const uint32_t sfb = T->line_sfb_l[sf][d], lim = sh0 ? 8u : 21u;                /* mixed: long sfb 0..7 only (pdmp3.c:1944) */
+            if (sfb < lim && T->sfb_l[sf][sfb] >= c1r) {
+              const uint32_t pp = scf2[0][sfb];                                             /* channel-0 scalefactor, sic (pdmp3.c:2163) */
+              if (pp != 7) { const float x = l; l = __fmul_rn(FC.is_l[pp & 7], x); r = __fmul_rn(FC.is_r[pp & 7], x); }
+            }
+          }
+          scr[d] = f2_make(l, r);
+        }
+        __syncwarp();
+        #pragma unroll
+        for (int m = 0; m < 18; m++) in[m] = scr[18 * sb + m];
+        __syncwarp();
+      }
+#endif
+
+      /* every lane is done with this buffer: bring in the granule after the next one */
+      __syncwarp();
+      if (q + 2 < 2 * nfr) issue(f_first + rel + 1, gr, b);
+
+      /* ---- C: antialias (pdmp3.c:1706-1732): the butterflies across a subband boundary take the neighbour lane's
+       *      lines through shuffles; both shuffles of a pair happen before either line is rewritten ---- */
+      {
+        const bool lo0 = sb >= 1 && sb < p0.sblim, hi0 = sb + 1 < p0.sblim;
+        const bool lo1 = sb >= 1 && sb < p1.sblim, hi1 = sb + 1 < p1.sblim;
+        #pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float ux = f2_x(in[i]), uy = f2_y(in[i]), lx = f2_x(in[17 - i]), ly = f2_y(in[17 - i]);
+          const float bx = __shfl_up_sync(0xffffffffu, lx, 1), by = __shfl_up_sync(0xffffffffu, ly, 1);       /* line 18sb-1-i */
+          const float ax = __shfl_down_sync(0xffffffffu, ux, 1), ay = __shfl_down_sync(0xffffffffu, uy, 1);   /* line 18(sb+1)+i */
+#ifndef SW_NOSLOW
+          if (p0.sblim == p1.sblim)
+#endif
+          {
+            const f2 u = in[i], l = in[17 - i];
+            if (lo0) in[i] = vadd(vmul(u, FC.cs[i]), vmul(f2_make(bx, by), FC.ca[i]));           /* ub (pdmp3.c:1726) */
+            if (hi0) in[17 - i] = vsub(vmul(l, FC.cs[i]), vmul(f2_make(ax, ay), FC.ca[i]));      /* lb (pdmp3.c:1725) */
+          }
+#ifndef SW_NOSLOW
+          else {
+            const float nux = lo0 ? __fadd_rn(__fmul_rn(ux, FC.cs[i]), __fmul_rn(bx, FC.ca[i])) : ux;
+            const float nuy = lo1 ? __fadd_rn(__fmul_rn(uy, FC.cs[i]), __fmul_rn(by, FC.ca[i])) : uy;
+            const float nlx = hi0 ? __fsub_rn(__fmul_rn(lx, FC.cs[i]), __fmul_rn(ax, FC.ca[i])) : lx;
+            const float nly = hi1 ? __fsub_rn(__fmul_rn(ly, FC.cs[i]), __fmul_rn(ay, FC.ca[i])) : ly;
+            in[i] = f2_make(nux, nuy); in[17 - i] = f2_make(nlx, nly);
+          }
+#endif
+        }
+      }
+
+      /* ---- D: IMDCT + window (pdmp3.c:1649-1700), overlap-add with the tail in registers (1774-1777),
+       *      frequency inversion (1738-1746); the subband samples go to the ring transposed [slot][subband] ---- */
+      {
+        const uint32_t bt0 = (p0.ws && p0.mixed && sb < 2) ? 0u : p0.bt, bt1 = (p1.ws && p1.mixed && sb < 2) ? 0u : p1.bt;
+        const float sgn = (sb & 1) ? -1.0f : 1.0f;
+#ifndef SW_NOSLOW
+        if (bt0 == bt1 && bt0 != 2)
+#endif
+        {
+          f2 t[18];
+          dct4_18<f2>(in, t);
+          /* 36-point IMDCT from the DCT-IV by symmetry (signs folded into swin): output p < 18 is overlap-added with
+           * the tail and leaves at once, output 18 + p becomes the new tail */
+          #pragma unroll
+          for (int k = 0; k < 9; k++) {
+            f2 ya = vadd(vmul(t[9 + k], FC.swin[bt0][k]), tail[k]);               /* rawout + store (pdmp3.c:1775) */
+            f2 yb = vadd(vmul(t[9 + k], FC.swin[bt0][17 - k]), tail[17 - k]);
+            if (k & 1) ya = vmul(ya, sgn); else yb = vmul(yb, sgn);               /* frequency inversion (1741-1743): odd slots of odd subbands */
+            blk[k * SW_PITCH + sb] = ya; blk[(17 - k) * SW_PITCH + sb] = yb;
+          }
+          #pragma unroll
+          for (int k = 0; k < 9; k++) { tail[8 - k] = vmul(t[k], FC.swin[bt0][26 - k]); tail[9 + k] = vmul(t[k], FC.swin[bt0][27 + k]); }
+        }
+#ifndef SW_NOSLOW
+        else {                                                      /* short block or different block types: one channel at a time */
+          float *blkf = reinterpret_cast<float *>(blk);
+          #pragma unroll 1
+          for (int c = 0; c < 2; c++) {
+            const uint32_t btc = c ? bt1 : bt0;
+            float v[18], xo[18], to[18];
+            #pragma unroll
+            for (int m = 0; m < 18; m++) v[m] = c ? f2_y(in[m]) : f2_x(in[m]);
+            if (btc != 2) {
+              float t[18];
+              dct4_18<float>(v, t);
+              #pragma unroll
+              for (int k = 0; k < 9; k++) {
+                to[8 - k] = __fmul_rn(t[k], FC.swin[btc][26 - k]); to[9 + k] = __fmul_rn(t[k], FC.swin[btc][27 + k]);
+                xo[k] = __fmul_rn(t[9 + k], FC.swin[btc][k]); xo[17 - k] = __fmul_rn(t[9 + k], FC.swin[btc][17 - k]);
+              }
+            } else {
+              float raw[36];
+              imdct_short(v, raw);
+              #pragma unroll
+              for (int i = 0; i < 18; i++) { xo[i] = raw[i]; to[i] = raw[18 + i]; }
+            }
+            #pragma unroll
+            for (int ss = 0; ss < 18; ss++) {
+              const float y = __fadd_rn(xo[ss], c ? f2_y(tail[ss]) : f2_x(tail[ss]));
+              blkf[2 * (ss * SW_PITCH + sb) + c] = (ss & 1) ? __fmul_rn(y, sgn) : y;
+              tail[ss] = c ? f2_make(f2_x(tail[ss]), to[ss]) : f2_make(to[ss], f2_y(tail[ss]));
+            }
+          }
+        }
+#endif
+      }
+      __syncwarp();
+
+      /* ---- E: 32-point DCT of each time slot, in place in its ring row ---- */
+      if (lane < 18) {
+        f2 *row = blk + lane * SW_PITCH;
+        f2 s[32];
+        #pragma unroll
+        for (int k = 0; k < 32; k++) s[k] = row[k];
+        dct2<32, f2>(s);
+        #pragma unroll
+        for (int k = 0; k < 32; k++) row[k] = s[k];
+      }
+      __syncwarp();
+
+      /* ---- F: 512-tap window from registers + PCM (pdmp3.c:2015-2041, 2307-2345) ---- */
+      if (emit) {
+        uint32_t *out = reinterpret_cast<uint32_t *>(pcm) + ((size_t)pcm_index * 1152 + gr * 576 + lane);
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {                              /* two runs of 9 slots over a 24-entry sliding window */
+          f2 sum[9];
+          #pragma unroll
+          for (int pass = 0; pass < 2; pass++) {                   /* even taps (column ia), then odd taps (column ib): half the live registers */
+            f2 A[24];                                              /* entry i = slot 9h + i - 15 of this granule (negative: previous granule) */
+            #pragma unroll
+            for (int i = 1 - pass; i < 24 - pass; i++) {           /* even taps touch entries 1..23, odd taps 0..22 */
+              const int rel = 9 * h + i - 15;
+              const f2 *rowp = rel < 0 ? prv + (18 + rel) * SW_PITCH : blk + rel * SW_PITCH;
+              A[i] = rowp[pass ? ib : ia];
+            }
+            #pragma unroll
+            for (int s9 = 0; s9 < 9; s9++) {
+              f2 acc = pass ? sum[s9] : f2_make(0.0f, 0.0f);
+              #pragma unroll
+              for (int k = 0; k < 8; k++) acc = pass ? vfma(A[15 + s9 - 2 * k - 1], co[k], acc) : vfma(A[15 + s9 - 2 * k], ce[k], acc);
+              sum[s9] = acc;
+            }
+          }
+          #pragma unroll
+          for (int s9 = 0; s9 < 9; s9++) out[(9 * h + s9) * 32] = sw_pcm2(sum[s9]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  /* ---- carried state out, after the last frame of the launch ---- */
+  if (c1 == f_end) {
+    #pragma unroll
+    for (int i = 0; i < 18; i++) { st_out->store[0][18 * sb + i] = f2_x(tail[i]); st_out->store[1][18 * sb + i] = f2_y(tail[i]); }
+    for (int age = 1; age <= 15; age++) {
+      const f2 v = W->xr[36 - age][lane];
+      st_out->xhist[0][age - 1][lane] = f2_x(v); st_out->xhist[1][age - 1][lane] = f2_y(v);
+    }
+  }
+}
+
+extern "C" size_t p3_synthw_smem_bytes(void) { return SW_LUT_BYTES + SW_WPB * sizeof(sw_warp_sm); }
+extern "C" int p3_synthw_warps_per_cta(void) { return SW_WPB; }

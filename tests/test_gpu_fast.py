@@ -62,9 +62,49 @@ def test_persistent_kernel_equals_two_kernel_path(fast_ctx, name):
     """k_decode_fused (one persistent launch, spectra through L2-resident scratch) must give the same
     bits as K1 + k_synth_fast (the path used when stage taps are requested)."""
     s, _ = H.synth(700, seed=5, **VARIANTS[name])
-    fast_ctx.reset(); a = fast_ctx.decode(s, lookahead=0)                  # persistent kernel
+    fast_ctx.set_synth_kernel(1)                                           # k_decode_fused shares k_synth_fast's arithmetic
+    fast_ctx.reset(); a = fast_ctx.decode(s, lookahead=0)                  # persistent kernel (with P3_PERSIST=1)
     fast_ctx.reset(); b, _ = fast_ctx.decode(s, lookahead=0, taps=True)    # two kernels
+    fast_ctx.set_synth_kernel(0)
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", [n for n in VARIANTS if VARIANTS[n].get("mode", 0) != 3])
+def test_warp_kernel(fast_ctx, name):
+    """k_synth_warp (the default for stereo batches: both channels packed in FFMA2 arithmetic, one autonomous warp
+    per run of frames): PCM within 1 LSB of the oracle on every stream type, bit-identical whatever the run length
+    (run boundaries, warm-up frames), and within 1 LSB of k_synth_fast (same operations; ptxas contracts some of the
+    packed mul+add pairs into FFMA2, so the two are not bit-identical)."""
+    s, _ = H.synth(300, seed=17, **VARIANTS[name])
+    o = H.oracle_decode(s, lookahead=0)
+    fast_ctx.reset(); fast_ctx.set_synth_kernel(1); cta = fast_ctx.decode(s, lookahead=0)
+    fast_ctx.set_synth_kernel(0)
+    assert cta.shape[2] == 2
+    got = {}
+    for fpw in (32, 5, 1):
+        fast_ctx.reset(); fast_ctx.set_frames_per_cta(fpw); got[fpw] = fast_ctx.decode(s, lookahead=0)
+    fast_ctx.set_frames_per_cta(32)
+    assert np.array_equal(got[32], got[5]) and np.array_equal(got[32], got[1]), "result depends on the run length"
+    d = np.abs(got[32].astype(np.int32) - o["pcm"].astype(np.int32))
+    assert d.max() <= PCM_TOL_LSB, "max |diff| vs oracle = %d LSB" % d.max()
+    assert (d == 0).mean() > 0.90
+    assert np.abs(got[32].astype(np.int32) - cta.astype(np.int32)).max() <= 1
+
+
+def test_warp_kernel_batches_with_carried_state(fast_ctx):
+    """four batches with the filter state carried in the context == one batch (k_synth_warp's state in/out)"""
+    import pdmp3_b200
+    s, _ = H.synth(260, seed=9, **H.CONFIGS["cfg4_vbr_mixed"])
+    fast_ctx.reset(); a = fast_ctx.decode(s, lookahead=0)
+    fast_ctx.reset()
+    st = pdmp3_b200._binding.P3ParseState(0, 0, 0, -1, -1)
+    pos, parts = 0, []
+    while True:
+        p = pdmp3_b200.parse_stream(s[pos:], lookahead=0, max_frames=70, state=st)
+        if p.n_frames == 0: break
+        for f in range(p.n_frames): p.c.frames[f].pcm_index = f
+        parts.append(fast_ctx.decode_parsed(p)); pos += p.consumed
+    assert np.array_equal(a, np.concatenate(parts))
 
 
 def test_one_million_frames_properties(fast_ctx):
