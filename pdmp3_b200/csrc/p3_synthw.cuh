@@ -27,7 +27,8 @@ struct __align__(16) sw_warp_sm {
   uint8_t scf[2][128];              /* [buffer][ch][64]: its scalefactors (TMA destination) */
   f2 xr[36][SW_PITCH];              /* two blocks of 18 DCT rows; the block of the granule about to be transformed doubles as scratch */
   float scale[40][2];               /* band scales fl(t1*t2) of the current granule, [band][ch] */
-  unsigned long long mbar[2];
+  struct { uint4 fr; uint4 gc[4]; int32_t c1[4]; } desc[2];   /* [frame parity] second half of p3_frame, the 4 p3_gc, their count1 (TMA destination) */
+  unsigned long long mbar[2], dbar[2];
 };
 
 __device__ __forceinline__ uint32_t sw_s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,58 +121,53 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   #pragma unroll
   for (int i = 0; i < 18; i++) tail[i] = warm ? f2_make(0.0f, 0.0f) : f2_make(st_in->store[0][18 * sb + i], st_in->store[1][18 * sb + i]);
   for (uint32_t i = lane; i < 36 * SW_PITCH; i += 32) (&W->xr[0][0])[i] = f2_make(0.0f, 0.0f);
-  if (lane == 0) { sw_mbar_init(&W->mbar[0], 1); sw_mbar_init(&W->mbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (lane == 0) { sw_mbar_init(&W->mbar[0], 1); sw_mbar_init(&W->mbar[1], 1); sw_mbar_init(&W->dbar[0], 1); sw_mbar_init(&W->dbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncwarp();
   if (!warm)
     for (int age = 1; age <= 15; age++) W->xr[36 - age][lane] = f2_make(st_in->xhist[0][age - 1][lane], st_in->xhist[1][age - 1][lane]);
   __syncwarp();
 
-  auto issue = [&](int64_t f, int gr, int b) {             /* TMA: spectra + scalefactors of granule (f, gr) -> buffer b */
-    if (lane == 0) {
-      const int64_t o = (f - f_first) * 4 + 2 * gr;
-      sw_mbar_expect(&W->mbar[b], 2304 + 128);
-      sw_bulk_g2s(W->isb[b], is_in + o * 576, 2304, &W->mbar[b]);
-      sw_bulk_g2s(W->scf[b], scf + o * P3_SCF_STRIDE, 128, &W->mbar[b]);
-    }
-  };
   const int32_t rel0 = (int32_t)(fs - f_first), nfr = (int32_t)(c1 - fs);   /* first frame (relative to the launch) and frames of this warp */
   const int32_t rel_last = (int32_t)(f_end - 1 - f_first);
   const p3_frame *fr_l = frames + f_first; const p3_gc *gc_l = gcs + 4 * f_first;
-  issue(fs, 0, 0); issue(fs, 1, 1);
-
-  /* descriptors of a granule: side info of both channels and their count1, fetched one granule ahead */
-  uint4 ga, gb; int2 cq;
-  auto fetch_desc = [&](int32_t g /* granule index relative to the launch */) {
-    ga = __ldg(reinterpret_cast<const uint4 *>(gc_l) + 2 * g);
-    gb = __ldg(reinterpret_cast<const uint4 *>(gc_l) + 2 * g + 1);
-    cq = __ldg(reinterpret_cast<const int2 *>(count1) + g);
+  auto issue = [&](int32_t rel, int gr, int b) {           /* TMA: spectra + scalefactors of granule (rel, gr) -> buffer b */
+    if (lane == 0) {
+      const int32_t o = rel * 4 + 2 * gr;
+      sw_mbar_expect(&W->mbar[b], 2304 + 128);
+      sw_bulk_g2s(W->isb[b], is_in + (size_t)o * 576, 2304, &W->mbar[b]);
+      sw_bulk_g2s(W->scf[b], scf + (size_t)o * P3_SCF_STRIDE, 128, &W->mbar[b]);
+    }
   };
-  fetch_desc(2 * rel0);
-  uint4 frq = __ldg(reinterpret_cast<const uint4 *>(fr_l + rel0) + 1);
-  uint32_t mode = 0, mode_ext = 0, pcm_index = 0; bool emit = false;
+  auto issue_desc = [&](int32_t rel, int d) {              /* TMA: the descriptors of frame `rel` -> descriptor buffer d */
+    if (lane == 0) {
+      sw_mbar_expect(&W->dbar[d], 96);
+      sw_bulk_g2s(&W->desc[d].fr, reinterpret_cast<const uint8_t *>(fr_l + rel) + 16, 16, &W->dbar[d]);
+      sw_bulk_g2s(&W->desc[d].gc[0], gc_l + 4 * (size_t)rel, 64, &W->dbar[d]);
+      sw_bulk_g2s(&W->desc[d].c1[0], count1 + 4 * (size_t)rel, 16, &W->dbar[d]);
+    }
+  };
+  issue_desc(rel0, 0); if (nfr > 1) issue_desc(rel0 + 1, 1);
+  issue(rel0, 0, 0); issue(rel0, 1, 1);
 
   double inv_sqrt2; asm volatile("mov.f64 %0, 0d3FE6A09E667F3BCD;" : "=d"(inv_sqrt2));     /* 0.70710678118654752440, kept in registers */
   #pragma unroll 1
   for (int32_t q = 0; q < 2 * nfr; q++) {                  /* q: granules done by this warp */
     {
-      const int32_t gr = q & 1, rel = rel0 + (q >> 1);       /* frame relative to the launch */
+      const int32_t gr = q & 1, fi = q >> 1, rel = rel0 + fi; /* frame index within the warp's run / relative to the launch */
       const uint32_t b = q & 1;
       f2 *blk = &W->xr[18 * gr][0], *prv = &W->xr[18 * (gr ^ 1)][0];
-      if (gr == 0) {
-        mode = (frq.y >> 8) & 0xffu; mode_ext = (frq.y >> 16) & 0xffu; pcm_index = frq.w;
-        emit = !(warm && q == 0) && ((frq.z >> 8) & P3_FRAME_DECODE);
-        if (q + 2 < 2 * nfr) frq = __ldg(reinterpret_cast<const uint4 *>(fr_l + rel + 1) + 1);
-      }
+      if (gr == 0) sw_mbar_wait(&W->dbar[fi & 1], (fi >> 1) & 1);
+      const uint4 frq = W->desc[fi & 1].fr, ga = W->desc[fi & 1].gc[2 * gr], gb = W->desc[fi & 1].gc[2 * gr + 1];
+      const uint32_t mode = (frq.y >> 8) & 0xffu, mode_ext = (frq.y >> 16) & 0xffu;
       const bool st_on = mode == 1 && mode_ext != 0;
       const bool is_on = st_on && (mode_ext & 1);
 
       /* ---- this granule's parameters; effective count1 (Q6: an empty part keeps the slot's previous value) ---- */
-      int32_t ce0 = cq.x, ce1 = cq.y;
+      int32_t ce0 = W->desc[fi & 1].c1[2 * gr], ce1 = W->desc[fi & 1].c1[2 * gr + 1];
       if (ga.w) ce0 = (int32_t)ga.w <= rel ? count1[(rel - (int32_t)ga.w) * 4 + 2 * gr] : st_in->count1[gr][0];
       if (gb.w) ce1 = (int32_t)gb.w <= rel ? count1[(rel - (int32_t)gb.w) * 4 + 2 * gr + 1] : st_in->count1[gr][1];
       if (rel == rel_last && lane == 0) { st_out->count1[gr][0] = ce0; st_out->count1[gr][1] = ce1; }
       const sw_par p0 = sw_unpack(ga, ce0), p1 = sw_unpack(gb, ce1);
-      if (q + 1 < 2 * nfr) fetch_desc(2 * rel0 + q + 1);
 
       sw_mbar_wait(&W->mbar[b], (q >> 1) & 1);
       const uint8_t (*scf2)[P3_SCF_STRIDE] = reinterpret_cast<const uint8_t (*)[P3_SCF_STRIDE]>(W->scf[b]);
@@ -292,7 +288,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
 
       /* every lane is done with this buffer: bring in the granule after the next one */
       __syncwarp();
-      if (q + 2 < 2 * nfr) issue(f_first + rel + 1, gr, b);
+      if (q + 2 < 2 * nfr) issue(rel + 1, gr, b);
 
       /* ---- C: antialias (pdmp3.c:1706-1732): the butterflies across a subband boundary take the neighbour lane's
        *      lines through shuffles; both shuffles of a pair happen before either line is rewritten ---- */
@@ -395,8 +391,8 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       __syncwarp();
 
       /* ---- F: 512-tap window from registers + PCM (pdmp3.c:2015-2041, 2307-2345) ---- */
-      if (emit) {
-        uint32_t *out = reinterpret_cast<uint32_t *>(pcm) + ((size_t)pcm_index * 1152 + gr * 576 + lane);
+      if (!(warm && fi == 0) && ((frq.z >> 8) & P3_FRAME_DECODE)) {
+        uint32_t *out = reinterpret_cast<uint32_t *>(pcm) + ((size_t)frq.w * 1152 + gr * 576 + lane);
         #pragma unroll
         for (int h = 0; h < 2; h++) {                              /* two runs of 9 slots over a 24-entry sliding window */
           f2 sum[9];
@@ -422,6 +418,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
         }
       }
       __syncwarp();
+      if (gr == 1 && fi + 2 < nfr) issue_desc(rel + 2, fi & 1);   /* both granules of the frame are done with this descriptor buffer */
     }
   }
 
