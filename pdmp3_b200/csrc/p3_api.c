@@ -88,14 +88,16 @@ int pdmp3_open_feed(pdmp3_handle *id)
 static size_t in_filled(const pdmp3_handle *id) { return id->iend - id->istart; }
 static size_t in_free(const pdmp3_handle *id) { return id->cap - in_filled(id); }
 
-/* large feeds are copied by a few threads (a single core moves ~10 GB/s, the PCIe link 50+) */
+/* large feeds are copied by several threads (a single core moves ~10 GB/s, the PCIe link 50+): one per online core, at most 32 */
 typedef struct { unsigned char *d; const unsigned char *s; size_t n; } cpjob;
 static void *cp_worker(void *a) { cpjob *j = (cpjob *)a; memcpy(j->d, j->s, j->n); return NULL; }
 static void big_memcpy(unsigned char *d, const unsigned char *s, size_t n)
 {
-  enum { NT = 8 };
+  enum { NTMAX = 32 };
   if (n < ((size_t)32 << 20)) { memcpy(d, s, n); return; }
-  pthread_t th[NT]; cpjob jb[NT]; int ok[NT];
+  long nc = sysconf(_SC_NPROCESSORS_ONLN);
+  const int NT = nc < 2 ? 2 : nc > NTMAX ? NTMAX : (int)nc;
+  pthread_t th[NTMAX]; cpjob jb[NTMAX]; int ok[NTMAX];
   for (int t = 0; t < NT; t++) {
     size_t lo = n * t / NT, hi = n * (t + 1) / NT;
     jb[t].d = d + lo; jb[t].s = s + lo; jb[t].n = hi - lo;

@@ -4,55 +4,57 @@
 #pragma once
 #include "p3_device.cuh"
 
-/* MSB-first bit reader over the big-endian words in shared memory: two consecutive words in registers
- * plus a bit offset, so a 32-bit look-ahead is ONE funnel shift and advancing is branch-free (the next
- * word is loaded unconditionally, off the critical path).  The reference does a byte access per BIT
- * (pdmp3.c:1489-1527). */
+/* MSB-first bit reader over the big-endian words in shared memory: two consecutive words in registers plus a bit
+ * offset, so a 32-bit look-ahead is ONE funnel shift; advancing adds to the offset and, when it crosses a word,
+ * shifts the pair and loads the next word under a predicate -- no branch, one shared-memory load per 32 bits.
+ * The reference does a byte access per BIT (pdmp3.c:1489-1527). */
 struct k1_bits {
-  const uint32_t *sw; uint32_t cur, nxt, off, widx;       /* cur = sw[widx], nxt = sw[widx+1], off in 0..31 */
+  const uint32_t *wp; uint32_t hi, lo, off;               /* hi:lo = words at wp[-2], wp[-1]; off in 0..31 */
+  const uint32_t *base;
   __device__ __forceinline__ void init(const uint32_t *s, uint32_t bitpos)
   {
-    sw = s; widx = bitpos >> 5; off = bitpos & 31; cur = s[widx]; nxt = s[widx + 1];
+    base = s; wp = s + (bitpos >> 5) + 2; off = bitpos & 31; hi = wp[-2]; lo = wp[-1];
   }
-  __device__ __forceinline__ uint32_t pos() const { return widx * 32 + off; }
-  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(nxt, cur, off); }   /* next 32 bits */
+  __device__ __forceinline__ uint32_t pos() const { return (uint32_t)(wp - base - 2) * 32 + off; }
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, off); }     /* next 32 bits */
   __device__ __forceinline__ void skip(uint32_t n)                                              /* n <= 32 */
   {
-    const uint32_t w = sw[widx + 2];
     off += n;
-    const bool adv = off >= 32;
-    cur = adv ? nxt : cur; nxt = adv ? w : nxt;
-    widx += adv ? 1u : 0u; off &= 31u;
+    if (off >= 32) { hi = lo; lo = *wp; wp++; }
+    off &= 31u;
   }
 };
 
-/* one Huffman-coded pair (pdmp3.c:1593-1643); tb = base | pbits<<16 | linbits<<24 */
-__device__ __forceinline__ uint32_t k1_pair(k1_bits &bb, const uint16_t *lut, uint32_t tb)
+/* One Huffman-coded pair (pdmp3.c:1593-1643) as a packed int16 pair.  tl: the code book's LUT, sh = 32 - width of
+ * its first level.  Fast path (no escape): the LUT leaf gives x, y and the code length; the sign bits follow the
+ * code word, x's first; a zero value has no sign bit, and negating zero is harmless, so no test is needed. */
+__device__ __forceinline__ uint32_t k1_pair(k1_bits &bb, const uint16_t *tl, uint32_t sh, uint32_t linbits)
 {
-  const uint32_t base = tb & 0xffffu, linbits = (tb >> 24) & 31u;
   const uint32_t w0 = bb.peek();
-  uint32_t cw = (tb >> 16) & 31u, used = 0;
-  uint32_t e = lut[base + (w0 >> (32 - cw))];
-  while (e & 0x8000u) {                                 /* next LUT level (codes longer than 8 bits) */
-    used += cw; cw = (e >> 10) & 7;
-    e = lut[base + (e & 1023u) + ((w0 << used) >> (32 - cw))];
+  uint32_t e = tl[w0 >> sh], used = 0;
+  if (e & 0x8000u) {                                      /* codes longer than the first level: walk the next levels */
+    uint32_t cw = 32 - sh;
+    do { used += cw; cw = (e >> 10) & 7; e = tl[(e & 1023u) + ((w0 << used) >> (32 - cw))]; } while (e & 0x8000u);
   }
   used += (e >> 8) & 31;
   int x = (e >> 4) & 15, y = e & 15;
-  /* bits after the code word: x linbits, x sign, y linbits, y sign (pdmp3.c:1637-1640).  If code + worst-case
-   * escapes cannot fit the 32-bit window (only tables with >= 8 linbits), re-read after the code word. */
-  uint32_t w = w0 << used, total = used;
-  if (used + 2 * linbits + 2 > 32) { bb.skip(used); w = bb.peek(); total = 0; }
-  const uint32_t ex = x == 15 ? linbits : 0u;
-  x += (int)((w >> 1) >> (31 - ex)); w <<= ex;
-  const uint32_t sx = x != 0;
-  x = (sx & (w >> 31)) ? -x : x; w <<= sx;
-  const uint32_t ey = y == 15 ? linbits : 0u;
-  y += (int)((w >> 1) >> (31 - ey)); w <<= ey;
-  const uint32_t sy = y != 0;
-  y = (sy & (w >> 31)) ? -y : y;
-  bb.skip(total + ex + sx + ey + sy);
-  return (uint32_t)(x & 0xffff) | ((uint32_t)y << 16);
+  if ((e & 0x4000u) && linbits) {                         /* x or y is 15 and the table has linbits (pdmp3.c:1637-1640): rare */
+    bb.skip(used);
+    uint32_t w = bb.peek(), n = 0;
+    if (x == 15) { x += (int)(w >> (32 - linbits)); w <<= linbits; n += linbits; }
+    if (x) { if ((int)w < 0) x = -x; w <<= 1; n++; }
+    if (y == 15) { y += (int)(w >> (32 - linbits)); w <<= linbits; n += linbits; }
+    if (y) { if ((int)w < 0) y = -y; n++; }
+    bb.skip(n);
+    return __byte_perm((uint32_t)x, (uint32_t)y, 0x5410);
+  }
+  const uint32_t nx = min(x, 1), ny = min(y, 1);
+  uint32_t w = w0 << used;
+  int m = (int)w >> 31; x = (x ^ m) - m;                  /* the bit after the code word is x's sign (if x != 0) */
+  w <<= nx;
+  m = (int)w >> 31; y = (y ^ m) - m;
+  bb.skip(used + nx + ny);
+  return __byte_perm((uint32_t)x, (uint32_t)y, 0x5410);    /* (x & 0xffff) | y << 16 */
 }
 
 /* Per-thread output staging: 8 words (16 spectral values = half a 32-byte sector) are collected in
@@ -182,22 +184,38 @@ __device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw, const uint1
       if (is_short) { r1s = 36; r2s = 576; }
       else { r1s = T->sfb_l[fr.sfreq][P3_GC_REG0(g) + 1]; r2s = T->sfb_l[fr.sfreq][P3_GC_REG0(g) + P3_GC_REG1(g) + 2]; }
       const uint32_t bv2 = 2 * P3_GC_BIGV(g);
-      uint32_t tbs[3];
+      const uint16_t *tls[3]; uint32_t shs[3], lbs[3];
       #pragma unroll
       for (int r = 0; r < 3; r++) {
         const uint32_t t = P3_GC_TSEL(g, r);
         const int book = T->table_book[t];
-        tbs[r] = book < 0 ? 0xffffffffu : ((uint32_t)T->book_base[book] | (uint32_t)T->book_pbits[book] << 16 | (uint32_t)T->table_linbits[t] << 24);
+        /* empty tables 0/4/14: zeros, no bits (pdmp3.c:1599-1602) = a pseudo book whose every leaf is (0, 0, length 0) */
+        tls[r] = lut + (book < 0 ? T->hlut_zero : T->book_base[book]);
+        shs[r] = 32u - (book < 0 ? 1u : T->book_pbits[book]);
+        lbs[r] = book < 0 ? 0u : T->table_linbits[t];
       }
-      /* one loop over all big_values pairs; the table changes at the region boundaries, so every lane of
-       * the warp stays in the same loop whatever its region split */
-      uint32_t tb = tbs[0];
+      /* one loop over all big_values pairs; the table changes at the region boundaries, so every lane of the warp
+       * stays in the same loop whatever its region split.  Four pairs (half a sector) per iteration leave straight
+       * from registers as one 16-byte store; the up to three pairs left over go through the staging ring below. */
+      const uint16_t *tl = tls[0]; uint32_t sh = shs[0], lb = lbs[0];
+      uint32_t nsw = r1s;                                   /* next value index at which the table changes */
       k1_bits bb; bb.init(sw, pos);
-      for (uint32_t i = 0; i < bv2; i += 2) {
-        if (i == r1s) tb = tbs[1];
-        if (i == r2s) tb = tbs[2];
-        ob.put(tb == 0xffffffffu ? 0u : k1_pair(bb, lut, tb));            /* empty tables: zeros, no bits (pdmp3.c:1599-1602) */
+      uint32_t i = 0;
+      auto pair_at = [&](uint32_t at) -> uint32_t {
+        if (at == nsw) {
+          if (at == r1s) { tl = tls[1]; sh = shs[1]; lb = lbs[1]; }
+          if (at == r2s) { tl = tls[2]; sh = shs[2]; lb = lbs[2]; }
+          nsw = r2s > at ? r2s : 0xffffffffu;
+        }
+        return k1_pair(bb, tl, sh, lb);
+      };
+      for (; i + 8 <= bv2; i += 8) {
+        uint4 o;
+        o.x = pair_at(i); o.y = pair_at(i + 2); o.z = pair_at(i + 4); o.w = pair_at(i + 6);
+        ob.dst[i >> 3] = o;
       }
+      ob.pw = i >> 1;
+      for (; i < bv2; i += 2) ob.put(pair_at(i));
       /* count1 quads (pdmp3.c:2091-2103) */
       uint32_t is_pos = bv2;
       const bool tabB = P3_GC_C1TAB(g);                  /* reference quirk Q1: table B = leaf 0011, no code bits */

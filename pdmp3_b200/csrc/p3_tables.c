@@ -44,7 +44,7 @@ static void build_level(const p3_hcode *c, int n, int prefix_len, uint32_t prefi
     if (rem <= width) {                 /* leaf, replicated over the don't-care bits */
       uint32_t lo = (c[k].code & ((1u << rem) - 1)) << (width - rem);
       for (uint32_t j = 0; j < (1u << (width - rem)); j++)
-        g_t.hlut[at + lo + j] = (uint16_t)((rem << 8) | (c[k].x << 4) | c[k].y);
+        g_t.hlut[at + lo + j] = (uint16_t)((rem << 8) | (c[k].x << 4) | c[k].y | ((c[k].x == 15 || c[k].y == 15) ? 0x4000 : 0));
     }
   }
   /* links: group the longer codes by their next `width` bits */
@@ -77,6 +77,8 @@ static void build_huffman(void)
     g_fill += 1u << pb;
     build_level(c, n, 0, 0, pb, g_base);
   }
+  /* pseudo book of the empty tables 0/4/14 (pdmp3.c:1599-1602): whatever bit comes next, a leaf of length 0 with x = y = 0 */
+  g_t.hlut_zero = g_fill; g_t.hlut[g_fill] = g_t.hlut[g_fill + 1] = 0; g_fill += 2;
   g_t.hlut_used = g_fill;
   for (int t = 0; t < 34; t++) { g_t.table_book[t] = p3_table_book[t]; g_t.table_linbits[t] = p3_table_linbits[t]; }
 }

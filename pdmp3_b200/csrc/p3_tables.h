@@ -25,7 +25,8 @@ extern "C" {
 typedef struct { uint8_t len; uint32_t code; uint8_t x, y; } p3_hcode;
 
 /* Huffman LUT entry (u16):
- *   leaf: bit15=0, bits12..8 = code bits consumed AT THIS LEVEL, bits7..4 = x, bits3..0 = y
+ *   leaf: bit15=0, bit14 = x or y is 15 (an escape if the table has linbits), bits12..8 = code bits consumed AT THIS LEVEL,
+ *         bits7..4 = x, bits3..0 = y
  *   link: bit15=1, bits12..10 = width w of the next level, bits9..0 = offset of the next level
  *         relative to the book base; the caller consumes this level's full width and indexes
  *         the next level with the following w bits. */
@@ -56,6 +57,7 @@ typedef struct {
   int8_t   table_book[36];         /* -1: empty table (0, 4, 14) */
   uint8_t  table_linbits[36];
   uint32_t hlut_used;
+  uint32_t hlut_zero;              /* two all-zero leaves: the code book of the empty tables 0/4/14 */
 } p3_tables;
 
 const p3_tables *p3_tables_get(void);
