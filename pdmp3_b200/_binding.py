@@ -8,7 +8,7 @@ PDMP3_ENC_SIGNED_16 = 0x80 | 0x40 | 0x10
 MODE_EXACT, MODE_FAST = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBPATH = os.path.join(_HERE, "libpdmp3_b200.so")
+_LIBPATH = os.environ.get("P3_LIB") or os.path.join(_HERE, "libpdmp3_b200.so")     # P3_LIB: kernel-variant experiments
 
 
 class P3Error(RuntimeError):

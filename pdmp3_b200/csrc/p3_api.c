@@ -26,6 +26,9 @@
 #include <fcntl.h>
 #include <unistd.h>
 #include <pthread.h>
+#include <time.h>
+
+static double now_ms(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
 
 #define P3_DEFAULT_RING 16384u              /* INBUF_SIZE (pdmp3.c:123) */
 #define P3_API_CHUNK    32768               /* frames per GPU batch inside one pdmp3_read() */
@@ -137,6 +140,7 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
 {
   if (!(id && outmemory && outsize && done)) return PDMP3_ERR;
   int res = PDMP3_ERR, inflight = 0;
+  const int trace = getenv("P3_TRACE") != NULL; double t_parse = 0, t_decode = 0, t_sync = 0; int nb = 0;
   *done = 0;
   if (id->pend_pos < id->pend_end) {                /* rest of a previously decoded frame (pdmp3.c:2437-2442) */
     size_t n = id->pend_end - id->pend_pos; if (n > outsize) n = outsize;
@@ -163,7 +167,9 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
       if (!id->dfr[k]) { id->dfr[k] = (p3_frame *)p3_host_alloc(sizeof(p3_frame) * P3_API_CHUNK); id->dgc[k] = (p3_gc *)p3_host_alloc(sizeof(p3_gc) * 4 * P3_API_CHUNK); }
       if (id->dfr[k] && id->dgc[k]) { dfr = id->dfr[k]; dgc = id->dgc[k]; }
     }
+    double t0 = trace ? now_ms() : 0;
     if (p3_parse_into(id->in + id->istart, in_filled(id), &po, &ps, &pb, dfr, dgc, P3_API_CHUNK) != P3_OK) { res = PDMP3_ERR; break; }
+    if (trace) { t_parse += now_ms() - t0; nb++; }
     if (pb.n_frames == 0) {
       int stop = pb.stop;
       p3_parsed_free(&pb);
@@ -184,8 +190,10 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
     for (int64_t f = 0; f < pb.n_frames; f++) pb.frames[f].pcm_index = (uint32_t)f;   /* slots restart at 0 for every batch */
     int64_t nfr = pb.n_frames; uint64_t used = pb.consumed; int sf_last = pb.frames[pb.n_frames - 1].sfreq;
     const uint64_t upl = in_filled(id) < used + 64 ? in_filled(id) : used + 64;   /* bytes this batch can touch */
+    t0 = trace ? now_ms() : 0;
     int rc = direct ? p3_decode_batch_async(id->ctx, id->in + id->istart, upl, &pb, target)
                     : p3_decode_batch(id->ctx, id->in + id->istart, upl, &pb, target, NULL);
+    if (trace) t_decode += now_ms() - t0;
     p3_parsed_free(&pb);                                                     /* (the async call took the arrays over) */
     if (rc != P3_OK) { fprintf(stderr, "pdmp3_b200: %s\n", p3_last_error()); res = PDMP3_ERR; break; }
     inflight |= direct;
@@ -203,7 +211,9 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
     }
     res = PDMP3_OK;
   }
-  if (inflight && p3_batch_sync(id->ctx) != P3_OK) { fprintf(stderr, "pdmp3_b200: %s\n", p3_last_error()); res = PDMP3_ERR; }
+  { double t0 = trace ? now_ms() : 0;
+    if (inflight && p3_batch_sync(id->ctx) != P3_OK) { fprintf(stderr, "pdmp3_b200: %s\n", p3_last_error()); res = PDMP3_ERR; }
+    if (trace) { t_sync = now_ms() - t0; fprintf(stderr, "pdmp3_read: %d batches, parse %.1f ms, enqueue (incl. waiting for a slot) %.1f ms, final sync %.1f ms\n", nb, t_parse, t_decode, t_sync); } }
   if (id->istart == id->iend) id->istart = id->iend = 0;
   if (id->new_header == 1 && res == PDMP3_OK) res = PDMP3_NEW_FORMAT;       /* pdmp3.c:2470-2472 */
   return res;

@@ -21,6 +21,9 @@ extern "C" __global__ void k_synth_warp(const p3_frame *frames, const p3_gc *gcs
 extern "C" __global__ void k_synth_fast(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_cta,
     const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, float *xr_tap, float *y_tap);
 
+#include <time.h>
+static double now_ms(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; }
+static double g_tr_wait, g_tr_stage, g_tr_launch; static int g_trace = -1;     /* P3_TRACE=1: where the host time of the async path goes */
 static thread_local char g_err[512];
 static int fail(int code, const char *fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap); return code; }
 extern "C" const char *p3_last_error(void) { return g_err; }
@@ -386,6 +389,7 @@ extern "C" int p3_batch_sync(p3_ctx *c)
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->s_h2d)); CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->s_d2h));
   for (int i = 0; i < 2; i++) slot_release(&c->slot[i]);
+  if (g_trace > 0 && g_tr_stage > 0) { fprintf(stderr, "p3 async: slot wait %.1f ms, stage %.1f ms, launch %.1f ms\n", g_tr_wait, g_tr_stage, g_tr_launch); g_tr_wait = g_tr_stage = g_tr_launch = 0; }
   return P3_OK;
 }
 
@@ -439,9 +443,13 @@ extern "C" int p3_decode_batch_async(p3_ctx *c, const uint8_t *raw, uint64_t raw
   c->taps = 0;
   c->cur_slot ^= 1;
   p3_slot *sl = &c->slot[c->cur_slot];
+  if (g_trace < 0) g_trace = getenv("P3_TRACE") != NULL;
+  double t0 = g_trace ? now_ms() : 0;
   slot_release(sl);                                        /* wait for the batch that used this slot two calls ago */
+  double t1 = g_trace ? now_ms() : 0;
   int rc = stage_batch(c, sl, raw, raw_bytes, b, c->s_h2d);
   if (rc) return rc;
+  double t2 = g_trace ? now_ms() : 0;
   if (!b->external) { sl->keep = *b; sl->have_keep = 1; b->frames = NULL; b->gcs = NULL; }   /* caller-owned arrays: the caller rotates them */
   CK(cudaEventRecord(sl->h2d_done, c->s_h2d));
   CK(cudaStreamWaitEvent(c->stream, sl->h2d_done, 0));
@@ -455,6 +463,7 @@ extern "C" int p3_decode_batch_async(p3_ctx *c, const uint8_t *raw, uint64_t raw
    * its next stage_batch() waits for d2h_done through slot_release() */
   sl->busy = 1;
   if (c->have_next_tail) { memcpy(c->h_tail, c->next_tail, 512); c->have_next_tail = 0; }
+  if (g_trace) { g_tr_wait += t1 - t0; g_tr_stage += t2 - t1; g_tr_launch += now_ms() - t2; }
   return P3_OK;
 }
 

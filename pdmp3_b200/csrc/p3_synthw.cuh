@@ -18,13 +18,21 @@
  *   - the Huffman output of the next granules (2304 B of spectra + 128 B of scalefactors) is brought in by the
  *     TMA engine (cp.async.bulk, completion on an mbarrier) two granules ahead, no registers involved.
  */
+#ifndef SW_WPB
 #define SW_WPB    4                 /* warps per CTA (each one independent) */
+#endif
+#ifndef SW_NBUF
+#define SW_NBUF   2                 /* spectra buffers per warp: 2 = fetched two granules ahead, 1 = one granule ahead (less shared memory) */
+#endif
+#ifndef SW_MINB
+#define SW_MINB   3                 /* CTAs per SM the register allocation aims at */
+#endif
 #define SW_PITCH  33                /* f2 elements per DCT row: 66 words -> conflict-free for row-per-lane and column-per-lane access */
-#define SW_LUT_BYTES 1728           /* CTA-shared: reorder_src u16[576] | line_sfbw_s u8[576] */
+#define SW_LUT_BYTES (1728 + 1440)  /* CTA-shared: reorder_src u16[576] | line_sfbw_s u8[576] | t1h f32[40] | t2 f32[320] */
 
 struct __align__(16) sw_warp_sm {
-  uint8_t isb[2][2304];             /* [buffer][ch][576] int16: Huffman output of one granule (TMA destination) */
-  uint8_t scf[2][128];              /* [buffer][ch][64]: its scalefactors (TMA destination) */
+  uint8_t isb[SW_NBUF][2304];             /* [buffer][ch][576] int16: Huffman output of one granule (TMA destination) */
+  uint8_t scf[SW_NBUF][128];              /* [buffer][ch][64]: its scalefactors (TMA destination) */
   f2 xr[36][SW_PITCH];              /* two blocks of 18 DCT rows; the block of the granule about to be transformed doubles as scratch */
   float scale[40][2];               /* band scales fl(t1*t2) of the current granule, [band][ch] */
   struct { uint4 fr; uint4 gc[4]; int32_t c1[4]; } desc[2];   /* [frame parity] second half of p3_frame, the 4 p3_gc, their count1 (TMA destination) */
@@ -84,7 +92,7 @@ __device__ __forceinline__ uint32_t sw_pcm2(f2 sum)
   return __vmaxs2(v, 0x80018001u);
 }
 
-extern "C" __global__ void __launch_bounds__(SW_WPB * 32, 3)
+extern "C" __global__ void __launch_bounds__(SW_WPB * 32, SW_MINB)
 k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
              int64_t f_first, int64_t f_end, int frames_per_warp,
              const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf,
@@ -94,11 +102,13 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   extern __shared__ __align__(16) uint8_t sw_dsm[];
   uint16_t *s_reo = reinterpret_cast<uint16_t *>(sw_dsm);
   uint8_t *s_sfbw = sw_dsm + 1152;
+  float *s_t1h = reinterpret_cast<float *>(sw_dsm + 1728), *s_t2 = s_t1h + 40;   /* per-lane indexed: shared memory, not the constant bank */
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   sw_warp_sm *W = reinterpret_cast<sw_warp_sm *>(sw_dsm + SW_LUT_BYTES) + warp;
 
   const uint32_t sf = frames[f_first].sfreq;               /* a batch never mixes sample rates */
   for (uint32_t i = threadIdx.x; i < 576; i += blockDim.x) { s_reo[i] = T->reorder_src[sf][i]; s_sfbw[i] = T->line_sfbw_s[sf][i]; }
+  for (uint32_t i = threadIdx.x; i < 360; i += blockDim.x) s_t1h[i] = i < 40 ? T->t1h[i] : T->t2[i - 40];
   __syncthreads();                                         /* the only CTA-wide barrier */
 
   const int64_t gw = (int64_t)blockIdx.x * SW_WPB + warp;
@@ -147,14 +157,14 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
     }
   };
   issue_desc(rel0, 0); if (nfr > 1) issue_desc(rel0 + 1, 1);
-  issue(rel0, 0, 0); issue(rel0, 1, 1);
+  issue(rel0, 0, 0); if (SW_NBUF == 2) issue(rel0, 1, 1);
 
   double inv_sqrt2; asm volatile("mov.f64 %0, 0d3FE6A09E667F3BCD;" : "=d"(inv_sqrt2));     /* 0.70710678118654752440, kept in registers */
   #pragma unroll 1
   for (int32_t q = 0; q < 2 * nfr; q++) {                  /* q: granules done by this warp */
     {
       const int32_t gr = q & 1, fi = q >> 1, rel = rel0 + fi; /* frame index within the warp's run / relative to the launch */
-      const uint32_t b = q & 1;
+      const uint32_t b = SW_NBUF == 2 ? (q & 1) : 0;
       f2 *blk = &W->xr[18 * gr][0], *prv = &W->xr[18 * (gr ^ 1)][0];
       if (gr == 0) sw_mbar_wait(&W->dbar[fi & 1], (fi >> 1) & 1);
       const uint4 frq = W->desc[fi & 1].fr, ga = W->desc[fi & 1].gc[2 * gr], gb = W->desc[fi & 1].gc[2 * gr + 1];
@@ -169,7 +179,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       if (rel == rel_last && lane == 0) { st_out->count1[gr][0] = ce0; st_out->count1[gr][1] = ce1; }
       const sw_par p0 = sw_unpack(ga, ce0), p1 = sw_unpack(gb, ce1);
 
-      sw_mbar_wait(&W->mbar[b], (q >> 1) & 1);
+      sw_mbar_wait(&W->mbar[b], SW_NBUF == 2 ? (q >> 1) & 1 : q & 1);
       const uint8_t (*scf2)[P3_SCF_STRIDE] = reinterpret_cast<const uint8_t (*)[P3_SCF_STRIDE]>(W->scf[b]);
 
       /* ---- band scales fl(t1*t2) (pdmp3.c:2127-2128, 2144-2146); same table layout as k_synth_fast: long blocks
@@ -190,7 +200,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
           /* pretab (pdmp3.c:2123): sfb 11..20 = 1,1,1,1,2,2,3,3,3,2, two bits each */
           if (longband) sc += pre * ((bnd >= 11 && bnd < 21) ? (0xbfa55u >> (2 * (bnd - 11))) & 3u : 0u);
           const int32_t qq = gg - (longband ? 0 : (int32_t)((sbg >> (8 * win)) & 0xffu));
-          const float v = __fmul_rn(FC.t1h[mult * sc], FC.t2[qq + P3_T2_BIAS]);
+          const float v = __fmul_rn(s_t1h[mult * sc], s_t2[qq + P3_T2_BIAS]);
           W->scale[bnd][c] = active ? v : 0.0f;
         }
       }
@@ -288,7 +298,8 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
 
       /* every lane is done with this buffer: bring in the granule after the next one */
       __syncwarp();
-      if (q + 2 < 2 * nfr) issue(rel + 1, gr, b);
+      if (SW_NBUF == 2) { if (q + 2 < 2 * nfr) issue(rel + 1, gr, b); }
+      else if (q + 1 < 2 * nfr) issue(rel + gr, gr ^ 1, 0);
 
       /* ---- C: antialias (pdmp3.c:1706-1732): the butterflies across a subband boundary take the neighbour lane's
        *      lines through shuffles; both shuffles of a pair happen before either line is rewritten ---- */
