@@ -268,6 +268,23 @@ extern "C" int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes
   return stage_batch(c, sl, raw, raw_bytes, b, c->stream);
 }
 
+/* FAST mode synthesis (K2+K3+K4 fused, p3_fused.cu) of frames [f0,f1): stereo batches go to the warp-autonomous packed
+ * kernel, mono batches and tapped runs to the one-channel-per-thread kernel. */
+static void launch_synth(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, const int16_t *is16, const int32_t *c1, const uint8_t *scf,
+                         const p3_state *si, p3_state *so)
+{
+  const p3_frame *fr = (const p3_frame *)sl->frames.p; const p3_gc *gc = (const p3_gc *)sl->gcs.p;
+  const int64_t nf = f1 - f0;
+  if (c->nch == 2 && !c->taps && c->synth_kernel == 0) {
+    const int wpb = p3_synthw_warps_per_cta();
+    const int64_t warps = (nf + c->fpc - 1) / c->fpc;
+    k_synth_warp<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
+        is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207);
+  } else
+    k_synth_fast<<<(unsigned)((nf + c->fpc - 1) / c->fpc), 128, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc, is16, c1, scf, si, so,
+        (int16_t *)sl->pcm.p, c->taps ? (float *)c->xr.p : NULL, c->taps ? (float *)c->y.p : NULL);
+}
+
 /* Launch K1..K4 over frames [f0,f1) of the batch staged in `sl`.  ev != NULL: record stage events. */
 static int run_chunk(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, cudaEvent_t *ev)
 {
@@ -282,17 +299,7 @@ static int run_chunk(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, cudaEvent_t
       (int16_t *)c->is16.p, (int32_t *)c->count1.p, (uint8_t *)c->scf.p);
   if (ev) CK(cudaEventRecord(ev[1], c->stream));
   if (c->mode == P3_MODE_FAST) {
-    /* K2+K3+K4 fused (p3_fused.cu): stereo batches go to the warp-autonomous packed kernel, mono batches and tapped
-     * runs to the one-channel-per-thread kernel; both give the same bits */
-    if (c->nch == 2 && !c->taps && c->synth_kernel == 0) {
-      const int wpb = p3_synthw_warps_per_cta();
-      const int64_t warps = (nf + c->fpc - 1) / c->fpc;
-      k_synth_warp<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
-          (const int16_t *)c->is16.p, (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207);
-    } else
-    k_synth_fast<<<(unsigned)((nf + c->fpc - 1) / c->fpc), 128, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
-        (const int16_t *)c->is16.p, (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so, (int16_t *)sl->pcm.p,
-        c->taps ? (float *)c->xr.p : NULL, c->taps ? (float *)c->y.p : NULL);
+    launch_synth(c, sl, f0, f1, (const int16_t *)c->is16.p, (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so);
     if (ev) { CK(cudaEventRecord(ev[2], c->stream)); CK(cudaEventRecord(ev[3], c->stream)); CK(cudaEventRecord(ev[4], c->stream)); }
     CK(cudaGetLastError());
     c->cur ^= 1; c->launches += 2;
@@ -335,8 +342,7 @@ static int run_pingpong(p3_ctx *c, p3_slot *sl)
     CK(cudaStreamWaitEvent(c->stream, c->k1_done[b], 0));
     p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
     CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
-    k_synth_fast<<<(unsigned)((nf + c->fpc - 1) / c->fpc), 128, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc, is16, c1, scf,
-        si, so, (int16_t *)sl->pcm.p, NULL, NULL);
+    launch_synth(c, sl, f0, f1, is16, c1, scf, si, so);
     CK(cudaEventRecord(c->syn_done[b], c->stream));
     c->cur ^= 1; c->launches += 2;
   }
