@@ -82,6 +82,8 @@ typedef struct {
                                 sync position (reference: 1152, pdmp3.c:2445); 0 = every complete frame */
   int32_t  nthreads;         /* side-info parse threads (<=0: pick)                              */
   uint32_t warmup_frames;    /* first N frames flagged WARMUP (no PCM slot)                      */
+  uint32_t hop_only;         /* 1: only the sequential header hop runs on the host; the side info (Read_Audio_L3,
+                                pdmp3.c:1129-1200) is parsed ON THE DEVICE by k_sideinfo when the batch is staged */
 } p3_parse_opts;
 
 typedef struct {
@@ -92,6 +94,8 @@ typedef struct {
   int64_t  n_pcm_frames;     /* frames holding a PCM slot                                        */
   int32_t  external;         /* arrays belong to the caller (p3_parse_into) */
   int32_t  stop;             /* 0: ran out of data, 1: max_frames, 2: no sync within 1152 bytes (pdmp3.c:1337), 3: channel count / sample rate changes at `consumed` */
+  int32_t  hop_only;         /* gcs[] (and frames[].scfsi / the BAD flag) are NOT filled: the device parses the side info */
+  int32_t  pad_;
 } p3_parsed;
 
 int  p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *opts, p3_parse_state *state, p3_parsed *out);
@@ -146,6 +150,7 @@ int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_
 int p3_batch_run(p3_ctx *c);                          /* launches the kernel sequence on the ctx stream */
 int p3_batch_sync(p3_ctx *c);
 int p3_batch_download(p3_ctx *c, int16_t *pcm, const p3_taps *host_taps);
+int p3_batch_download_desc(p3_ctx *c, p3_frame *frames, p3_gc *gcs);   /* the descriptors as the kernels see them (tests of the device parser) */
 void *p3_batch_pcm_device(p3_ctx *c, uint64_t *bytes);
 void *p3_ctx_stream(p3_ctx *c);                       /* cudaStream_t of the context */
 int  p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_stage /*[8]*/);  /* CUDA-event timing of p3_batch_run */

@@ -30,12 +30,13 @@ class P3ParseState(C.Structure):
 
 
 class P3ParseOpts(C.Structure):
-    _fields_ = [("max_frames", C.c_int64), ("lookahead", C.c_uint32), ("nthreads", C.c_int32), ("warmup_frames", C.c_uint32)]
+    _fields_ = [("max_frames", C.c_int64), ("lookahead", C.c_uint32), ("nthreads", C.c_int32), ("warmup_frames", C.c_uint32), ("hop_only", C.c_uint32)]
 
 
 class P3Parsed(C.Structure):
     _fields_ = [("n_frames", C.c_int64), ("frames", C.POINTER(P3Frame)), ("gcs", C.POINTER(P3Gc)),
-                ("consumed", C.c_uint64), ("n_pcm_frames", C.c_int64), ("external", C.c_int32), ("stop", C.c_int32)]
+                ("consumed", C.c_uint64), ("n_pcm_frames", C.c_int64), ("external", C.c_int32), ("stop", C.c_int32),
+                ("hop_only", C.c_int32), ("pad_", C.c_int32)]
 
 
 class P3Taps(C.Structure):
@@ -72,6 +73,7 @@ def lib():
     L.p3_batch_run.argtypes = [C.c_void_p]
     L.p3_batch_sync.argtypes = [C.c_void_p]
     L.p3_batch_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(P3Taps)]
+    L.p3_batch_download_desc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.p3_batch_pcm_device.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.p3_batch_pcm_device.restype = C.c_void_p
     L.p3_ctx_stream.argtypes = [C.c_void_p]
@@ -102,11 +104,11 @@ def _check(rc, what):
 class Parsed:
     """Owns a p3_parsed (host descriptors of one batch)."""
 
-    def __init__(self, stream, lookahead=0, max_frames=0, warmup=0, nthreads=0, state=None):
+    def __init__(self, stream, lookahead=0, max_frames=0, warmup=0, nthreads=0, state=None, hop_only=False):
         self.stream = np.ascontiguousarray(stream, dtype=np.uint8)
         self.c = P3Parsed()
         self.state = state if state is not None else P3ParseState(0, 0, 0, -1, -1)
-        o = P3ParseOpts(max_frames, lookahead, nthreads, warmup)
+        o = P3ParseOpts(max_frames, lookahead, nthreads, warmup, 1 if hop_only else 0)
         _check(lib().p3_parse(self.stream.ctypes.data, len(self.stream), C.byref(o), C.byref(self.state), C.byref(self.c)), "p3_parse")
 
     n_frames = property(lambda s: s.c.n_frames)
@@ -209,6 +211,12 @@ class Context:
         pcm = np.zeros((p.n_pcm_frames, 1152, p.nch), np.int16)
         _check(lib().p3_batch_download(self.h, pcm.ctypes.data, None), "p3_batch_download")
         return pcm
+
+    def download_desc(self, n_frames):
+        """the frame / granule-channel descriptors as the kernels see them (after the device side-info parser)"""
+        fr = np.zeros(n_frames, FRAME_DT); gc = np.zeros((n_frames, 4, 4), np.uint32)
+        _check(lib().p3_batch_download_desc(self.h, fr.ctypes.data, gc.ctypes.data), "p3_batch_download_desc")
+        return fr, gc
 
     def time(self, iters=5):
         tot = C.c_float(); st = (C.c_float * 8)()

@@ -40,7 +40,7 @@ struct pdmp3_handle {
   size_t pend_pos, pend_end;                        /* undelivered PCM bytes of it: [pend_pos,pend_end) */
   int in_pinned;
   p3_frame *dfr[3]; p3_gc *dgc[3]; int dnext;       /* page-locked descriptor arrays, rotated over the in-flight batches */
-  p3_ctx *ctx; int device; int ctx_failed; int mode;
+  p3_ctx *ctx; int device; int ctx_failed; int mode; int host_sideinfo;
   p3_parse_state ps;
   int new_header;                                   /* 0 none yet, 1 seen, -1 reported (pdmp3.c:1318,2470,2531) */
   int nch, sfreq;
@@ -59,6 +59,7 @@ pdmp3_handle *pdmp3_new(const char *decoder, int *error)
     if ((p = strstr(decoder, "ring="))) { unsigned long long v = strtoull(p + 5, NULL, 10); if (v >= 4096) id->cap = (size_t)v; }
     if ((p = strstr(decoder, "device="))) id->device = atoi(p + 7);
     if (strstr(decoder, "mode=exact")) id->mode = P3_MODE_EXACT;   /* bit-identical PCM; default is FAST (<= 1 LSB) */
+    if (strstr(decoder, "sideinfo=host")) id->host_sideinfo = 1;   /* parse the side info on the host instead of on the device */
   }
   if (id->cap > (1u << 20)) { id->in = (unsigned char *)p3_host_alloc(id->cap); id->in_pinned = id->in != NULL; }   /* page-locked: full-speed H2D */
   if (!id->in) id->in = (unsigned char *)malloc(id->cap);
@@ -158,7 +159,7 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
     int direct = outsize >= fbytes;
     int64_t want = direct ? (int64_t)(outsize / fbytes) : 1;
     if (want > P3_API_CHUNK) want = P3_API_CHUNK;
-    p3_parse_opts po = {want, 2 * 576, want >= 8192 ? 4 : 1, 0};
+    p3_parse_opts po = {want, 2 * 576, want >= 8192 ? 4 : 1, 0, id->host_sideinfo ? 0u : 1u};   /* side info: parsed on the device */
     p3_parse_state ps = id->ps;
     p3_parsed pb;
     p3_frame *dfr = NULL; p3_gc *dgc = NULL;

@@ -48,6 +48,7 @@ static int ensure(dbuf *b, size_t n)
 struct p3_slot {
   dbuf raw, frames, gcs, pcm;
   uint8_t *d_tail; uint8_t *h_tail;       /* 512 main-data bytes in front of the batch (pinned host copy) */
+  int *d_any_empty; int hop_only;         /* device side-info parser: flag for the Q6 chain; pending for this slot */
   cudaEvent_t h2d_done, compute_done, d2h_done;
   p3_parsed keep; int have_keep;          /* host descriptors owned until the upload has completed */
   int busy;
@@ -68,7 +69,7 @@ struct p3_ctx {
   /* current (most recently uploaded) batch */
   int64_t n_frames, n_pcm_frames; uint32_t nch; uint64_t raw_bytes;
   uint32_t k1_smem_words; int64_t chunk_frames;
-  int launches; int taps; int fpc;
+  int launches; int launches_parse; int taps; int fpc;
   float *d_pow43s; int synth_kernel;      /* signed |is|^(4/3) table (k_synth_warp); 0 = pick, 1 = always k_synth_fast */
   uint8_t next_tail[512]; int have_next_tail;
 };
@@ -104,6 +105,7 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
     CK(cudaEventCreateWithFlags(&sl->h2d_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sl->compute_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&sl->d2h_done, cudaEventDisableTiming));
     CK(cudaMalloc(&sl->d_tail, 512)); CK(cudaMemset(sl->d_tail, 0, 512));
+    CK(cudaMalloc(&sl->d_any_empty, sizeof(int)));
     CK(cudaHostAlloc((void **)&sl->h_tail, 512, cudaHostAllocDefault)); memset(sl->h_tail, 0, 512);
   }
   for (int i = 0; i < 10; i++) CK(cudaEventCreate(&c->ev[i]));
@@ -148,7 +150,7 @@ extern "C" void p3_ctx_destroy(p3_ctx *c)
     slot_release(sl);
     dbuf *bs[] = {&sl->raw, &sl->frames, &sl->gcs, &sl->pcm};
     for (dbuf *b : bs) if (b->p) cudaFree(b->p);
-    cudaFree(sl->d_tail); cudaFreeHost(sl->h_tail);
+    cudaFree(sl->d_tail); cudaFree(sl->d_any_empty); cudaFreeHost(sl->h_tail);
     cudaEventDestroy(sl->h2d_done); cudaEventDestroy(sl->compute_done); cudaEventDestroy(sl->d2h_done);
   }
   dbuf *bs[] = {&c->is16, &c->count1, &c->scf, &c->xr, &c->y, &c->is16b, &c->count1b, &c->scfb, &c->scratch};
@@ -253,7 +255,8 @@ static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_
   memcpy(sl->h_tail, c->h_tail, 512);
   CK(cudaMemcpyAsync(sl->raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(sl->frames.p, b->frames, (size_t)nf * sizeof(p3_frame), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(sl->gcs.p, b->gcs, (size_t)nf * 4 * sizeof(p3_gc), cudaMemcpyHostToDevice, st));
+  sl->hop_only = b->hop_only;
+  if (!b->hop_only) CK(cudaMemcpyAsync(sl->gcs.p, b->gcs, (size_t)nf * 4 * sizeof(p3_gc), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(sl->d_tail, sl->h_tail, 512, cudaMemcpyHostToDevice, st));
   compute_tail(raw, b, c->h_tail, c->next_tail); c->have_next_tail = 1;
   return P3_OK;
@@ -369,9 +372,23 @@ static int run_persist(p3_ctx *c, p3_slot *sl)
   return P3_OK;
 }
 
+/* Read_Audio_L3 on the device (k_sideinfo + the Q6 chain): once per staged batch, in front of the first decode */
+static int run_sideinfo(p3_ctx *c, p3_slot *sl)
+{
+  if (!sl->hop_only || c->n_frames == 0) return P3_OK;
+  CK(cudaMemsetAsync(sl->d_any_empty, 0, sizeof(int), c->stream));
+  k_sideinfo<<<(unsigned)((c->n_frames + 127) / 128), 128, 0, c->stream>>>((const uint8_t *)sl->raw.p, (p3_frame *)sl->frames.p, (p3_gc *)sl->gcs.p, c->n_frames, sl->d_any_empty);
+  k_q6_chain<<<1, 1024, 0, c->stream>>>((const p3_frame *)sl->frames.p, (p3_gc *)sl->gcs.p, c->n_frames, sl->d_any_empty);
+  CK(cudaGetLastError());
+  sl->hop_only = 0;                                        /* the descriptors are complete now; later runs of the same batch reuse them */
+  c->launches_parse = 2;
+  return P3_OK;
+}
+
 static int run_all(p3_ctx *c, p3_slot *sl)
 {
   c->launches = 0;
+  { int rc = run_sideinfo(c, sl); if (rc) return rc; }
   if (c->mode == P3_MODE_FAST && c->persist && !c->taps) return run_persist(c, sl);
   if (c->mode == P3_MODE_FAST && c->pingpong && !c->taps && c->n_frames > c->chunk_frames) return run_pingpong(c, sl);
   for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames) {
@@ -422,6 +439,17 @@ extern "C" int p3_batch_download(p3_ctx *c, int16_t *pcm, const p3_taps *t)
     if (t->y)       CK(cudaMemcpyAsync(t->y, c->y.p, ngc * 576 * 4, cudaMemcpyDeviceToHost, c->stream));
   }
   CK(cudaStreamSynchronize(c->stream));
+  return P3_OK;
+}
+
+extern "C" int p3_batch_download_desc(p3_ctx *c, p3_frame *frames, p3_gc *gcs)
+{
+  if (!c) return fail(P3_EINVAL, "null ctx");
+  CK(cudaSetDevice(c->device));
+  p3_slot *sl = &c->slot[c->cur_slot];
+  CK(cudaStreamSynchronize(c->stream));
+  if (frames && c->n_frames) CK(cudaMemcpy(frames, sl->frames.p, (size_t)c->n_frames * sizeof(p3_frame), cudaMemcpyDeviceToHost));
+  if (gcs && c->n_frames) CK(cudaMemcpy(gcs, sl->gcs.p, (size_t)c->n_frames * 4 * sizeof(p3_gc), cudaMemcpyDeviceToHost));
   return P3_OK;
 }
 
@@ -479,6 +507,7 @@ extern "C" int p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_st
 {
   if (!c || iters <= 0) return fail(P3_EINVAL, "bad argument");
   CK(cudaSetDevice(c->device));
+  { int rc = run_sideinfo(c, &c->slot[c->cur_slot]); if (rc) return rc; }
   p3_state *save; CK(cudaMalloc(&save, sizeof(p3_state)));
   CK(cudaMemcpyAsync(save, c->d_state[c->cur], sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
   float tot = 0, st[4] = {0, 0, 0, 0};

@@ -375,3 +375,107 @@ k_polyphase(const p3_frame *__restrict__ frames, const p3_tables *__restrict__ T
       }
   }
 }
+
+/* =============================================================================================
+ * k_sideinfo -- Read_Audio_L3 (pdmp3.c:1129-1200) on the device: one thread per frame turns the 17/32 bytes of
+ * side info in front of the frame's main data into the four p3_gc descriptors, scfsi and the validity flag
+ * (SURVEY Q10), exactly what parse_side() of p3_parse.c produces on the host.  Every field sits at a fixed bit
+ * position (a granule-channel is 59 bits whether or not window switching is on), so after the bytes are
+ * realigned to big-endian words the extraction is compile-time shifts.  any_empty: set when a part has length 0
+ * (the Q6 chain of k_q6_chain is needed).
+ * ============================================================================================= */
+__device__ __forceinline__ uint32_t si_get(const uint32_t (&w)[9], int pos, int n)   /* n <= 16, MSB first */
+{
+  const int i = pos >> 5, o = pos & 31;
+  const uint32_t v = o ? __funnelshift_l(w[i + 1], w[i], o) : w[i];
+  return v >> (32 - n);
+}
+
+template <int NCH>
+__device__ __forceinline__ void si_parse(const uint32_t (&w)[9], p3_frame &fr, p3_gc (&gc)[4], int &any_empty)
+{
+  constexpr int P0 = 9 + (NCH == 1 ? 5 : 3);
+  fr.scfsi = (uint8_t)__brev(si_get(w, P0, 4 * NCH) << (32 - 4 * NCH));   /* first bit read = band 0 of ch 0 = bit 0 */
+  uint32_t start = 0, bad = 0;
+  #pragma unroll
+  for (int k = 0; k < 4; k++) { gc[k].w0 = gc[k].w1 = gc[k].w2 = gc[k].w3 = 0; }
+  #pragma unroll
+  for (int gr = 0; gr < 2; gr++)
+    #pragma unroll
+    for (int ch = 0; ch < NCH; ch++) {
+      const int B = P0 + 4 * NCH + 59 * (gr * NCH + ch);
+      const uint32_t p23l = si_get(w, B, 12), bigv = si_get(w, B + 12, 9), gain = si_get(w, B + 21, 8), sfc = si_get(w, B + 29, 4);
+      const uint32_t ws = si_get(w, B + 33, 1);
+      uint32_t bt = 0, mixed = 0, t0, t1, t2 = 0, s0 = 0, s1 = 0, s2 = 0, r0, r1;
+      if (ws) {
+        bt = si_get(w, B + 34, 2); mixed = si_get(w, B + 36, 1);
+        t0 = si_get(w, B + 37, 5); t1 = si_get(w, B + 42, 5);
+        s0 = si_get(w, B + 47, 3); s1 = si_get(w, B + 50, 3); s2 = si_get(w, B + 53, 3);
+        r0 = (bt == 2 && !mixed) ? 8 : 7; r1 = 20 - r0;                       /* implicit (pdmp3.c:1181-1185) */
+        if (bt == 0) bad = 1;
+      } else {
+        t0 = si_get(w, B + 34, 5); t1 = si_get(w, B + 39, 5); t2 = si_get(w, B + 44, 5);
+        r0 = si_get(w, B + 49, 4); r1 = si_get(w, B + 53, 3);
+        if (r0 + r1 + 2 > 22) bad = 1;
+      }
+      const uint32_t pre = si_get(w, B + 56, 1), scale = si_get(w, B + 57, 1), c1t = si_get(w, B + 58, 1);
+      if (bigv > 288) bad = 1;
+      p3_gc &g = gc[gr * 2 + ch];
+      g.w0 = p23l | bigv << 12 | gain << 21 | pre << 29 | scale << 30 | c1t << 31;
+      g.w1 = sfc | ws << 4 | bt << 5 | mixed << 7 | t0 << 8 | t1 << 13 | t2 << 18 | r0 << 23 | r1 << 27;
+      g.w2 = s0 | s1 << 3 | s2 << 6 | start << 9;
+      start += p23l;
+      if (p23l == 0) any_empty = 1;
+    }
+  if (start > 8u * ((uint32_t)fr.main_begin + fr.main_size)) bad = 1;          /* parts overrun the frame's data */
+  if (bad) fr.flags |= P3_FRAME_BAD;
+}
+
+extern "C" __global__ void __launch_bounds__(128)
+k_sideinfo(const uint8_t *__restrict__ raw, p3_frame *__restrict__ frames, p3_gc *__restrict__ gcs, int64_t n_frames, int *__restrict__ any_empty)
+{
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  p3_frame fr = frames[f];
+  const uint32_t silen = fr.nch == 1 ? 17u : 32u;
+  const uint8_t *si = raw + fr.main_off - silen;
+  const uint32_t *al = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(si) & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(si) & 3) * 8;
+  uint32_t l[10], w[9];
+  #pragma unroll
+  for (int k = 0; k < 10; k++) l[k] = __ldg(al + k);                            /* the staged stream carries 64 bytes of slack */
+  #pragma unroll
+  for (int k = 0; k < 9; k++) w[k] = __byte_perm(__funnelshift_r(l[k], l[k + 1], sh), 0, 0x0123);   /* stream order, first byte in the MSB */
+  p3_gc gc[4]; int empty = 0;
+  if (fr.nch == 1) si_parse<1>(w, fr, gc, empty); else si_parse<2>(w, fr, gc, empty);
+  uint4 *out = reinterpret_cast<uint4 *>(gcs + 4 * f);
+  #pragma unroll
+  for (int k = 0; k < 4; k++) out[k] = make_uint4(gc[k].w0, gc[k].w1, gc[k].w2, 0u);
+  frames[f].scfsi = fr.scfsi; frames[f].flags = fr.flags;
+  if (empty) *any_empty = 1;
+}
+
+/* Q6 (pdmp3.c:2057-2061): a zero-length part leaves count1 of its [gr][ch] slot stale; w3 of such a part = how many
+ * frames back the slot was last written (0x7fffffff: not in this batch -> the carried state).  Runs only when
+ * k_sideinfo saw an empty part: one CTA, every thread scans a contiguous chunk of frames twice. */
+extern "C" __global__ void __launch_bounds__(1024)
+k_q6_chain(const p3_frame *__restrict__ frames, p3_gc *__restrict__ gcs, int64_t n_frames, const int *__restrict__ any_empty)
+{
+  if (!*any_empty) return;
+  __shared__ int64_t s_last[1024][4];
+  const int t = threadIdx.x;
+  const int64_t per = (n_frames + 1023) / 1024, lo = (int64_t)t * per, hi = min(lo + per, n_frames);
+  auto written = [&](int64_t f, int k) { return P3_GC_P23L(gcs[4 * f + k]) != 0 || (frames[f].flags & (P3_FRAME_NODATA | P3_FRAME_BAD)); };
+  int64_t last[4] = {-1, -1, -1, -1};
+  for (int64_t f = lo; f < hi; f++) for (int k = 0; k < 4; k++) if ((k & 1) < frames[f].nch && written(f, k)) last[k] = f;
+  for (int k = 0; k < 4; k++) s_last[t][k] = last[k];
+  __syncthreads();
+  if (t < 4) { int64_t run = -1; for (int i = 0; i < 1024; i++) { const int64_t v = s_last[i][t]; s_last[i][t] = run; if (v >= 0) run = v; } }   /* exclusive scan */
+  __syncthreads();
+  for (int k = 0; k < 4; k++) last[k] = s_last[t][k];
+  for (int64_t f = lo; f < hi; f++) for (int k = 0; k < 4; k++) {
+    if ((k & 1) >= frames[f].nch) continue;
+    if (written(f, k)) { last[k] = f; gcs[4 * f + k].w3 = 0; }
+    else gcs[4 * f + k].w3 = last[k] >= 0 ? (uint32_t)(f - last[k]) : 0x7fffffffu;
+  }
+}

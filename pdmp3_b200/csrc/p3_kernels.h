@@ -19,6 +19,8 @@ extern "C" {
 __global__ void k_huffman(const uint8_t *raw, const p3_frame *frames, const p3_gc *gcs, const p3_tables *T,
                           const uint8_t *tail, int64_t f_first, int64_t f_end, uint32_t smem_words,
                           int16_t *is_out, int32_t *count1_out, uint8_t *scf_out);
+__global__ void k_sideinfo(const uint8_t *raw, p3_frame *frames, p3_gc *gcs, int64_t n_frames, int *any_empty);
+__global__ void k_q6_chain(const p3_frame *frames, p3_gc *gcs, int64_t n_frames, const int *any_empty);
 __global__ void k_requant(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end,
                           const int16_t *is_in, const int32_t *count1, const uint8_t *scf,
                           const p3_state *st_in, p3_state *st_out, float *xr_out);

@@ -111,7 +111,7 @@ int p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_parse_s
 int p3_parse_into(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_parse_state *st, p3_parsed *out,
                   p3_frame *frames_buf, p3_gc *gcs_buf, int64_t buf_cap)
 {
-  p3_parse_opts od = {0, 0, 0, 0};
+  p3_parse_opts od = {0, 0, 0, 0, 0};
   p3_parse_state sd = {0, 0, 0, -1, -1};
   if (!data || !out) return P3_EINVAL;
   if (!o) o = &od;
@@ -167,6 +167,11 @@ int p3_parse_into(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_pa
   out->gcs = ext ? gcs_buf : (p3_gc *)malloc((size_t)(nf > 0 ? nf : 1) * 4 * sizeof(p3_gc));
   if (!out->gcs) { free(fr); return P3_ENOMEM; }
 
+  if (o->hop_only) {                                      /* the side info is parsed on the device (k_sideinfo) */
+    out->hop_only = 1;
+    memset(out->gcs, 0, (size_t)(nf > 0 ? nf : 1) * 4 * sizeof(p3_gc));
+    return P3_OK;
+  }
   /* ---- phase 2: side info, in parallel ---- */
   int nt = o->nthreads;
   if (nt <= 0) { long c = sysconf(_SC_NPROCESSORS_ONLN); nt = c > 16 ? 16 : (int)c; }

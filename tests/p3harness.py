@@ -92,10 +92,11 @@ class P3Gc(C.Structure):
 class P3ParseState(C.Structure):
     _fields_ = [("main_pos", C.c_uint64), ("top", C.c_uint32), ("pcm_index", C.c_uint32), ("nch", C.c_int32), ("sfreq", C.c_int32)]
 class P3ParseOpts(C.Structure):
-    _fields_ = [("max_frames", C.c_int64), ("lookahead", C.c_uint32), ("nthreads", C.c_int32), ("warmup_frames", C.c_uint32)]
+    _fields_ = [("max_frames", C.c_int64), ("lookahead", C.c_uint32), ("nthreads", C.c_int32), ("warmup_frames", C.c_uint32), ("hop_only", C.c_uint32)]
 class P3Parsed(C.Structure):
     _fields_ = [("n_frames", C.c_int64), ("frames", C.POINTER(P3Frame)), ("gcs", C.POINTER(P3Gc)),
-                ("consumed", C.c_uint64), ("n_pcm_frames", C.c_int64), ("external", C.c_int32), ("stop", C.c_int32)]
+                ("consumed", C.c_uint64), ("n_pcm_frames", C.c_int64), ("external", C.c_int32), ("stop", C.c_int32),
+                ("hop_only", C.c_int32), ("pad_", C.c_int32)]
 FRAME_DT = np.dtype([("main_off", "<u8"), ("main_pos", "<u8"), ("main_size", "<u2"), ("main_begin", "<u2"),
                      ("nch", "u1"), ("mode", "u1"), ("mode_ext", "u1"), ("sfreq", "u1"), ("scfsi", "u1"),
                      ("flags", "u1"), ("bitrate_kbps", "<u2"), ("pcm_index", "<u4")])

@@ -1,3 +1,3 @@
-for ch in 16384 32768 65536 131072 262144; do echo "== two streams, chunk $ch"; P3_PINGPONG=1 P3_CHUNK=$ch timeout 300 python bench.py --no-cpu --no-e2e 2>&1 | grep -o '"ms_per_step": [0-9.]*'; done
-echo "== default"; timeout 300 python bench.py --no-cpu --no-e2e 2>&1 | grep -o '"ms_per_step": [0-9.]*'
-P3_PINGPONG=1 P3_CHUNK=65536 timeout 600 python -m pytest tests/test_gpu_fast.py -x -q -k "million or partition" 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_sideinfo.py -x -q 2>&1 | tail -15
+timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_sideinfo.py 2>&1 | tail -3
+P3_TRACE=1 timeout 300 python tools/dbg/e2e_parts.py 2>&1 | tail -6
