@@ -130,3 +130,19 @@ def test_bad_side_info_flagged():
     assert fr2["flags"][2] & 4
     o = H.oracle_decode(t, lookahead=0)
     assert o["n_frames"] == 6                                      # decodes (as silence for that frame) without crashing
+
+
+def test_hop_only_parse_gives_the_same_frames():
+    """p3_parse_opts.hop_only (side info left to the device parser): same frame descriptors except scfsi and the
+    validity flag, which the device fills in; the granule descriptors stay zero on the host."""
+    import pdmp3_b200
+    s, _ = H.synth(300, seed=12, **H.CONFIGS["cfg4_vbr_mixed"])
+    a = pdmp3_b200.parse_stream(s, lookahead=1152)
+    b = pdmp3_b200.parse_stream(s, lookahead=1152, hop_only=True)
+    assert a.n_frames == b.n_frames and a.consumed == b.consumed and a.n_pcm_frames == b.n_pcm_frames
+    fa, fb = a.frames(), b.frames()
+    for name in fa.dtype.names:
+        if name in ("scfsi", "flags"): continue
+        assert np.array_equal(fa[name], fb[name]), name
+    assert np.array_equal(fa["flags"] & 0xfb, fb["flags"])          # P3_FRAME_BAD (4) comes from the side info
+    assert b.c.hop_only == 1 and not b.gcs().any()
