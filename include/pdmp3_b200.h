@@ -140,6 +140,12 @@ typedef struct {
 int p3_decode_batch(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *batch,
                     int16_t *pcm, const p3_taps *host_taps);
 
+/* BASELINE configs[1]: the two transform stages only.  `xr` = host spectra after requantize / reorder / stereo /
+ * antialias (what Decode_L3 hands to L3_Hybrid_Synthesis, pdmp3.c:1042), [n_frames][2][2][576] fp32; the device runs
+ * L3_Hybrid_Synthesis + L3_Frequency_Inversion (1752-1780, 1738-1746) and L3_Subband_Synthesis (1978-2045) with the
+ * reference's summation order (bit-exact PCM).  Only block types / flags of the descriptors are used. */
+int p3_synth_from_xr(p3_ctx *c, const float *xr, const p3_parsed *batch, int16_t *pcm);
+
 /* Asynchronous, double-buffered variant behind pdmp3_read(): enqueue upload, kernels and PCM download of
  * one batch and return; takes ownership of *batch.  raw/pcm must stay valid until p3_batch_sync(). */
 int p3_decode_batch_async(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, p3_parsed *batch, int16_t *pcm);

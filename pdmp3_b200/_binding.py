@@ -69,6 +69,7 @@ def lib():
     L.p3_ctx_set_frames_per_cta.argtypes = [C.c_void_p, C.c_int]
     L.p3_ctx_set_synth_kernel.argtypes = [C.c_void_p, C.c_int]
     L.p3_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3Parsed), C.c_void_p, C.POINTER(P3Taps)]
+    L.p3_synth_from_xr.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(P3Parsed), C.c_void_p]
     L.p3_batch_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3Parsed)]
     L.p3_batch_run.argtypes = [C.c_void_p]
     L.p3_batch_sync.argtypes = [C.c_void_p]
@@ -194,6 +195,14 @@ class Context:
 
     def decode(self, stream, lookahead=0, taps=False, **kw):
         return self.decode_parsed(Parsed(stream, lookahead=lookahead, **kw), taps=taps)
+
+    def synth_from_xr(self, xr, parsed):
+        """BASELINE configs[1]: IMDCT + polyphase only, spectra (after antialias) from the host. -> pcm"""
+        xr = np.ascontiguousarray(xr, dtype=np.float32)
+        assert xr.shape == (parsed.n_frames, 2, 2, 576)
+        pcm = np.zeros((parsed.n_pcm_frames, 1152, parsed.nch), np.int16)
+        _check(lib().p3_synth_from_xr(self.h, xr.ctypes.data, C.byref(parsed.c), pcm.ctypes.data), "p3_synth_from_xr")
+        return pcm
 
     # device-resident path (bench)
     def upload(self, parsed):

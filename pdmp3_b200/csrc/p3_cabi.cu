@@ -466,6 +466,45 @@ extern "C" int p3_decode_batch(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes
   return P3_OK;
 }
 
+/* K3 + K4 only, from host spectra (BASELINE configs[1]: Huffman and requantization still on the host) */
+extern "C" int p3_synth_from_xr(p3_ctx *c, const float *xr, const p3_parsed *b, int16_t *pcm)
+{
+  if (!c || !xr || !b || !pcm) return fail(P3_EINVAL, "null argument");
+  if (b->hop_only) return fail(P3_EINVAL, "p3_synth_from_xr needs host-parsed descriptors");
+  int rc;
+  if ((rc = p3_batch_sync(c))) return rc;
+  CK(cudaSetDevice(c->device));
+  const int64_t nf = b->n_frames;
+  if (nf == 0) return P3_OK;
+  p3_slot *sl = &c->slot[c->cur_slot];
+  c->n_frames = nf; c->n_pcm_frames = b->n_pcm_frames; c->nch = b->frames[0].nch;
+  if ((rc = ensure(&sl->frames, (size_t)nf * sizeof(p3_frame)))) return rc;
+  if ((rc = ensure(&sl->gcs, (size_t)nf * 4 * sizeof(p3_gc)))) return rc;
+  if ((rc = ensure(&sl->pcm, (size_t)(b->n_pcm_frames ? b->n_pcm_frames : 1) * 1152 * c->nch * sizeof(int16_t)))) return rc;
+  const int64_t cf = nf < (1 << 17) ? nf : (1 << 17);               /* frames per launch pair: 2 x 1.2 GB of fp32 intermediates */
+  if ((rc = ensure(&c->xr, (size_t)cf * 4 * 576 * 4))) return rc;
+  if ((rc = ensure(&c->y, (size_t)cf * 4 * 576 * 4))) return rc;
+  CK(cudaMemcpyAsync(sl->frames.p, b->frames, (size_t)nf * sizeof(p3_frame), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(sl->gcs.p, b->gcs, (size_t)nf * 4 * sizeof(p3_gc), cudaMemcpyHostToDevice, c->stream));
+  const p3_frame *fr = (const p3_frame *)sl->frames.p; const p3_gc *gc = (const p3_gc *)sl->gcs.p;
+  c->launches = 0;
+  for (int64_t f0 = 0; f0 < nf; f0 += cf) {
+    const int64_t f1 = f0 + cf < nf ? f0 + cf : nf, n = f1 - f0;
+    p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
+    CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->xr.p, xr + (size_t)f0 * 4 * 576, (size_t)n * 4 * 576 * 4, cudaMemcpyHostToDevice, c->stream));
+    k_imdct<<<(unsigned)(4 * n), K3_THREADS, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, (const float *)c->xr.p, si, so, (float *)c->y.p);
+    size_t smem4 = (size_t)(2048 + 512 + 2 * (15 + K4_SLOTS) * 96) * 4;
+    k_polyphase<<<(unsigned)((2 * n + K4_GRAN - 1) / K4_GRAN), K4_THREADS, smem4, c->stream>>>(fr, c->d_tables, f0, f1, (const float *)c->y.p, si, so, (int16_t *)sl->pcm.p);
+    CK(cudaGetLastError());
+    c->cur ^= 1; c->launches += 2;
+  }
+  if (b->n_pcm_frames)
+    CK(cudaMemcpyAsync(pcm, sl->pcm.p, (size_t)b->n_pcm_frames * 1152 * c->nch * sizeof(int16_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return P3_OK;
+}
+
 /* Asynchronous batch: uploads on the H2D stream, kernels on the kernel stream, the PCM download on
  * the D2H stream, chained by events; returns as soon as everything is enqueued.  Alternating between
  * two slots overlaps the transfer of one batch with the kernels of the other.  Takes ownership of

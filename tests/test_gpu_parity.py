@@ -108,3 +108,36 @@ def test_full_size_properties():
     ctx.reset(); alone = ctx.decode(blk, lookahead=0)
     assert np.array_equal(alone[1:], tiles[1][1:]) and not np.array_equal(alone[0], tiles[1][0])
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg4", "mono", "k48"])
+def test_config2_imdct_and_polyphase_only(gpu_ctx, name):
+    """BASELINE configs[1]: Huffman .. antialias on the host (here: the oracle), IMDCT + polyphase on the device
+    (p3_synth_from_xr): PCM bit-identical to the oracle's, first frame (zero state) included."""
+    import pdmp3_b200
+    s, _ = H.synth(400, seed=23, **VARIANTS[name])
+    o = H.oracle_decode(s, lookahead=1152)
+    p = pdmp3_b200.parse_stream(s, lookahead=1152)
+    gpu_ctx.reset()
+    pcm = gpu_ctx.synth_from_xr(o["xr_ali"], p)
+    assert pcm.shape[0] == o["n_frames"]
+    assert np.array_equal(pcm, o["pcm"][:, :, :pcm.shape[2]])
+    assert gpu_ctx.launch_count() == 2
+
+
+def test_config2_full_size_65536_frames(gpu_ctx):
+    """configs[1] at its full size (65 536 frames of 128 kbps stereo = 262 144 granule-channels, 604 MB of fp32 spectra
+    in, 302 MB of PCM out): the transform-only entry point fed with the spectra of the full pipeline gives the full
+    pipeline's PCM, bit for bit, and the 4096-frame blocks the stream is tiled from decode identically."""
+    import pdmp3_b200
+    blk, _ = H.synth(4096, seed=2, **H.CONFIGS["cfg1_128k_stereo_long"])
+    s = np.tile(blk, 16)
+    p = pdmp3_b200.parse_stream(s, lookahead=0)
+    assert p.n_frames == 65536
+    gpu_ctx.reset(); pcm, t = gpu_ctx.decode_parsed(p, taps=True)
+    xr = t["xr"]; del t
+    gpu_ctx.reset(); pcm2 = gpu_ctx.synth_from_xr(xr, p)
+    assert np.array_equal(pcm, pcm2)
+    tiles = pcm2.reshape(16, 4096, 1152, 2)
+    for k in range(2, 16):
+        assert np.array_equal(tiles[k], tiles[1]), "tile %d" % k

@@ -1,1 +1,1 @@
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/s7_bench_2gpu.json 2> gpurun_out/s7_bench_2gpu.err; cat gpurun_out/s7_bench_2gpu.json; tail -3 gpurun_out/s7_bench_2gpu.err
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -k config2 2>&1 | tail -8
