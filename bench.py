@@ -233,7 +233,7 @@ def main():
     frame_bytes = len(stream) / parsed.n_frames
     alg_bytes = (frame_bytes + 4608.0) * n_frames
     synth = "k_synth_fast" if os.environ.get("P3_SYNTH") == "cta" else "k_synth_warp"       # stereo workload: the packed-FFMA2 warp kernel
-    names = ["k_huffman", synth, "-", "-"] if a.mode == "fast" else ["k_huffman", "k_requant", "k_imdct", "k_polyphase"]
+    names = ["k_compact", "k_huffman", synth, "-", "-"] if a.mode == "fast" else ["k_compact", "k_huffman", "k_requant", "k_imdct", "k_polyphase"]
     dom = int(np.argmax(ms_stage)) if sum(ms_stage) > 0 else 0
     dom_ms = ms_stage[dom] if sum(ms_stage) > 0 else ms
     traffic = None

@@ -159,7 +159,7 @@ int p3_batch_download(p3_ctx *c, int16_t *pcm, const p3_taps *host_taps);
 int p3_batch_download_desc(p3_ctx *c, p3_frame *frames, p3_gc *gcs);   /* the descriptors as the kernels see them (tests of the device parser) */
 void *p3_batch_pcm_device(p3_ctx *c, uint64_t *bytes);
 void *p3_ctx_stream(p3_ctx *c);                       /* cudaStream_t of the context */
-int  p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_stage /*[8]*/);  /* CUDA-event timing of p3_batch_run */
+int  p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_stage /*[8]: k_compact, K1, K2 or the fused synthesis, K3, K4*/);  /* CUDA-event timing of p3_batch_run */
 int  p3_kernel_launch_count(p3_ctx *c);               /* kernels launched by the last p3_batch_run */
 
 #ifdef __cplusplus

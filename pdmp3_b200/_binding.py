@@ -230,7 +230,7 @@ class Context:
     def time(self, iters=5):
         tot = C.c_float(); st = (C.c_float * 8)()
         _check(lib().p3_batch_time(self.h, iters, C.byref(tot), st), "p3_batch_time")
-        return tot.value, [st[i] for i in range(4)]
+        return tot.value, [st[i] for i in range(5)]
 
     def launch_count(self):
         return lib().p3_kernel_launch_count(self.h)

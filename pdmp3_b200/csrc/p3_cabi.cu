@@ -10,10 +10,6 @@
 #include <math.h>
 
 extern "C" int p3_fused_upload_consts(const p3_tables *T, const float *dct4);
-extern "C" size_t p3_fused_smem_bytes(uint32_t k1_words, uint32_t hlut_used);
-extern "C" int p3_fused_group_frames(void);
-extern "C" __global__ void k_decode_fused(const uint8_t *raw, const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, const uint8_t *tail, int64_t f_first, int64_t f_end,
-    uint32_t k1_words, int16_t *scratch, const p3_state *st_in, p3_state *st_out, int16_t *pcm);
 extern "C" size_t p3_synthw_smem_bytes(void);
 extern "C" int p3_synthw_warps_per_cta(void);
 extern "C" __global__ void k_synth_warp(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_warp,
@@ -29,7 +25,6 @@ static int fail(int code, const char *fmt, ...) { va_list ap; va_start(ap, fmt);
 extern "C" const char *p3_last_error(void) { return g_err; }
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(P3_ECUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
-#define P3_PP_CHUNK 8192            /* frames per ping-pong step: 2 x 38 MB of spectra stay inside the 126 MB L2 */
 struct dbuf { void *p; size_t cap; };
 static int ensure(dbuf *b, size_t n)
 {
@@ -46,7 +41,8 @@ static int ensure(dbuf *b, size_t n)
 /* One in-flight batch: its inputs, its PCM and the events that order H2D -> kernels -> D2H.  Two slots
  * let the upload of batch k+1 and the download of batch k-1 overlap the kernels of batch k. */
 struct p3_slot {
-  dbuf raw, frames, gcs, pcm;
+  dbuf raw, frames, gcs, pcm, ms;         /* ms: compact main-data stream (k_compact -> k_huffman) */
+  uint64_t ms_bytes;
   uint8_t *d_tail; uint8_t *h_tail;       /* 512 main-data bytes in front of the batch (pinned host copy) */
   int *d_any_empty; int hop_only;         /* device side-info parser: flag for the Q6 chain; pending for this slot */
   cudaEvent_t h2d_done, compute_done, d2h_done;
@@ -63,12 +59,10 @@ struct p3_ctx {
   uint8_t h_tail[512];                    /* last 512 main-data bytes before the next batch */
   p3_slot slot[2]; int cur_slot;
   dbuf is16, count1, scf, xr, y;          /* intermediates, only touched by the kernel streams */
-  dbuf is16b, count1b, scfb;              /* FAST mode ping-pong partner (L2-resident hand-over K1 -> fused kernel) */
-  cudaStream_t s_k1; cudaEvent_t k1_done[2], syn_done[2], fork; int pingpong;
-  dbuf scratch; uint32_t kf_words; int persist; int n_sm;   /* k_decode_fused: private spectra rows of the resident CTAs */
+  int n_sm;
   /* current (most recently uploaded) batch */
   int64_t n_frames, n_pcm_frames; uint32_t nch; uint64_t raw_bytes;
-  uint32_t k1_smem_words; int64_t chunk_frames;
+  int64_t chunk_frames;
   int launches; int launches_parse; int taps; int fpc;
   float *d_pow43s; int synth_kernel;      /* signed |is|^(4/3) table (k_synth_warp); 0 = pick, 1 = always k_synth_fast */
   uint8_t next_tail[512]; int have_next_tail;
@@ -93,13 +87,7 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->s_k1, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) { CK(cudaEventCreateWithFlags(&c->k1_done[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->syn_done[i], cudaEventDisableTiming)); }
-  CK(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
-  c->persist = 0; { const char *e = getenv("P3_PERSIST"); if (e) c->persist = atoi(e); }   /* one persistent kernel: HBM traffic = algorithmic bytes, but 14 % slower than K1 + k_synth_fast (profiles/README.md) */
   c->n_sm = prop.multiProcessorCount;
-  CK(cudaFuncSetAttribute(k_decode_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  c->pingpong = 0; { const char *e = getenv("P3_PINGPONG"); if (e) c->pingpong = atoi(e); }   /* experiment, off: small launches underfill the GPU (profiles/README.md) */
   for (int i = 0; i < 2; i++) {
     p3_slot *sl = &c->slot[i];
     CK(cudaEventCreateWithFlags(&sl->h2d_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sl->compute_done, cudaEventDisableTiming));
@@ -148,15 +136,13 @@ extern "C" void p3_ctx_destroy(p3_ctx *c)
   for (int i = 0; i < 2; i++) {
     p3_slot *sl = &c->slot[i];
     slot_release(sl);
-    dbuf *bs[] = {&sl->raw, &sl->frames, &sl->gcs, &sl->pcm};
+    dbuf *bs[] = {&sl->raw, &sl->frames, &sl->gcs, &sl->pcm, &sl->ms};
     for (dbuf *b : bs) if (b->p) cudaFree(b->p);
     cudaFree(sl->d_tail); cudaFree(sl->d_any_empty); cudaFreeHost(sl->h_tail);
     cudaEventDestroy(sl->h2d_done); cudaEventDestroy(sl->compute_done); cudaEventDestroy(sl->d2h_done);
   }
-  dbuf *bs[] = {&c->is16, &c->count1, &c->scf, &c->xr, &c->y, &c->is16b, &c->count1b, &c->scfb, &c->scratch};
+  dbuf *bs[] = {&c->is16, &c->count1, &c->scf, &c->xr, &c->y};
   for (dbuf *b : bs) if (b->p) cudaFree(b->p);
-  cudaStreamDestroy(c->s_k1); cudaEventDestroy(c->fork);
-  for (int i = 0; i < 2; i++) { cudaEventDestroy(c->k1_done[i]); cudaEventDestroy(c->syn_done[i]); }
   cudaFree(c->d_tables); cudaFree(c->d_state[0]); cudaFree(c->d_state[1]); cudaFree(c->d_pow43s);
   for (int i = 0; i < 10; i++) cudaEventDestroy(c->ev[i]);
   cudaStreamDestroy(c->stream); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
@@ -178,7 +164,7 @@ extern "C" int p3_ctx_set_mode(p3_ctx *c, int mode)
   if (!c || (mode != P3_MODE_EXACT && mode != P3_MODE_FAST)) return fail(P3_EINVAL, "bad mode");
   c->mode = mode;
   /* frames per kernel-sequence launch: EXACT keeps fp32 intermediates of every stage in HBM (28 KB/frame), FAST only the int16 spectra */
-  c->chunk_frames = mode == P3_MODE_FAST ? (c->pingpong ? P3_PP_CHUNK : (1 << 21)) : (1 << 18);
+  c->chunk_frames = mode == P3_MODE_FAST ? (1 << 21) : (1 << 18);
   { const char *e = getenv("P3_CHUNK"); if (e && atoi(e) >= 64) c->chunk_frames = atoi(e); }
   return P3_OK;
 }
@@ -214,44 +200,20 @@ static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_
   if ((rc = ensure(&sl->frames, (size_t)nf * sizeof(p3_frame)))) return rc;
   if ((rc = ensure(&sl->gcs, (size_t)nf * 4 * sizeof(p3_gc)))) return rc;
   if ((rc = ensure(&sl->pcm, (size_t)(b->n_pcm_frames ? b->n_pcm_frames : 1) * 1152 * c->nch * sizeof(int16_t)))) return rc;
-  const int use_persist = c->mode == P3_MODE_FAST && c->persist && !c->taps;
   int64_t cf = nf < c->chunk_frames ? nf : c->chunk_frames;
-  if (use_persist) {
-    const int FGn = p3_fused_group_frames();
-    uint64_t mg = 0;
-    for (int64_t f0 = 0; f0 < nf; f0++) {                    /* any FG consecutive frames can form a group */
-      int64_t f1 = f0 + FGn < nf ? f0 + FGn : nf;
-      uint64_t span = b->frames[f1 - 1].main_pos + b->frames[f1 - 1].main_size - b->frames[f0].main_pos;
-      if (span > mg) mg = span;
-    }
-    c->kf_words = (uint32_t)((512 + mg + 16 + 3) / 4 + 3) & ~3u;
-    if (p3_fused_smem_bytes(c->kf_words, p3_tables_get()->hlut_used) > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
-    if ((rc = ensure(&c->scratch, (size_t)c->n_sm * 4 * FGn * 4 * 576 * 2))) return rc;
-    cf = 0;
-  }
   if (cf) {
   if ((rc = ensure(&c->is16, (size_t)cf * 4 * 576 * 2))) return rc;
   if ((rc = ensure(&c->count1, (size_t)cf * 4 * 4))) return rc;
   if ((rc = ensure(&c->scf, (size_t)cf * 4 * P3_SCF_STRIDE))) return rc;
-  if (c->mode == P3_MODE_FAST && c->pingpong && !c->taps) {
-    if ((rc = ensure(&c->is16b, (size_t)cf * 4 * 576 * 2))) return rc;
-    if ((rc = ensure(&c->count1b, (size_t)cf * 4 * 4))) return rc;
-    if ((rc = ensure(&c->scfb, (size_t)cf * 4 * P3_SCF_STRIDE))) return rc;
-  }
   if (c->mode == P3_MODE_EXACT || c->taps) {
     if ((rc = ensure(&c->xr, (size_t)cf * 4 * 576 * 4))) return rc;
     if ((rc = ensure(&c->y, (size_t)cf * 4 * 576 * 4))) return rc;
   }
   }
-  /* K1 shared-memory window: 512 reservoir bytes + the largest group of K1_FPB frames */
-  uint64_t maxg = 0;
-  for (int64_t f0 = 0; f0 < nf; f0 += K1_FPB) {
-    int64_t f1 = f0 + K1_FPB < nf ? f0 + K1_FPB : nf;
-    uint64_t span = b->frames[f1 - 1].main_pos + b->frames[f1 - 1].main_size - b->frames[f0].main_pos;
-    if (span > maxg) maxg = span;
-  }
-  c->k1_smem_words = (uint32_t)((512 + maxg + 16 + 3) / 4 + 3) & ~3u;   /* multiple of 16 bytes: the staging areas behind it hold uint4 */
-  if ((size_t)c->k1_smem_words * 4 + sizeof(((p3_tables *)0)->hlut) + 4 * K1_THREADS * 4 > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
+  /* compact main-data stream: 512 reservoir bytes + all main data of the batch, zero padded (the bit readers run a few words ahead) */
+  sl->ms_bytes = 512 + (b->frames[nf - 1].main_pos + b->frames[nf - 1].main_size - b->frames[0].main_pos);
+  if ((rc = ensure(&sl->ms, sl->ms_bytes + 256))) return rc;
+  CK(cudaMemsetAsync((uint8_t *)sl->ms.p + (sl->ms_bytes & ~(uint64_t)3), 0, 128, st));
   memcpy(sl->h_tail, c->h_tail, 512);
   CK(cudaMemcpyAsync(sl->raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(sl->frames.p, b->frames, (size_t)nf * sizeof(p3_frame), cudaMemcpyHostToDevice, st));
@@ -296,79 +258,31 @@ static int run_chunk(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, cudaEvent_t
   p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
   CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));   /* fields a launch does not rewrite carry over */
   if (ev) CK(cudaEventRecord(ev[0], c->stream));
-  size_t smem1 = (size_t)c->k1_smem_words * 4 + 4 * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
-  k_huffman<<<(unsigned)((nf + K1_FPB - 1) / K1_FPB), K1_THREADS, smem1, c->stream>>>(
-      (const uint8_t *)sl->raw.p, fr, gc, c->d_tables, sl->d_tail, f0, f1, c->k1_smem_words,
-      (int16_t *)c->is16.p, (int32_t *)c->count1.p, (uint8_t *)c->scf.p);
+  k_compact<<<(unsigned)((nf + 3) / 4), 128, 0, c->stream>>>((const uint8_t *)sl->raw.p, fr, sl->d_tail, f0, f1, (uint32_t *)sl->ms.p);
   if (ev) CK(cudaEventRecord(ev[1], c->stream));
+  size_t smem1 = 4 * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
+  k_huffman<<<(unsigned)((nf + K1_FPB - 1) / K1_FPB), K1_THREADS, smem1, c->stream>>>((const uint32_t *)sl->ms.p, fr, gc, c->d_tables, f0, f1,
+      (int16_t *)c->is16.p, (int32_t *)c->count1.p, (uint8_t *)c->scf.p);
+  if (ev) CK(cudaEventRecord(ev[2], c->stream));
   if (c->mode == P3_MODE_FAST) {
     launch_synth(c, sl, f0, f1, (const int16_t *)c->is16.p, (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so);
-    if (ev) { CK(cudaEventRecord(ev[2], c->stream)); CK(cudaEventRecord(ev[3], c->stream)); CK(cudaEventRecord(ev[4], c->stream)); }
+    if (ev) { CK(cudaEventRecord(ev[3], c->stream)); CK(cudaEventRecord(ev[4], c->stream)); CK(cudaEventRecord(ev[5], c->stream)); }
     CK(cudaGetLastError());
-    c->cur ^= 1; c->launches += 2;
+    c->cur ^= 1; c->launches += 3;
     return P3_OK;
   }
   k_requant<<<(unsigned)(2 * nf), K2_THREADS, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, (const int16_t *)c->is16.p,
       (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so, (float *)c->xr.p);
-  if (ev) CK(cudaEventRecord(ev[2], c->stream));
-  k_imdct<<<(unsigned)(4 * nf), K3_THREADS, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, (const float *)c->xr.p, si, so, (float *)c->y.p);
   if (ev) CK(cudaEventRecord(ev[3], c->stream));
+  k_imdct<<<(unsigned)(4 * nf), K3_THREADS, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, (const float *)c->xr.p, si, so, (float *)c->y.p);
+  if (ev) CK(cudaEventRecord(ev[4], c->stream));
   size_t smem4 = (size_t)(2048 + 512 + 2 * (15 + K4_SLOTS) * 96) * 4;
   k_polyphase<<<(unsigned)((2 * nf + K4_GRAN - 1) / K4_GRAN), K4_THREADS, smem4, c->stream>>>(fr, c->d_tables, f0, f1,
       (const float *)c->y.p, si, so, (int16_t *)sl->pcm.p);
-  if (ev) CK(cudaEventRecord(ev[4], c->stream));
+  if (ev) CK(cudaEventRecord(ev[5], c->stream));
   CK(cudaGetLastError());
   c->cur ^= 1;
-  c->launches += 4;
-  return P3_OK;
-}
-
-/* FAST mode, two streams: K1 of step k+1 runs beside the fused kernel of step k, and the spectra of a
- * step (38 MB) are consumed straight out of the 126 MB L2 and overwritten in place two steps later,
- * so most of them never travel to HBM. */
-static int run_pingpong(p3_ctx *c, p3_slot *sl)
-{
-  const p3_frame *fr = (const p3_frame *)sl->frames.p; const p3_gc *gc = (const p3_gc *)sl->gcs.p;
-  size_t smem1 = (size_t)c->k1_smem_words * 4 + 4 * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
-  CK(cudaEventRecord(c->fork, c->stream));                 /* everything queued on the kernel stream so far (uploads) comes first */
-  CK(cudaStreamWaitEvent(c->s_k1, c->fork, 0));
-  int step = 0;
-  for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames, step++) {
-    int64_t f1 = f0 + c->chunk_frames < c->n_frames ? f0 + c->chunk_frames : c->n_frames, nf = f1 - f0;
-    const int b = step & 1;
-    int16_t *is16 = (int16_t *)(b ? c->is16b.p : c->is16.p); int32_t *c1 = (int32_t *)(b ? c->count1b.p : c->count1.p);
-    uint8_t *scf = (uint8_t *)(b ? c->scfb.p : c->scf.p);
-    if (step >= 2) CK(cudaStreamWaitEvent(c->s_k1, c->syn_done[b], 0));     /* buffer b is free again */
-    k_huffman<<<(unsigned)((nf + K1_FPB - 1) / K1_FPB), K1_THREADS, smem1, c->s_k1>>>((const uint8_t *)sl->raw.p, fr, gc, c->d_tables,
-        sl->d_tail, f0, f1, c->k1_smem_words, is16, c1, scf);
-    CK(cudaEventRecord(c->k1_done[b], c->s_k1));
-    CK(cudaStreamWaitEvent(c->stream, c->k1_done[b], 0));
-    p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
-    CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
-    launch_synth(c, sl, f0, f1, is16, c1, scf, si, so);
-    CK(cudaEventRecord(c->syn_done[b], c->stream));
-    c->cur ^= 1; c->launches += 2;
-  }
-  CK(cudaGetLastError());
-  return P3_OK;
-}
-
-/* FAST mode default: the whole batch in one persistent launch (p3_fused.cu, k_decode_fused) */
-static int run_persist(p3_ctx *c, p3_slot *sl)
-{
-  const int64_t nf = c->n_frames;
-  if (nf == 0) return P3_OK;
-  p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
-  CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
-  int64_t grid = (int64_t)c->n_sm * 4;
-  const int FGn = p3_fused_group_frames();
-  if (grid > (nf + 2 * FGn - 1) / (2 * FGn)) grid = (nf + 2 * FGn - 1) / (2 * FGn);     /* at least two groups per run */
-  if (grid < 1) grid = 1;
-  size_t smem = p3_fused_smem_bytes(c->kf_words, p3_tables_get()->hlut_used);
-  k_decode_fused<<<(unsigned)grid, 128, smem, c->stream>>>((const uint8_t *)sl->raw.p, (const p3_frame *)sl->frames.p, (const p3_gc *)sl->gcs.p,
-      c->d_tables, sl->d_tail, 0, nf, c->kf_words, (int16_t *)c->scratch.p, si, so, (int16_t *)sl->pcm.p);
-  CK(cudaGetLastError());
-  c->cur ^= 1; c->launches += 1;
+  c->launches += 5;
   return P3_OK;
 }
 
@@ -389,8 +303,6 @@ static int run_all(p3_ctx *c, p3_slot *sl)
 {
   c->launches = 0;
   { int rc = run_sideinfo(c, sl); if (rc) return rc; }
-  if (c->mode == P3_MODE_FAST && c->persist && !c->taps) return run_persist(c, sl);
-  if (c->mode == P3_MODE_FAST && c->pingpong && !c->taps && c->n_frames > c->chunk_frames) return run_pingpong(c, sl);
   for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames) {
     int64_t f1 = f0 + c->chunk_frames < c->n_frames ? f0 + c->chunk_frames : c->n_frames;
     int rc = run_chunk(c, sl, f0, f1, NULL);
@@ -541,7 +453,7 @@ extern "C" int p3_decode_batch_async(p3_ctx *c, const uint8_t *raw, uint64_t raw
 }
 
 /* CUDA-event timing of the kernel sequence with everything resident in HBM.  The carried state is
- * restored before every iteration so that each one decodes the same thing.  ms_stage: K1..K4. */
+ * restored before every iteration so that each one decodes the same thing.  ms_stage: K0 (compact), K1..K4. */
 extern "C" int p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_stage)
 {
   if (!c || iters <= 0) return fail(P3_EINVAL, "bad argument");
@@ -549,22 +461,21 @@ extern "C" int p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_st
   { int rc = run_sideinfo(c, &c->slot[c->cur_slot]); if (rc) return rc; }
   p3_state *save; CK(cudaMalloc(&save, sizeof(p3_state)));
   CK(cudaMemcpyAsync(save, c->d_state[c->cur], sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
-  float tot = 0, st[4] = {0, 0, 0, 0};
+  float tot = 0, st[5] = {0, 0, 0, 0, 0};
   for (int it = 0; it < iters; it++) {
     CK(cudaMemcpyAsync(c->d_state[c->cur], save, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
     c->launches = 0;
     CK(cudaEventRecord(c->ev[8], c->stream));
-    if (c->mode == P3_MODE_FAST && c->persist && !c->taps) { int rc = run_all(c, &c->slot[c->cur_slot]); if (rc) { cudaFree(save); return rc; } }
-    else if (c->n_frames <= c->chunk_frames) { int rc = run_chunk(c, &c->slot[c->cur_slot], 0, c->n_frames, c->ev); if (rc) { cudaFree(save); return rc; } }
+    if (c->n_frames <= c->chunk_frames) { int rc = run_chunk(c, &c->slot[c->cur_slot], 0, c->n_frames, c->ev); if (rc) { cudaFree(save); return rc; } }
     else { int rc = run_all(c, &c->slot[c->cur_slot]); if (rc) { cudaFree(save); return rc; } }
     CK(cudaEventRecord(c->ev[9], c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms; CK(cudaEventElapsedTime(&ms, c->ev[8], c->ev[9])); tot += ms;
-    if (c->n_frames <= c->chunk_frames && !(c->mode == P3_MODE_FAST && c->persist && !c->taps))
-      for (int k = 0; k < 4; k++) { CK(cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1])); st[k] += ms; }
+    if (c->n_frames <= c->chunk_frames)
+      for (int k = 0; k < 5; k++) { CK(cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1])); st[k] += ms; }
   }
   cudaFree(save);
   if (ms_total) *ms_total = tot / iters;
-  if (ms_stage) for (int k = 0; k < 4; k++) ms_stage[k] = st[k] / iters;
+  if (ms_stage) for (int k = 0; k < 5; k++) ms_stage[k] = st[k] / iters;
   return P3_OK;
 }

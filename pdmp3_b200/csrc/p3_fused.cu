@@ -17,7 +17,6 @@
  */
 #include "p3_device.cuh"
 #include "p3_kernels.h"
-#include "p3_k1.cuh"
 #include "p3_xform.cuh"
 
 struct p3_fconst {
@@ -489,171 +488,5 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   __syncthreads();
   if (c1 == f_end) synth_store_state(S, n - 1, st_out);
 }
-
-/* =============================================================================================
- * k_decode_fused -- the whole path in ONE persistent kernel (FAST mode, default).
- *
- * Each CTA owns a contiguous run of frames and alternates two phases over groups of FG frames:
- *   H  (Huffman, K1): gather the group's main data into the shared-memory bit reservoir, one thread per
- *      granule-channel decodes scalefactors + spectra; the spectra go to a PRIVATE scratch row block in
- *      global memory that the same CTA re-reads a few microseconds later and overwrites for its next
- *      group -- with ~600 resident CTAs x 74 KB the scratch lives in the 126 MB L2 and practically never
- *      reaches HBM; scalefactors and count1 stay in shared memory.
- *   S  (synthesis, stages A..F of synth_frame): requantize .. PCM for the group's frames, filter state
- *      (IMDCT tail, DCT history) carried in shared memory from group to group.
- * HBM traffic is therefore the compressed stream + descriptors in and PCM out: the algorithmic bytes.
- * CTAs drift apart in phase, so the latency-bound Huffman phase of one CTA overlaps the FMA-bound
- * synthesis of the others on the same SM.
- * Run boundaries are placed (identically by both neighbours) at the first frame at or after the even
- * split point whose own and preceding frame have no zero-length part, so the stale-count1 chain (Q6)
- * never reaches across a boundary; each run but the first is primed by the frame in front of it.
- * ============================================================================================= */
-#define FG 16                      /* frames per group: 64 Huffman threads, 74 KB of scratch */
-
-__device__ __forceinline__ bool frame_clean(const p3_gc *__restrict__ gcs, int64_t f)
-{
-  return (gcs[4 * f].w3 | gcs[4 * f + 1].w3 | gcs[4 * f + 2].w3 | gcs[4 * f + 3].w3) == 0;
-}
-/* first frame of run k of B over frames [f_first, f_end) */
-__device__ __forceinline__ int64_t run_start(const p3_gc *__restrict__ gcs, int64_t f_first, int64_t f_end, int64_t k, int64_t B)
-{
-  if (k <= 0) return f_first;
-  if (k >= B) return f_end;
-  const int64_t nf = f_end - f_first;
-  int64_t f = f_first + nf * k / B;
-  const int64_t lim = f_first + nf * (k + 1) / B;
-  for (int64_t g = f; g < lim && g < f + 256; g++)
-    if (g > f_first && frame_clean(gcs, g - 1) && frame_clean(gcs, g)) return g;
-  return f;                                                /* no clean frame nearby: keep the even split */
-}
-
-extern "C" __global__ void __launch_bounds__(FT, 4)
-k_decode_fused(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
-               const p3_tables *__restrict__ T, const uint8_t *__restrict__ tail, int64_t f_first, int64_t f_end,
-               uint32_t k1_words, int16_t *__restrict__ scratch, const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out,
-               int16_t *__restrict__ pcm)
-{
-  extern __shared__ __align__(16) uint8_t dsm[];
-  /* ---- persistent part ---- */
-  float (*xring)[XSLOTS][XPITCH] = reinterpret_cast<float (*)[XSLOTS][XPITCH]>(dsm);
-  float (*tail2)[576] = reinterpret_cast<float (*)[576]>(dsm + sizeof(float) * 2 * XSLOTS * XPITCH);          /* tails[2]: carried IMDCT tail */
-  uint8_t *p = reinterpret_cast<uint8_t *>(tail2) + sizeof(float) * 2 * 576;
-  uint8_t (*scfg)[P3_SCF_STRIDE] = reinterpret_cast<uint8_t (*)[P3_SCF_STRIDE]>(p); p += FG * 4 * P3_SCF_STRIDE;   /* scalefactors of the group */
-  int32_t *c1g = reinterpret_cast<int32_t *>(p); p += FG * 4 * 4;                                                /* count1 of the group, made effective in place */
-  float (*s_scale)[4][40] = reinterpret_cast<float (*)[4][40]>(p); p += 2 * 4 * 40 * 4;
-  gcpar (*s_par)[4] = reinterpret_cast<gcpar (*)[4]>(p); p += 2 * 4 * sizeof(gcpar);
-  uint8_t (*s_scf2)[4][P3_SCF_STRIDE] = reinterpret_cast<uint8_t (*)[4][P3_SCF_STRIDE]>(p); p += 2 * 4 * P3_SCF_STRIDE;
-  uint16_t *s_reo = reinterpret_cast<uint16_t *>(p); p += 576 * 2;
-  uint8_t *s_sfb_l = p; p += 576; uint8_t *s_sfbw_s = p; p += 576;
-  int32_t *s_eff = reinterpret_cast<int32_t *>(p); p += 16;
-  p = dsm + ((p - dsm + 15) & ~(size_t)15);
-  int64_t *s_fb = reinterpret_cast<int64_t *>(p); p += 16;
-  /* ---- phase-local part: synthesis buffers and the Huffman buffers share the same bytes ---- */
-  uint8_t *u = p;
-  float (*xs)[576] = reinterpret_cast<float (*)[576]>(u);                       /* [4] */
-  float (*tails01)[2][576] = reinterpret_cast<float (*)[2][576]>(u + 4 * 576 * 4);   /* tails[0], tails[1] */
-  int16_t (*isbuf)[576] = reinterpret_cast<int16_t (*)[576]>(u + 8 * 576 * 4);  /* [4] */
-  uint32_t *sw = reinterpret_cast<uint32_t *>(u);                               /* bit reservoir */
-  uint32_t *ring = sw + k1_words;                                               /* [4][FG*4] output staging */
-  uint16_t *lut = reinterpret_cast<uint16_t *>(ring + 4 * FG * 4);
-
-  const int tid = threadIdx.x;
-  const int64_t B = gridDim.x;
-  const int64_t r0 = run_start(gcs, f_first, f_end, blockIdx.x, B), r1 = run_start(gcs, f_first, f_end, blockIdx.x + 1, B);
-  if (r0 >= r1) return;
-  const int warm = r0 > f_first ? 1 : 0;
-  const uint32_t nch = frames[r0].nch;
-  int16_t *my = scratch + (size_t)blockIdx.x * FG * 4 * 576;
-
-  synth_sm S = {xs, NULL, xring, isbuf, s_sfb_l, s_sfbw_s, s_reo, s_par, s_scale, s_scf2, tails01, tail2};
-  float ce[8], co[8]; int ia, ib;
-  synth_window_coeffs(T, ce, co, ia, ib);
-  sf_load_luts(S, T, frames[r0].sfreq);
-  synth_load_state(S, warm ? NULL : st_in);
-  if (tid < 4) s_eff[tid] = warm ? 0 : st_in->count1[tid >> 1][tid & 1];
-  __syncthreads();
-
-  int n = 0;
-  for (int64_t F0 = r0 - warm; F0 < r1; F0 += FG) {
-    const int64_t F1 = min(F0 + (int64_t)FG, r1);
-    const int ngc = (int)(F1 - F0) * 4;
-    /* ================= phase H ================= */
-    for (uint32_t i = tid; i < (T->hlut_used + 1) / 2; i += FT) reinterpret_cast<uint32_t *>(lut)[i] = reinterpret_cast<const uint32_t *>(T->hlut)[i];
-    for (uint32_t i = tid; i < k1_words; i += FT) sw[i] = 0;
-    for (uint32_t i = tid; i < FG * 4 * P3_SCF_STRIDE / 4; i += FT) reinterpret_cast<uint32_t *>(&scfg[0][0])[i] = 0;
-    k1_gather(raw, frames, tail, F0, F1, sw, s_fb);
-    if (tid < ngc) {
-      const int64_t f = F0 + (tid >> 2);
-      const uint32_t gr = (tid >> 1) & 1, ch = tid & 1;
-      const p3_frame fr = frames[f]; const p3_gc g = gcs[4 * f + 2 * gr + ch];
-      k1_out ob; ob.ring = ring + tid; ob.stride = FG * 4; ob.pw = 0; ob.dst = reinterpret_cast<uint4 *>(my + (size_t)tid * 576);
-      const int32_t c = (int32_t)k1_decode_gc(sw, lut, T, gcs, fr, g, f, gr, ch, frames[F0].main_pos, ob, scfg[tid]);
-      /* bit 30: this part overwrites the slot's count1 (non-empty, or a flagged frame decoded as silence) */
-      const bool own = ch < fr.nch && (P3_GC_P23L(g) != 0 || (fr.flags & (P3_FRAME_NODATA | P3_FRAME_BAD)));
-      c1g[tid] = ch < fr.nch ? (c | (own ? 0x40000000 : 0)) : 0x40000000;
-    }
-    __syncthreads();
-    if (tid < 4) {                                        /* stale count1 chain (Q6): an empty part keeps the slot's previous value */
-      int32_t e = s_eff[tid];
-      for (int k = 0; k < ngc / 4; k++) {
-        const int32_t v = c1g[4 * k + tid];
-        e = (v & 0x40000000) ? (v & 0x3fffffff) : e;
-        c1g[4 * k + tid] = e;
-      }
-      s_eff[tid] = e;
-    }
-    /* ================= phase S ================= */
-    uint32_t pre[9];
-    const uint32_t *isw = reinterpret_cast<const uint32_t *>(my);
-    #pragma unroll
-    for (int k = 0; k < 9; k++) pre[k] = __ldcg(isw + tid + FT * k);
-    __syncthreads();
-    for (int64_t f = F0; f < F1; f++, n++) {
-      const p3_frame fr = frames[f];
-      const int k = (int)(f - F0);
-      const bool emit = !(warm && n == 0) && (fr.flags & P3_FRAME_DECODE);
-      __syncthreads();                                    /* previous frame completely done */
-      {
-        p3_gc gcur = {0, 0, 0, 0}; int32_t cc = 0;
-        if (tid < 4) { cc = c1g[4 * k + tid]; gcur = gcs[4 * f + tid]; }
-        const uint32_t w = tid < 64 ? reinterpret_cast<const uint32_t *>(&scfg[4 * k][0])[tid] : 0u;
-        sf_hist(S);
-        sf_land(S, 0, pre, w, gcur, cc, nch);
-        if (f + 1 < F1) {
-          const uint32_t *nx = isw + (size_t)(k + 1) * 4 * 288;
-          #pragma unroll
-          for (int q = 0; q < 9; q++) pre[q] = __ldcg(nx + tid + FT * q);
-        }
-      }
-      __syncthreads();
-      sf_scale(S, 0);
-      __syncthreads();
-      sf_stageAB<0>(S, 0, fr, T, nch);
-      __syncthreads();
-      sf_stageD(S, 0, n, NULL);
-      __syncthreads();
-      sf_stageE(S, n, nch, NULL);
-      __syncthreads();
-      sf_stageF<true>(S, fr, nch, emit, pcm, ce, co, ia, ib);
-    }
-    __syncthreads();
-  }
-  if (r1 == f_end) {
-    synth_store_state(S, n - 1, st_out);
-    if (tid < 4) st_out->count1[tid >> 1][tid & 1] = s_eff[tid];
-  }
-}
-
-/* bytes of dynamic shared memory k_decode_fused needs for a K1 window of `k1_words` words */
-extern "C" size_t p3_fused_smem_bytes(uint32_t k1_words, uint32_t hlut_used)
-{
-  size_t pers = sizeof(float) * 2 * XSLOTS * XPITCH + sizeof(float) * 2 * 576 + FG * 4 * P3_SCF_STRIDE + FG * 4 * 4 + 2 * 4 * 40 * 4 + 2 * 4 * sizeof(gcpar)
-              + 2 * 4 * P3_SCF_STRIDE + 576 * 2 + 576 + 576 + 16;
-  pers = (pers + 15) & ~(size_t)15; pers += 16;
-  size_t syn = 8 * 576 * 4 + 4 * 576 * 2;
-  size_t huf = (size_t)k1_words * 4 + 4 * FG * 4 * 4 + (size_t)hlut_used * 2 + 16;
-  return pers + (syn > huf ? syn : huf);
-}
-extern "C" int p3_fused_group_frames(void) { return FG; }
 
 #include "p3_synthw.cuh"

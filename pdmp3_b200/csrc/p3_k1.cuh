@@ -1,26 +1,26 @@
-/* p3_k1.cuh -- device code of the Huffman stage (K1), shared by k_huffman (p3_kernels.cu) and the
- * persistent fused kernel (p3_fused.cu).  Reference: Read_Main_L3 1376-1435, Read_Huffman 2051-2115,
+/* p3_k1.cuh -- device code of the Huffman stage (K1, k_huffman in p3_kernels.cu).  Reference: Read_Main_L3 1376-1435, Read_Huffman 2051-2115,
  * Huffman_Decode 1593-1643, Get_Main_Data 1096-1122 of /root/reference/pdmp3.c. */
 #pragma once
 #include "p3_device.cuh"
 
-/* MSB-first bit reader over the big-endian words in shared memory: two consecutive words in registers plus a bit
- * offset, so a 32-bit look-ahead is ONE funnel shift; advancing adds to the offset and, when it crosses a word,
- * shifts the pair and loads the next word under a predicate -- no branch, one shared-memory load per 32 bits.
- * The reference does a byte access per BIT (pdmp3.c:1489-1527). */
+/* MSB-first bit reader over the compact main-data stream (big-endian words in global memory, written by k_compact):
+ * two consecutive words in registers plus a bit offset, so a 32-bit look-ahead is ONE funnel shift; advancing adds
+ * to the offset and, when it crosses a word, shifts the pair and takes the next word from a register that was
+ * loaded one refill earlier -- the global load has a whole refill interval (~100 instructions) to complete, and
+ * there is no branch.  The reference does a byte access per BIT (pdmp3.c:1489-1527). */
 struct k1_bits {
-  const uint32_t *wp; uint32_t hi, lo, off;               /* hi:lo = words at wp[-2], wp[-1]; off in 0..31 */
+  const uint32_t *wp; uint32_t hi, lo, nx, off;           /* hi, lo, nx = words at wp[-3], wp[-2], wp[-1]; off in 0..31 */
   const uint32_t *base;
   __device__ __forceinline__ void init(const uint32_t *s, uint32_t bitpos)
   {
-    base = s; wp = s + (bitpos >> 5) + 2; off = bitpos & 31; hi = wp[-2]; lo = wp[-1];
+    base = s; wp = s + (bitpos >> 5) + 3; off = bitpos & 31; hi = __ldg(wp - 3); lo = __ldg(wp - 2); nx = __ldg(wp - 1);
   }
-  __device__ __forceinline__ uint32_t pos() const { return (uint32_t)(wp - base - 2) * 32 + off; }
+  __device__ __forceinline__ uint32_t pos() const { return (uint32_t)(wp - base - 3) * 32 + off; }
   __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, off); }     /* next 32 bits */
   __device__ __forceinline__ void skip(uint32_t n)                                              /* n <= 32 */
   {
     off += n;
-    if (off >= 32) { hi = lo; lo = *wp; wp++; }
+    if (off >= 32) { hi = lo; lo = nx; nx = __ldg(wp); wp++; }
     off &= 31u;
   }
 };
@@ -81,64 +81,9 @@ struct k1_out {
 };
 
 
-/* Gather the main data of frames [F0,F1) plus the up-to-512 reservoir bytes in front of them into
- * shared memory as big-endian words: smem byte 512 <-> logical main-data byte frames[F0].main_pos.
- * `sw` must be zeroed; ends with __syncthreads().  s_fb: one int64 of shared scratch. */
-__device__ __forceinline__ void k1_gather(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames,
-                                          const uint8_t *__restrict__ tail, int64_t F0, int64_t F1, uint32_t *sw, int64_t *s_fb_p)
-{
-  const uint64_t base0 = frames[F0].main_pos;
-#define s_fb (*s_fb_p)
-  if (threadIdx.x == 0) {                                /* earliest frame whose data reaches into the window */
-    int64_t fs = F0; uint32_t acc = 0;
-    while (fs > 0 && acc < 512) { fs--; acc += frames[fs].main_size; }
-    s_fb = fs;
-  }
-  __syncthreads();
-  uint8_t *sb8 = reinterpret_cast<uint8_t *>(sw);
-  {
-    /* bytes that precede frame 0 of the batch come from the context's tail buffer */
-    const int64_t fb = s_fb;
-    const int64_t lo = (int64_t)base0 - 512;             /* logical position of smem byte 0 */
-    if (fb == 0) {
-      int64_t first = (int64_t)frames[0].main_pos;       /* logical start of the batch */
-      for (int64_t L = lo + threadIdx.x; L < first; L += blockDim.x) {
-        int64_t back = first - L;                        /* 1..512 */
-        if (back <= 512) sb8[(uint32_t)(L - lo) ^ 3u] = tail[512 - back];
-      }
-    }
-    /* one warp per source frame: whole destination words via two aligned loads + funnel shift, the
-     * ragged ends byte by byte (a word can straddle two frames' data) */
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    for (int64_t fs = fb + warp; fs < F1; fs += nwarp) {
-      const uint8_t *src = raw + frames[fs].main_off;
-      const int64_t d0 = (int64_t)frames[fs].main_pos - lo;   /* smem byte of the frame's first data byte */
-      const int32_t n = frames[fs].main_size;
-      const int32_t b0 = d0 < 0 ? (int32_t)(-d0) : 0;    /* first byte that lands inside the window */
-      if (b0 >= n) continue;
-      const int32_t lead = (int32_t)((4 - ((d0 + b0) & 3)) & 3);          /* bytes up to the next word boundary */
-      const int32_t wb = b0 + lead;                      /* first byte of the first whole word */
-      const int32_t nw = wb < n ? (n - wb) >> 2 : 0;     /* whole words */
-      for (int32_t b = b0 + (int32_t)lane; b < min(wb, n); b += 32) sb8[(uint32_t)(d0 + b) ^ 3u] = src[b];
-      for (int32_t b = wb + 4 * nw + (int32_t)lane; b < n; b += 32) sb8[(uint32_t)(d0 + b) ^ 3u] = src[b];
-      const uintptr_t sa = (uintptr_t)(src + wb);
-      const uint32_t *al = reinterpret_cast<const uint32_t *>(sa & ~(uintptr_t)3);
-      const uint32_t sh = (uint32_t)(sa & 3) * 8;
-      uint32_t *dw = sw + ((d0 + wb) >> 2);
-      for (int32_t k = lane; k < nw; k += 32) {
-        const uint32_t v = __funnelshift_r(__ldcs(al + k), __ldcs(al + k + 1), sh);   /* 4 stream bytes, first byte in bits 0-7 */
-        dw[k] = __byte_perm(v, 0, 0x0123);               /* first byte to the MSB */
-      }
-    }
-  }
-  __syncthreads();
-
-#undef s_fb
-}
-
 /* Scalefactors + Huffman of ONE granule-channel by ONE thread, spectra through `ob`, scalefactor bytes
  * to scf[64] (zeroed by the caller).  Returns count1. */
-__device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw, const uint16_t *lut, const p3_tables *__restrict__ T,
+__device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *__restrict__ sw /* compact main-data stream */, const uint16_t *lut, const p3_tables *__restrict__ T,
                                                  const p3_gc *__restrict__ gcs, const p3_frame &fr, const p3_gc &g, int64_t f,
                                                  uint32_t gr, uint32_t ch, uint64_t base0, k1_out &ob, uint8_t *scf)
 {
@@ -146,7 +91,11 @@ __device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw, const uint1
   {
     const bool ok = ch < fr.nch && !(fr.flags & (P3_FRAME_NODATA | P3_FRAME_BAD));
     const uint32_t p23l = ok ? P3_GC_P23L(g) : 0u;
-    const uint32_t fstart = (uint32_t)((int64_t)fr.main_pos - fr.main_begin - ((int64_t)base0 - 512)) * 8u;
+    /* where this frame's bits start in the compact stream: main_data_begin bytes in front of its own data.  The
+     * stream of a batch can exceed 2^32 bits, so the word pointer is rebased and bit positions stay relative. */
+    const int64_t byte0 = (int64_t)fr.main_pos - fr.main_begin - ((int64_t)base0 - 512);
+    sw += byte0 >> 2;
+    const uint32_t fstart = (uint32_t)(byte0 & 3) * 8u;
     uint32_t pos = fstart + P3_GC_START(g);
     const uint32_t part2_start = pos;
     const bool is_short = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;

@@ -1,5 +1,6 @@
 /* p3_kernels.cu -- hand-written sm_100a kernels for the MP3 Layer III granule decode path.
  *
+ *   k_compact   K0  bit reservoir: header-stripped main-data stream    (Get_Main_Data 1096-1122)
  *   k_huffman   K1  scalefactors + Huffman      (Read_Main_L3 1376-1435, Read_Huffman 2051-2115,
  *                                                Huffman_Decode 1593-1643)
  *   k_requant   K2  requantize+reorder+stereo+antialias, fused
@@ -20,33 +21,66 @@
 #include "p3_kernels.h"
 
 /* =============================================================================================
- * K1: Huffman.  One CTA per group of K1_FPB frames, one thread per granule-channel.
- * The group's main data (plus up to 512 bytes of reservoir before it) is gathered from the raw
- * stream into shared memory as big-endian words -- the "bit reservoir" of Get_Main_Data
- * (pdmp3.c:1096-1122) for the whole group at once; header and side-info bytes never reach smem.
+ * K0: k_compact -- the bit reservoir of Get_Main_Data (pdmp3.c:1096-1122) for the whole batch at once.
+ * Copies the main data of every frame (the bytes between the side info and the next header) into ONE contiguous,
+ * header-stripped stream of big-endian 32-bit words in global memory: byte 512 of the stream is the first
+ * main-data byte of the batch, bytes 0..511 are the reservoir carried over from the previous batch.  A frame whose
+ * main_data_begin reaches back then simply starts main_data_begin bytes earlier in the same stream.
+ * One warp per frame: whole destination words through two aligned loads + funnel shift, the ragged ends (a word
+ * can straddle two frames' data) byte by byte.
+ * ============================================================================================= */
+extern "C" __global__ void __launch_bounds__(128)
+k_compact(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames, const uint8_t *__restrict__ tail,
+          int64_t f_first, int64_t f_end, uint32_t *__restrict__ ms)
+{
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t *mb = reinterpret_cast<uint8_t *>(ms);
+  if (f_first == 0 && blockIdx.x == 0)                     /* the 512 bytes in front of the batch */
+    for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) mb[i ^ 3u] = tail[i];
+  const int64_t fs = f_first + (int64_t)blockIdx.x * 4 + warp;
+  if (fs >= f_end) return;
+  const uint4 fa = __ldg(reinterpret_cast<const uint4 *>(frames + fs)), fb = __ldg(reinterpret_cast<const uint4 *>(frames + fs) + 1);
+  const uint64_t main_off = (uint64_t)fa.x | (uint64_t)fa.y << 32, main_pos = (uint64_t)fa.z | (uint64_t)fa.w << 32;
+  const uint64_t base0 = frames[0].main_pos;
+  const int32_t n = (int32_t)(fb.x & 0xffffu);
+  const uint8_t *src = raw + main_off;
+  const uint64_t d0 = 512 + (main_pos - base0);            /* stream byte of the frame's first data byte */
+  const int32_t lead = (int32_t)((4 - (d0 & 3)) & 3);     /* bytes up to the next word boundary */
+  const int32_t nw = lead < n ? (n - lead) >> 2 : 0;       /* whole words */
+  for (int32_t b = (int32_t)lane; b < min(lead, n); b += 32) mb[(d0 + b) ^ 3u] = src[b];
+  for (int32_t b = lead + 4 * nw + (int32_t)lane; b < n; b += 32) mb[(d0 + b) ^ 3u] = src[b];
+  const uintptr_t sa = (uintptr_t)(src + lead);
+  const uint32_t *al = reinterpret_cast<const uint32_t *>(sa & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(sa & 3) * 8;
+  uint32_t *dw = ms + ((d0 + lead) >> 2);
+  for (int32_t k = lane; k < nw; k += 32) {
+    const uint32_t v = __funnelshift_r(__ldcs(al + k), __ldcs(al + k + 1), sh);   /* 4 stream bytes, first byte in bits 0-7 */
+    dw[k] = __byte_perm(v, 0, 0x0123);                     /* first byte to the MSB */
+  }
+}
+
+/* =============================================================================================
+ * K1: Huffman.  One CTA per group of K1_FPB frames, one thread per granule-channel, reading its bits straight
+ * from the compact main-data stream (k_compact) through L1 -- no shared-memory staging of the stream, so the only
+ * shared memory is the decode LUT and a small output ring and an SM holds 40+ warps of independent decoders.
  * ============================================================================================= */
 #include "p3_k1.cuh"
 
 extern "C" __global__ void __launch_bounds__(K1_THREADS)
-k_huffman(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
-          const p3_tables *__restrict__ T, const uint8_t *__restrict__ tail /*512 B before the batch*/,
-          int64_t f_first, int64_t f_end /*frames [f_first,f_end) decoded by this launch*/,
-          uint32_t smem_words, int16_t *__restrict__ is_out, int32_t *__restrict__ count1_out, uint8_t *__restrict__ scf_out)
+k_huffman(const uint32_t *__restrict__ ms /* compact main-data stream */, const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
+          const p3_tables *__restrict__ T, int64_t f_first, int64_t f_end /*frames [f_first,f_end) decoded by this launch*/,
+          int16_t *__restrict__ is_out, int32_t *__restrict__ count1_out, uint8_t *__restrict__ scf_out)
 {
   extern __shared__ uint32_t sm[];
-  uint32_t *sw = sm;                                     /* main-data words, big-endian */
-  uint32_t *ring = sm + smem_words;                      /* [4][K1_THREADS] output staging */
+  uint32_t *ring = sm;                                   /* [4][K1_THREADS] output staging */
   uint16_t *lut = reinterpret_cast<uint16_t *>(ring + 4 * K1_THREADS);
-  __shared__ int64_t s_fb;
 
   const int64_t F0 = f_first + (int64_t)blockIdx.x * K1_FPB;
   const int64_t F1 = min(F0 + (int64_t)K1_FPB, f_end);
-  const uint64_t base0 = frames[F0].main_pos;            /* smem byte 512 <-> logical byte base0 */
+  const uint64_t base0 = frames[0].main_pos;             /* stream byte 512 <-> logical byte base0 */
 
   for (uint32_t i = threadIdx.x; i < (T->hlut_used + 1) / 2; i += blockDim.x)
     reinterpret_cast<uint32_t *>(lut)[i] = reinterpret_cast<const uint32_t *>(T->hlut)[i];
-  for (uint32_t i = threadIdx.x; i < smem_words; i += blockDim.x) sw[i] = 0;
-  k1_gather(raw, frames, tail, F0, F1, sw, &s_fb);
 
   /* Lanes of a warp run in lock step, so a warp takes as long as its longest part.  Parts are therefore
    * handed out sorted by big_values (bitonic sort of the group's 128 keys in shared memory): each warp
@@ -76,11 +110,10 @@ k_huffman(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames, 
     const int64_t o = o_cta + gi;
     const p3_frame fr = frames[f]; const p3_gc g = gcs[4 * f + 2 * gr + ch];
     k1_out ob; ob.ring = ring + threadIdx.x; ob.stride = K1_THREADS; ob.pw = 0; ob.dst = reinterpret_cast<uint4 *>(is_out + o * 576);
-    /* scalefactor bytes go straight to this part's 64-byte row (byte stores merge in L2): staging them
-     * in shared memory would cost 8 KB per CTA, i.e. one resident CTA per SM */
+    /* scalefactor bytes go straight to this part's 64-byte row (byte stores merge in L2) */
     uint8_t *scf = scf_out + o * P3_SCF_STRIDE;
     for (int q = 0; q < P3_SCF_STRIDE / 16; q++) reinterpret_cast<uint4 *>(scf)[q] = make_uint4(0, 0, 0, 0);
-    count1_out[o] = (int32_t)k1_decode_gc(sw, lut, T, gcs, fr, g, f, gr, ch, base0, ob, scf);
+    count1_out[o] = (int32_t)k1_decode_gc(ms, lut, T, gcs, fr, g, f, gr, ch, base0, ob, scf);
   }
 }
 
