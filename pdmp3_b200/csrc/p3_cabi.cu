@@ -62,7 +62,7 @@ struct p3_ctx {
   int n_sm;
   /* current (most recently uploaded) batch */
   int64_t n_frames, n_pcm_frames; uint32_t nch; uint64_t raw_bytes;
-  int64_t chunk_frames;
+  uint32_t k1_smem_words; int64_t chunk_frames;
   int launches; int launches_parse; int taps; int fpc;
   float *d_pow43s; int synth_kernel;      /* signed |is|^(4/3) table (k_synth_warp); 0 = pick, 1 = always k_synth_fast */
   uint8_t next_tail[512]; int have_next_tail;
@@ -210,9 +210,18 @@ static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_
     if ((rc = ensure(&c->y, (size_t)cf * 4 * 576 * 4))) return rc;
   }
   }
+  /* K1 shared-memory window: 512 reservoir bytes + the largest group of K1_FPB frames (+ alignment and read-ahead slack) */
+  uint64_t maxg = 0;
+  for (int64_t f0 = 0; f0 < nf; f0 += K1_FPB) {
+    int64_t f1 = f0 + K1_FPB < nf ? f0 + K1_FPB : nf;
+    uint64_t span = b->frames[f1 - 1].main_pos + b->frames[f1 - 1].main_size - b->frames[f0].main_pos;
+    if (span > maxg) maxg = span;
+  }
+  c->k1_smem_words = (uint32_t)(((512 + maxg + 64 + 15) & ~(uint64_t)15) / 4);
+  if ((size_t)c->k1_smem_words * 4 + sizeof(((p3_tables *)0)->hlut) + 4 * K1_THREADS * 4 > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
   /* compact main-data stream: 512 reservoir bytes + all main data of the batch, zero padded (the bit readers run a few words ahead) */
   sl->ms_bytes = 512 + (b->frames[nf - 1].main_pos + b->frames[nf - 1].main_size - b->frames[0].main_pos);
-  if ((rc = ensure(&sl->ms, sl->ms_bytes + 256))) return rc;
+  if ((rc = ensure(&sl->ms, sl->ms_bytes + 512))) return rc;
   CK(cudaMemsetAsync((uint8_t *)sl->ms.p + (sl->ms_bytes & ~(uint64_t)3), 0, 128, st));
   memcpy(sl->h_tail, c->h_tail, 512);
   CK(cudaMemcpyAsync(sl->raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, st));
@@ -260,9 +269,9 @@ static int run_chunk(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, cudaEvent_t
   if (ev) CK(cudaEventRecord(ev[0], c->stream));
   k_compact<<<(unsigned)((nf + 3) / 4), 128, 0, c->stream>>>((const uint8_t *)sl->raw.p, fr, sl->d_tail, f0, f1, (uint32_t *)sl->ms.p);
   if (ev) CK(cudaEventRecord(ev[1], c->stream));
-  size_t smem1 = 4 * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
+  size_t smem1 = (size_t)c->k1_smem_words * 4 + 4 * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
   k_huffman<<<(unsigned)((nf + K1_FPB - 1) / K1_FPB), K1_THREADS, smem1, c->stream>>>((const uint32_t *)sl->ms.p, fr, gc, c->d_tables, f0, f1,
-      (int16_t *)c->is16.p, (int32_t *)c->count1.p, (uint8_t *)c->scf.p);
+      c->k1_smem_words, (int16_t *)c->is16.p, (int32_t *)c->count1.p, (uint8_t *)c->scf.p);
   if (ev) CK(cudaEventRecord(ev[2], c->stream));
   if (c->mode == P3_MODE_FAST) {
     launch_synth(c, sl, f0, f1, (const int16_t *)c->is16.p, (const int32_t *)c->count1.p, (const uint8_t *)c->scf.p, si, so);

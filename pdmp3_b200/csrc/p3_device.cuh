@@ -20,11 +20,11 @@ struct p3_state {
   float xhist[2][15][32];         /* FAST mode: 32-point DCT of the last 15 slots, [ch][age-1][k]   */
 };
 
-/* ---- MSB-first random bit access over big-endian words (the compact main-data stream; pdmp3.c:1489-1527) ---- */
-__device__ __forceinline__ uint32_t p3_peek32(const uint32_t *__restrict__ sw, uint32_t bitpos)
+/* ---- MSB-first random bit access over big-endian words in shared memory (pdmp3.c:1489-1527) ---- */
+__device__ __forceinline__ uint32_t p3_peek32(const uint32_t *sw, uint32_t bitpos)
 {
   uint32_t i = bitpos >> 5;
-  return __funnelshift_l(__ldg(sw + i + 1), __ldg(sw + i), bitpos & 31);
+  return __funnelshift_l(sw[i + 1], sw[i], bitpos & 31);
 }
 __device__ __forceinline__ uint32_t p3_getbits(const uint32_t *sw, uint32_t &bitpos, uint32_t n)
 {

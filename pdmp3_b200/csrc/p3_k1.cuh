@@ -3,24 +3,24 @@
 #pragma once
 #include "p3_device.cuh"
 
-/* MSB-first bit reader over the compact main-data stream (big-endian words in global memory, written by k_compact):
- * two consecutive words in registers plus a bit offset, so a 32-bit look-ahead is ONE funnel shift; advancing adds
- * to the offset and, when it crosses a word, shifts the pair and takes the next word from a register that was
- * loaded one refill earlier -- the global load has a whole refill interval (~100 instructions) to complete, and
- * there is no branch.  The reference does a byte access per BIT (pdmp3.c:1489-1527). */
+/* MSB-first bit reader over the big-endian words of the CTA's window of the compact main-data stream in shared
+ * memory: two consecutive words in registers plus a bit offset, so a 32-bit look-ahead is ONE funnel shift;
+ * advancing adds to the offset and, when it crosses a word, shifts the pair and loads the next word under a
+ * predicate -- no branch, one shared-memory load per 32 bits.  The reference does a byte access per BIT
+ * (pdmp3.c:1489-1527). */
 struct k1_bits {
-  const uint32_t *wp; uint32_t hi, lo, nx, off;           /* hi, lo, nx = words at wp[-3], wp[-2], wp[-1]; off in 0..31 */
+  const uint32_t *wp; uint32_t hi, lo, off;               /* hi:lo = words at wp[-2], wp[-1]; off in 0..31 */
   const uint32_t *base;
   __device__ __forceinline__ void init(const uint32_t *s, uint32_t bitpos)
   {
-    base = s; wp = s + (bitpos >> 5) + 3; off = bitpos & 31; hi = __ldg(wp - 3); lo = __ldg(wp - 2); nx = __ldg(wp - 1);
+    base = s; wp = s + (bitpos >> 5) + 2; off = bitpos & 31; hi = wp[-2]; lo = wp[-1];
   }
-  __device__ __forceinline__ uint32_t pos() const { return (uint32_t)(wp - base - 3) * 32 + off; }
+  __device__ __forceinline__ uint32_t pos() const { return (uint32_t)(wp - base - 2) * 32 + off; }
   __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, off); }     /* next 32 bits */
   __device__ __forceinline__ void skip(uint32_t n)                                              /* n <= 32 */
   {
     off += n;
-    if (off >= 32) { hi = lo; lo = nx; nx = __ldg(wp); wp++; }
+    if (off >= 32) { hi = lo; lo = *wp; wp++; }
     off &= 31u;
   }
 };
@@ -83,19 +83,16 @@ struct k1_out {
 
 /* Scalefactors + Huffman of ONE granule-channel by ONE thread, spectra through `ob`, scalefactor bytes
  * to scf[64] (zeroed by the caller).  Returns count1. */
-__device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *__restrict__ sw /* compact main-data stream */, const uint16_t *lut, const p3_tables *__restrict__ T,
+__device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw /* the CTA's window of the compact main-data stream, shared memory */, const uint16_t *lut, const p3_tables *__restrict__ T,
                                                  const p3_gc *__restrict__ gcs, const p3_frame &fr, const p3_gc &g, int64_t f,
-                                                 uint32_t gr, uint32_t ch, uint64_t base0, k1_out &ob, uint8_t *scf)
+                                                 uint32_t gr, uint32_t ch, int64_t win0 /* stream byte of window byte 0 */, k1_out &ob, uint8_t *scf)
 {
   uint32_t c1 = 0;
   {
     const bool ok = ch < fr.nch && !(fr.flags & (P3_FRAME_NODATA | P3_FRAME_BAD));
     const uint32_t p23l = ok ? P3_GC_P23L(g) : 0u;
-    /* where this frame's bits start in the compact stream: main_data_begin bytes in front of its own data.  The
-     * stream of a batch can exceed 2^32 bits, so the word pointer is rebased and bit positions stay relative. */
-    const int64_t byte0 = (int64_t)fr.main_pos - fr.main_begin - ((int64_t)base0 - 512);
-    sw += byte0 >> 2;
-    const uint32_t fstart = (uint32_t)(byte0 & 3) * 8u;
+    /* where this frame's bits start: main_data_begin bytes in front of its own data, relative to the window */
+    const uint32_t fstart = (uint32_t)((int64_t)fr.main_pos - fr.main_begin - win0) * 8u;
     uint32_t pos = fstart + P3_GC_START(g);
     const uint32_t part2_start = pos;
     const bool is_short = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;

@@ -53,31 +53,56 @@ k_compact(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames, 
   const uint32_t *al = reinterpret_cast<const uint32_t *>(sa & ~(uintptr_t)3);
   const uint32_t sh = (uint32_t)(sa & 3) * 8;
   uint32_t *dw = ms + ((d0 + lead) >> 2);
-  for (int32_t k = lane; k < nw; k += 32) {
-    const uint32_t v = __funnelshift_r(__ldcs(al + k), __ldcs(al + k + 1), sh);   /* 4 stream bytes, first byte in bits 0-7 */
-    dw[k] = __byte_perm(v, 0, 0x0123);                     /* first byte to the MSB */
+  /* every lane takes its aligned source words for the whole frame first (all loads in flight together: a frame is at
+   * most 1441 bytes = 12 words per lane), the word after a lane's own comes from its neighbour by shuffle */
+  uint32_t a[12];
+  #pragma unroll
+  for (int j = 0; j < 12; j++) a[j] = (int32_t)(lane + 32 * j) <= nw ? __ldcs(al + lane + 32 * j) : 0u;
+  #pragma unroll
+  for (int j = 0; j < 12; j++) {
+    uint32_t nxt = __shfl_down_sync(0xffffffffu, a[j], 1);
+    const uint32_t wrap = __shfl_sync(0xffffffffu, j + 1 < 12 ? a[j + 1 < 12 ? j + 1 : j] : 0u, 0);
+    if (lane == 31) nxt = wrap;
+    const int32_t k = (int32_t)lane + 32 * j;
+    if (k < nw) dw[k] = __byte_perm(__funnelshift_r(a[j], nxt, sh), 0, 0x0123);   /* 4 stream bytes, first byte to the MSB */
   }
 }
 
 /* =============================================================================================
- * K1: Huffman.  One CTA per group of K1_FPB frames, one thread per granule-channel, reading its bits straight
- * from the compact main-data stream (k_compact) through L1 -- no shared-memory staging of the stream, so the only
- * shared memory is the decode LUT and a small output ring and an SM holds 40+ warps of independent decoders.
+ * K1: Huffman.  One CTA per group of K1_FPB frames, one thread per granule-channel.  The group's slice of the
+ * compact main-data stream (its frames' data plus the 512 reservoir bytes in front: contiguous and already in
+ * big-endian words thanks to k_compact) is brought into shared memory by ONE bulk copy of the TMA engine
+ * (cp.async.bulk + mbarrier) while the threads load the LUT and sort their parts.
  * ============================================================================================= */
 #include "p3_k1.cuh"
 
 extern "C" __global__ void __launch_bounds__(K1_THREADS)
 k_huffman(const uint32_t *__restrict__ ms /* compact main-data stream */, const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
           const p3_tables *__restrict__ T, int64_t f_first, int64_t f_end /*frames [f_first,f_end) decoded by this launch*/,
-          int16_t *__restrict__ is_out, int32_t *__restrict__ count1_out, uint8_t *__restrict__ scf_out)
+          uint32_t smem_words, int16_t *__restrict__ is_out, int32_t *__restrict__ count1_out, uint8_t *__restrict__ scf_out)
 {
-  extern __shared__ uint32_t sm[];
-  uint32_t *ring = sm;                                   /* [4][K1_THREADS] output staging */
+  extern __shared__ __align__(16) uint32_t sm[];
+  uint32_t *sw = sm;                                     /* window of the main-data stream, big-endian words */
+  uint32_t *ring = sm + smem_words;                      /* [4][K1_THREADS] output staging */
   uint16_t *lut = reinterpret_cast<uint16_t *>(ring + 4 * K1_THREADS);
+  __shared__ __align__(8) unsigned long long s_bar;
 
   const int64_t F0 = f_first + (int64_t)blockIdx.x * K1_FPB;
   const int64_t F1 = min(F0 + (int64_t)K1_FPB, f_end);
-  const uint64_t base0 = frames[0].main_pos;             /* stream byte 512 <-> logical byte base0 */
+  /* stream byte 512 = first main-data byte of the batch; the window starts (16-byte aligned) at or below the 512
+   * reservoir bytes in front of frame F0 and ends behind frame F1-1 */
+  const uint64_t base0 = frames[0].main_pos;
+  const int64_t win0 = (int64_t)((frames[F0].main_pos - base0) & ~(uint64_t)15);          /* stream byte of window byte 0 */
+  if (threadIdx.x == 0) {
+    const int64_t end = 512 + (int64_t)(frames[F1 - 1].main_pos + frames[F1 - 1].main_size - base0);
+    uint32_t bytes = (uint32_t)((end - win0 + 16 + 15) & ~(int64_t)15);
+    if (bytes > smem_words * 4) bytes = smem_words * 4;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\nfence.mbarrier_init.release.cluster;" :: "r"(bar) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(sw)), "l"(reinterpret_cast<const uint8_t *>(ms) + win0), "r"(bytes), "r"(bar) : "memory");
+  }
 
   for (uint32_t i = threadIdx.x; i < (T->hlut_used + 1) / 2; i += blockDim.x)
     reinterpret_cast<uint32_t *>(lut)[i] = reinterpret_cast<const uint32_t *>(T->hlut)[i];
@@ -102,6 +127,14 @@ k_huffman(const uint32_t *__restrict__ ms /* compact main-data stream */, const 
         __syncthreads();
       }
   }
+  {                                                        /* the window has landed (the sort above ended with a barrier, so s_bar is initialised for everyone) */
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    uint32_t ok = 0, spins = 0;
+    do {
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar) : "memory");
+      if (!ok && ++spins > (1u << 24)) __trap();
+    } while (!ok);
+  }
   const uint32_t gi = s_key[threadIdx.x] & 0xffu;         /* granule-channel within the group handled by this thread */
   const int64_t f = F0 + (gi >> 2);
   const int64_t o_cta = (F0 - f_first) * 4;
@@ -113,7 +146,7 @@ k_huffman(const uint32_t *__restrict__ ms /* compact main-data stream */, const 
     /* scalefactor bytes go straight to this part's 64-byte row (byte stores merge in L2) */
     uint8_t *scf = scf_out + o * P3_SCF_STRIDE;
     for (int q = 0; q < P3_SCF_STRIDE / 16; q++) reinterpret_cast<uint4 *>(scf)[q] = make_uint4(0, 0, 0, 0);
-    count1_out[o] = (int32_t)k1_decode_gc(ms, lut, T, gcs, fr, g, f, gr, ch, base0, ob, scf);
+    count1_out[o] = (int32_t)k1_decode_gc(sw, lut, T, gcs, fr, g, f, gr, ch, win0 - 512 + (int64_t)base0, ob, scf);
   }
 }
 

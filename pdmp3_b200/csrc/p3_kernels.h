@@ -18,7 +18,7 @@ struct p3_state;
 extern "C" {
 __global__ void k_compact(const uint8_t *raw, const p3_frame *frames, const uint8_t *tail, int64_t f_first, int64_t f_end, uint32_t *ms);
 __global__ void k_huffman(const uint32_t *ms, const p3_frame *frames, const p3_gc *gcs, const p3_tables *T,
-                          int64_t f_first, int64_t f_end, int16_t *is_out, int32_t *count1_out, uint8_t *scf_out);
+                          int64_t f_first, int64_t f_end, uint32_t smem_words, int16_t *is_out, int32_t *count1_out, uint8_t *scf_out);
 __global__ void k_sideinfo(const uint8_t *raw, p3_frame *frames, p3_gc *gcs, int64_t n_frames, int *any_empty);
 __global__ void k_q6_chain(const p3_frame *frames, p3_gc *gcs, int64_t n_frames, const int *any_empty);
 __global__ void k_requant(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end,
