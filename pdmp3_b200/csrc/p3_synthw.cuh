@@ -2,7 +2,8 @@
  * (included at the end of p3_fused.cu; shares its constant tables and scalar helpers)
  *
  * Same algorithm and operation order as k_synth_fast (requantize .. PCM of Decode_L3, pdmp3.c:1024-1060, plus
- * Convert_Frame_S16, 2307-2345); requantize / stereo / antialias keep the reference's exact arithmetic, the
+ * Convert_Frame_S16, 2307-2345); requantize / intensity stereo / antialias keep the reference's exact arithmetic, MS
+ * stereo reproduces its double-precision product in packed fp32 (identical but for ~1e-7 of the values, by 1 ulp), the
  * transforms agree with k_synth_fast to rounding (ptxas contracts some packed mul+add pairs into FFMA2), the PCM
  * is within 1 LSB of the reference like that kernel's.  Organised around the warp:
  *
@@ -159,7 +160,6 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   issue_desc(rel0, 0); if (nfr > 1) issue_desc(rel0 + 1, 1);
   issue(rel0, 0, 0); if (SW_NBUF == 2) issue(rel0, 1, 1);
 
-  double inv_sqrt2; asm volatile("mov.f64 %0, 0d3FE6A09E667F3BCD;" : "=d"(inv_sqrt2));     /* 0.70710678118654752440, kept in registers */
   #pragma unroll 1
   for (int32_t q = 0; q < 2 * nfr; q++) {                  /* q: granules done by this warp */
     {
@@ -220,7 +220,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
             const int m = 2 * i + h;
             const float2 sc = scl[(sfbp[m / 6] >> (5 * (m % 6))) & 31u];
             const int va = h ? (int)wa >> 16 : (int)(int16_t)(wa & 0xffffu), vb = h ? (int)wb >> 16 : (int)(int16_t)(wb & 0xffffu);
-            in[m] = f2_make(__fmul_rn(sc.x, __ldg(pow43s + va)), __fmul_rn(sc.y, __ldg(pow43s + vb)));   /* (t1*t2)*t3, t3 = sign*|is|^(4/3) */
+            in[m] = vmul(f2_make(__ldg(pow43s + va), __ldg(pow43s + vb)), f2_make(sc.x, sc.y));   /* (t1*t2)*t3, t3 = sign*|is|^(4/3); one product, nothing to contract */
           }
         }
       }
@@ -252,14 +252,20 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       const uint32_t c1r = (uint32_t)p1.c1;
       const uint32_t msn = (st_on && (mode_ext & 2)) ? min((uint32_t)p0.c1, c1r) : 0u;      /* min(count1), sic (pdmp3.c:1920) */
       if (18 * sb < msn) {
-        /* float sum times a double constant, rounded once to float (pdmp3.c:168,1923-1926) */
+        /* the reference multiplies the float sum by the DOUBLE constant 1/sqrt 2 and rounds once to float (pdmp3.c:168,
+         * 1923-1926).  Same result from packed fp32: with C = Ch + Cl (two floats), p = fl(a*Ch), e = a*Ch - p (exact, one
+         * fma), t = fl(a*Cl + e), result = fl(p + t).  It can differ from the double-precision product only when that
+         * lies within 2^-47 of a rounding boundary (~1e-7 of the values; none in 2*10^7 random ones, tools/proto). */
+        constexpr float Ch = 0.70710677f, Cl = 1.21016175e-08f;
         #pragma unroll
         for (int m = 0; m < 18; m++) {
           const float l = f2_x(in[m]), r = f2_y(in[m]);
-          const float a = __fadd_rn(l, r), d = __fsub_rn(l, r);
-          const float ml = __double2float_rn(__dmul_rn((double)a, inv_sqrt2)), mr = __double2float_rn(__dmul_rn((double)d, inv_sqrt2));
-          const bool on = 18 * sb + m < msn;
-          in[m] = f2_make(on ? ml : l, on ? mr : r);
+          const f2 ad = f2_make(__fadd_rn(l, r), __fsub_rn(l, r));
+          const f2 p = vmul(ad, Ch);
+          const f2 ne = vfma(ad, -Ch, p);                          /* -(a*Ch - p), exact */
+          const f2 nt = vfma(ad, -Cl, ne);                         /* -(a*Cl + e) */
+          const f2 ms = vfma(nt, -1.0f, p);                        /* p + t; written as an fma so that nothing can be contracted into it */
+          if (18 * sb + m < msn) in[m] = ms;
         }
       }
 #ifndef SW_NOSLOW
