@@ -27,6 +27,9 @@ import numpy as np
 BLOCK = 15625
 CFG = dict(bitrate_index=14, mode=1, mode_ext=2, blocks=0)       # configs[2]: 320 kbps CBR joint stereo (MS), long blocks
 WORKLOAD = "1M-frame 44.1kHz 320kbps CBR joint-stereo(MS) synthetic stream, full on-device pipeline (BASELINE configs[2]; per GPU of configs[4])"
+# --workload vbr: BASELINE configs[3], the divergence stress (not the headline line): VBR 32-320 kbps, long/short/mixed blocks, MS + intensity
+CFG_VBR = dict(bitrate_index=0, mode=1, mode_ext=-1, blocks=1, overrun_pm=30)
+WORKLOAD_VBR = "1M-frame 44.1kHz VBR 32-320kbps joint-stereo synthetic stream, mixed long/short/mixed blocks, MS+intensity, full on-device pipeline (BASELINE configs[3])"
 
 
 def make_stream(n_frames, seed=1):
@@ -122,7 +125,10 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["exact", "fast"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="cbr320", choices=["cbr320", "vbr"], help="cbr320 = BASELINE configs[2] (headline); vbr = configs[3]")
     a = ap.parse_args()
+    global CFG, WORKLOAD
+    if a.workload == "vbr": CFG, WORKLOAD = CFG_VBR, WORKLOAD_VBR
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = os.cpu_count() or 1
 

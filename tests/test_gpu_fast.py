@@ -125,3 +125,24 @@ def test_one_million_frames_properties(fast_ctx):
     ex.close()
     d = np.abs(two.astype(np.int32) - ref.astype(np.int32))
     assert d.max() <= 1 and (d == 0).mean() > 0.9
+
+
+def test_one_million_frames_vbr_mixed(fast_ctx):
+    """BASELINE configs[3] at full size (divergence stress): 1 000 000 frames of VBR 32-320 kbps joint stereo with long,
+    short and mixed blocks, MS and intensity stereo (a 15 625-frame block tiled 64x, 0.42 GB in, 4.6 GB of PCM out).
+    Tiles 2..64 decode to identical PCM, and tile 2 is within 1 LSB of the bit-exact decode of the same data."""
+    import pdmp3_b200
+    blk, _ = H.synth(15625, seed=4, **H.CONFIGS["cfg4_vbr_mixed"])
+    s = np.tile(blk, 64)
+    fast_ctx.reset()
+    pcm = fast_ctx.decode(s, lookahead=0, hop_only=True)
+    assert pcm.shape == (1000000, 1152, 2)
+    tiles = pcm.reshape(64, 15625, 1152, 2)
+    ref = tiles[1]
+    for k in range(2, 64):
+        assert np.array_equal(tiles[k], ref), "tile %d" % k
+    ex = pdmp3_b200.Context(0, pdmp3_b200.MODE_EXACT)
+    two = ex.decode(np.tile(blk, 2), lookahead=0)[15625:]
+    ex.close()
+    d = np.abs(two.astype(np.int32) - ref.astype(np.int32))
+    assert d.max() <= 1 and (d == 0).mean() > 0.9
