@@ -269,15 +269,22 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
         }
       }
 #ifndef SW_NOSLOW
-      if (is_on) {                                            /* intensity stereo: line by line through the scratch block, rare */
+      /* intensity stereo touches a band only if it starts at or above the right channel's count1: with count1 beyond the
+       * start of the last eligible band there is nothing to do (the usual case at high bit rates) */
+      const uint32_t first_short0 = p0.first_short;
+      bool is_any = false;
+      if (is_on) {                                            /* first line of the last band it can touch: long sfb 20, long sfb 7 (mixed), short sfb 11 (x3) */
+        const uint32_t ll = T->sfb_l[sf][first_short0 == 576 ? 20 : 7], ls = 3u * T->sfb_s[sf][11];
+        is_any = (first_short0 != 0 && ll >= c1r) || (first_short0 != 576 && ls >= c1r);
+      }
+      if (is_any) {                                           /* line by line through the scratch block, rare */
         f2 *scr = blk;                                           /* [576] */
         #pragma unroll
         for (int m = 0; m < 18; m++) scr[18 * sb + m] = in[m];
         __syncwarp();
-        const uint32_t first_short0 = p0.first_short;
         const bool sh0 = first_short0 < 576;
         #pragma unroll 1
-        for (uint32_t d = lane; d < 576; d += 32) {
+        for (uint32_t d = (c1r & ~31u) + lane; d < 576; d += 32) {   /* a line below count1 is in a band that starts below it */
           if (d < msn) continue;
           float l = f2_x(scr[d]), r = f2_y(scr[d]);
           if (d >= first_short0) {

@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_fast.py -x -q -k "vbr_mixed" 2>&1 | tail -3
-timeout 600 python bench.py --no-cpu --workload vbr > gpurun_out/s12_bench_vbr.json 2> gpurun_out/s12_bench_vbr.err; cat gpurun_out/s12_bench_vbr.json | grep -o '"ms_per_step": [0-9.]*\|stage_ms.*\|"value": [0-9.]*'; tail -3 gpurun_out/s12_bench_vbr.err
+for w in cbr320 vbr; do echo "== $w"; timeout 300 python bench.py --no-cpu --no-e2e --workload $w 2>&1 | grep -o 'stage_ms.*'; done
+timeout 600 python -m pytest tests/test_gpu_fast.py tests/test_gpu_parity.py -x -q 2>&1 | tail -2
