@@ -240,8 +240,10 @@ def main():
     alg_bytes = (frame_bytes + 4608.0) * n_frames
     synth = "k_synth_fast" if os.environ.get("P3_SYNTH") == "cta" else "k_synth_warp"       # stereo workload: the packed-FFMA2 warp kernel
     names = ["k_compact", "k_huffman", synth, "-", "-"] if a.mode == "fast" else ["k_compact", "k_huffman", "k_requant", "k_imdct", "k_polyphase"]
-    dom = int(np.argmax(ms_stage)) if sum(ms_stage) > 0 else 0
-    dom_ms = ms_stage[dom] if sum(ms_stage) > 0 else ms
+    staged = sum(ms_stage) > 0                              # per-kernel times exist when the batch ran as one launch sequence
+    dom = int(np.argmax(ms_stage)) if staged else 0
+    dom_ms = ms_stage[dom] if staged else ms
+    if not staged: names = ["whole launch sequence (chunked)"] + ["-"] * 4
     traffic = None
     tj = os.path.join(ROOT, "profiles", "traffic.json")       # dram__bytes_read+write per frame of each kernel, from the committed ncu captures
     if os.path.exists(tj):
