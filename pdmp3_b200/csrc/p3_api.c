@@ -32,12 +32,14 @@ static double now_ms(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &
 
 #define P3_DEFAULT_RING 16384u              /* INBUF_SIZE (pdmp3.c:123) */
 #define P3_API_CHUNK    32768               /* frames per GPU batch inside one pdmp3_read() */
+#define P3_API_DIRECT   64                  /* reads of at least this many frames are decoded straight into the caller's buffer */
+#define P3_API_AHEAD    4096                /* smaller reads: up to this many buffered frames are decoded at once into the handle's PCM queue */
 
 struct pdmp3_handle {
   unsigned char *in; size_t cap, istart, iend;      /* buffered bytes are in[istart,iend) */
   size_t processed;
-  int16_t *pcm;                                     /* one frame: the partially delivered frame */
-  size_t pend_pos, pend_end;                        /* undelivered PCM bytes of it: [pend_pos,pend_end) */
+  int16_t *pcm; size_t pcm_cap;                     /* PCM queue: frames decoded ahead of small reads (pcm_cap frames of room) */
+  size_t pend_pos, pend_end;                        /* undelivered PCM bytes of the queue: [pend_pos,pend_end) */
   int in_pinned;
   p3_frame *dfr[3]; p3_gc *dgc[3]; int dnext;       /* page-locked descriptor arrays, rotated over the in-flight batches */
   p3_ctx *ctx; int device; int ctx_failed; int mode; int host_sideinfo;
@@ -143,7 +145,7 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
   int res = PDMP3_ERR, inflight = 0;
   const int trace = getenv("P3_TRACE") != NULL; double t_parse = 0, t_decode = 0, t_sync = 0; int nb = 0;
   *done = 0;
-  if (id->pend_pos < id->pend_end) {                /* rest of a previously decoded frame (pdmp3.c:2437-2442) */
+  if (id->pend_pos < id->pend_end) {                /* PCM decoded earlier: the rest of a frame (pdmp3.c:2437-2442) and the frames decoded ahead */
     size_t n = id->pend_end - id->pend_pos; if (n > outsize) n = outsize;
     memcpy(outmemory, (unsigned char *)id->pcm + id->pend_pos, n);
     id->pend_pos += n; outmemory += n; outsize -= n; *done += n;
@@ -152,12 +154,14 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
   while (outsize) {
     if (in_filled(id) < 2 * 576) { res = PDMP3_NEED_MORE; break; }          /* pdmp3.c:2445,2466 */
     size_t fbytes = 1152 * sizeof(int16_t) * (size_t)(id->nch == 1 ? 1 : 2);
-    /* whole frames go straight into the caller's buffer, P3_API_CHUNK frames per GPU batch, the batches
-     * double-buffered (upload / kernels / download overlap, and so does the parsing of the next batch);
-     * a trailing partial frame is decoded into the handle and handed out piecewise (the reference's
-     * ostart cursor, pdmp3.c:2317-2344) */
-    int direct = outsize >= fbytes;
-    int64_t want = direct ? (int64_t)(outsize / fbytes) : 1;
+    /* Large reads: whole frames go straight into the caller's buffer, P3_API_CHUNK frames per GPU batch, the batches
+     * double-buffered (upload / kernels / download overlap, and so does the parsing of the next batch).
+     * Small reads (the reference CLI asks for 16 KiB = 3.6 frames at a time, pdmp3.c:2564): every frame that is
+     * already buffered and decodable goes through the GPU as ONE batch into the handle's PCM queue and is handed out
+     * piecewise (the reference's ostart cursor, pdmp3.c:2317-2344, extended from one frame to a queue).  Which
+     * frames are decoded, the bytes delivered and the return codes are the reference's; only the moment differs. */
+    int direct = outsize >= P3_API_DIRECT * fbytes;
+    int64_t want = direct ? (int64_t)(outsize / fbytes) : P3_API_AHEAD;
     if (want > P3_API_CHUNK) want = P3_API_CHUNK;
     p3_parse_opts po = {want, 2 * 576, want >= 8192 ? 4 : 1, 0, id->host_sideinfo ? 0u : 1u};   /* side info: parsed on the device */
     p3_parse_state ps = id->ps;
@@ -185,7 +189,11 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
     }
     int16_t *target = (int16_t *)outmemory;
     if (!direct) {
-      if (!id->pcm) { id->pcm = (int16_t *)malloc(1152 * 2 * sizeof(int16_t)); if (!id->pcm) { p3_parsed_free(&pb); res = PDMP3_ERR; break; } }
+      if (id->pcm_cap < (size_t)pb.n_frames) {
+        free(id->pcm); id->pcm_cap = (size_t)pb.n_frames + 16;
+        id->pcm = (int16_t *)malloc(id->pcm_cap * 1152 * 2 * sizeof(int16_t));
+        if (!id->pcm) { id->pcm_cap = 0; p3_parsed_free(&pb); res = PDMP3_ERR; break; }
+      }
       target = id->pcm;
     }
     for (int64_t f = 0; f < pb.n_frames; f++) pb.frames[f].pcm_index = (uint32_t)f;   /* slots restart at 0 for every batch */
@@ -206,9 +214,10 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
       size_t n = (size_t)nfr * fbytes;
       outmemory += n; outsize -= n; *done += n;
     } else {
-      memcpy(outmemory, id->pcm, outsize);
-      id->pend_pos = outsize; id->pend_end = fbytes;
-      *done += outsize; outmemory += outsize; outsize = 0;
+      const size_t have = (size_t)nfr * fbytes, n = have < outsize ? have : outsize;
+      memcpy(outmemory, id->pcm, n);
+      id->pend_pos = n; id->pend_end = have;
+      *done += n; outmemory += n; outsize -= n;
     }
     res = PDMP3_OK;
   }
