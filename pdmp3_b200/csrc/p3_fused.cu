@@ -46,19 +46,20 @@ extern "C" int p3_fused_upload_consts(const p3_tables *T, const float *dct4)
 
 /* fast transforms (32-point DCT-II, 18-point DCT-IV), shared with the packed-stereo kernel: p3_xform.cuh */
 
-/* three 12-point IMDCTs of a short block (pdmp3.c:1673-1686): raw[6w+6+p] += win2[p] * sum_m in[w+3m] cos12[m][p] */
-__device__ __forceinline__ void imdct_short(const float (&in)[18], float (&raw)[36])
+/* three 12-point IMDCTs of a short block (pdmp3.c:1673-1686): raw[6w+6+p] += win2[p] * sum_m in[w+3m] cos12[m][p];
+ * V = float (one channel) or f2 (both channels packed: the coefficients are the same for both) */
+template <class V> __device__ __forceinline__ void imdct_short(const V (&in)[18], V (&raw)[36])
 {
   #pragma unroll
-  for (int q = 0; q < 36; q++) raw[q] = 0.0f;
+  for (int q = 0; q < 36; q++) raw[q] = vzero(in[0]);
   #pragma unroll
   for (int w = 0; w < 3; w++)
     #pragma unroll
     for (int q = 0; q < 12; q++) {
-      float sum = 0.0f;
+      V sum = vzero(in[0]);
       #pragma unroll
-      for (int m = 0; m < 6; m++) sum = __fmaf_rn(in[w + 3 * m], FC.cos12[m][q], sum);
-      raw[6 * w + 6 + q] = __fmaf_rn(sum, FC.win[2][q], raw[6 * w + 6 + q]);
+      for (int m = 0; m < 6; m++) sum = vfma(in[w + 3 * m], FC.cos12[m][q], sum);
+      raw[6 * w + 6 + q] = vfma(sum, FC.win[2][q], raw[6 * w + 6 + q]);
     }
 }
 
@@ -294,7 +295,7 @@ __device__ __forceinline__ void sf_stageD(const synth_sm &S, int slot, int n, co
           }
         } else {
           float raw[36];
-          imdct_short(in, raw);
+          imdct_short<float>(in, raw);
           #pragma unroll
           for (int i = 0; i < 18; i++) { x[i] = raw[i]; tl[i] = raw[18 + i]; }
         }

@@ -277,7 +277,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
         const uint32_t ll = T->sfb_l[sf][first_short0 == 576 ? 20 : 7], ls = 3u * T->sfb_s[sf][11];
         is_any = (first_short0 != 0 && ll >= c1r) || (first_short0 != 576 && ls >= c1r);
       }
-      if (is_any) {                                           /* line by line through the scratch block, rare */
+      if (__builtin_expect(is_any, 0)) {                                           /* line by line through the scratch block, rare */
         f2 *scr = blk;                                           /* [576] */
         #pragma unroll
         for (int m = 0; m < 18; m++) scr[18 * sb + m] = in[m];
@@ -325,7 +325,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
           const float bx = __shfl_up_sync(0xffffffffu, lx, 1), by = __shfl_up_sync(0xffffffffu, ly, 1);       /* line 18sb-1-i */
           const float ax = __shfl_down_sync(0xffffffffu, ux, 1), ay = __shfl_down_sync(0xffffffffu, uy, 1);   /* line 18(sb+1)+i */
 #ifndef SW_NOSLOW
-          if (p0.sblim == p1.sblim)
+          if (__builtin_expect(p0.sblim == p1.sblim, 1))
 #endif
           {
             const f2 u = in[i], l = in[17 - i];
@@ -350,7 +350,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
         const uint32_t bt0 = (p0.ws && p0.mixed && sb < 2) ? 0u : p0.bt, bt1 = (p1.ws && p1.mixed && sb < 2) ? 0u : p1.bt;
         const float sgn = (sb & 1) ? -1.0f : 1.0f;
 #ifndef SW_NOSLOW
-        if (bt0 == bt1 && bt0 != 2)
+        if (__builtin_expect(bt0 == bt1 && bt0 != 2, 1))
 #endif
         {
           f2 t[18];
@@ -368,7 +368,20 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
           for (int k = 0; k < 9; k++) { tail[8 - k] = vmul(t[k], FC.swin[bt0][26 - k]); tail[9 + k] = vmul(t[k], FC.swin[bt0][27 + k]); }
         }
 #ifndef SW_NOSLOW
-        else {                                                      /* short block or different block types: one channel at a time */
+#ifndef SW_NO_PSHORT
+        else if (bt0 == bt1) {                                      /* short windows in both channels: three 12-point IMDCTs, packed */
+          f2 raw[36];
+          imdct_short<f2>(in, raw);
+          #pragma unroll
+          for (int ss = 0; ss < 18; ss++) {
+            f2 y = vadd(raw[ss], tail[ss]);
+            if (ss & 1) y = vmul(y, sgn);
+            blk[ss * SW_PITCH + sb] = y;
+            tail[ss] = raw[18 + ss];
+          }
+        }
+#endif
+        else {                                                      /* different block types in the two channels: one channel at a time */
           float *blkf = reinterpret_cast<float *>(blk);
           #pragma unroll 1
           for (int c = 0; c < 2; c++) {
@@ -386,7 +399,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
               }
             } else {
               float raw[36];
-              imdct_short(v, raw);
+              imdct_short<float>(v, raw);
               #pragma unroll
               for (int i = 0; i < 18; i++) { xo[i] = raw[i]; to[i] = raw[18 + i]; }
             }
