@@ -30,6 +30,10 @@ extern "C" {
 #define P3_FRAME_NODATA 2u   /* main_data_begin exceeds the reservoir (pdmp3.c:1101): silence   */
 #define P3_FRAME_BAD    4u   /* side info fails validation: silence               */
 #define P3_FRAME_WARMUP 8u   /* decoded for filter state only (shard halo), no PCM emitted     */
+#define P3_FRAME_ISO    16u  /* ISO 11172-3 semantics where the reference deviates: count1 table B
+                                decoded as the 4-bit code it is, MS stereo up to max(count1), intensity positions from the
+                                RIGHT channel's scalefactors with the ratio multiply in short blocks too, an empty part
+                                has count1 = 0.  Off (default) = bit-compatible with pdmp3.c.                          */
 
 typedef struct {             /* 32 bytes, one per MP3 frame */
   uint64_t main_off;         /* byte offset of this frame's main data inside the raw stream     */
@@ -84,6 +88,7 @@ typedef struct {
   uint32_t warmup_frames;    /* first N frames flagged WARMUP (no PCM slot)                      */
   uint32_t hop_only;         /* 1: only the sequential header hop runs on the host; the side info (Read_Audio_L3,
                                 pdmp3.c:1129-1200) is parsed ON THE DEVICE by k_sideinfo when the batch is staged */
+  uint32_t iso;              /* 1: flag every frame P3_FRAME_ISO (ISO-correct decoding instead of the reference's quirks) */
 } p3_parse_opts;
 
 typedef struct {

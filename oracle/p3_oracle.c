@@ -30,13 +30,14 @@ static inline unsigned rd_bit(rd_t *r) { unsigned b = (r->d[r->pos >> 3] >> (7 -
 static inline unsigned rd_bits(rd_t *r, unsigned n) { unsigned v = 0; while (n--) v = (v << 1) | rd_bit(r); return v; }
 
 /* ---- Huffman word: bit-serial match against the canonical code list (pdmp3.c:1593-1643) ---- */
-static void huff_word(rd_t *r, const p3_tables *T, unsigned table, int *x, int *y, int *v, int *w)
+static void huff_word(rd_t *r, const p3_tables *T, unsigned table, int iso, int *x, int *y, int *v, int *w)
 {
   int book = T->table_book[table];
   *x = *y = *v = *w = 0;
   if (book < 0) return;                                   /* empty tables 0/4/14: zeros, no bits (1599-1602) */
   int leaf = -1;
-  if (table == 33) leaf = 0x03;                           /* Q1: table B is mis-wired to a leaf: no code bits, value 0011 */
+  if (table == 33 && !iso) leaf = 0x03;                   /* Q1: table B is mis-wired to a leaf: no code bits, value 0011 */
+  else if (table == 33) leaf = (int)(~rd_bits(r, 4) & 15u);   /* ISO mode: count1 table B is a plain 4-bit code, value = ~code (ISO 11172-3 table B.7) */
   else {
     const p3_hcode *c; int n = p3_book_codes(book, &c);
     unsigned code = 0, len = 0;
@@ -96,7 +97,8 @@ static void read_huffman(rd_t *r, const p3_tables *T, ostate *S, const p3_frame 
                          unsigned gr, unsigned ch, uint64_t part2_start, float is[576])
 {
   unsigned p23l = P3_GC_P23L(*g);
-  if (p23l == 0) { memset(is, 0, 576 * sizeof(float)); return; }      /* count1 stays stale (Q6) */
+  const int iso = (fr->flags & P3_FRAME_ISO) != 0;
+  if (p23l == 0) { memset(is, 0, 576 * sizeof(float)); if (iso) S->count1[gr][ch] = 0; return; }      /* reference: count1 stays stale (Q6) */
   uint64_t bit_pos_end = part2_start + p23l - 1;
   unsigned r1s, r2s;
   if (P3_GC_WINSW(*g) && P3_GC_BTYPE(*g) == 2) { r1s = 36; r2s = 576; }
@@ -105,12 +107,12 @@ static void read_huffman(rd_t *r, const p3_tables *T, ostate *S, const p3_frame 
   int x, y, v, w;
   for (is_pos = 0; is_pos < bv2; is_pos++) {
     unsigned t = is_pos < r1s ? P3_GC_TSEL(*g, 0) : is_pos < r2s ? P3_GC_TSEL(*g, 1) : P3_GC_TSEL(*g, 2);
-    huff_word(r, T, t, &x, &y, &v, &w);
+    huff_word(r, T, t, iso, &x, &y, &v, &w);
     is[is_pos++] = (float)x; is[is_pos] = (float)y;
   }
   unsigned tq = 32 + P3_GC_C1TAB(*g);
   for (is_pos = bv2; is_pos <= 572 && r->pos <= bit_pos_end; is_pos++) {
-    huff_word(r, T, tq, &x, &y, &v, &w);
+    huff_word(r, T, tq, iso, &x, &y, &v, &w);
     is[is_pos++] = (float)v; if (is_pos >= 576) break;
     is[is_pos++] = (float)w; if (is_pos >= 576) break;
     is[is_pos++] = (float)x; if (is_pos >= 576) break;
@@ -171,6 +173,34 @@ static void stereo(const p3_tables *T, ostate *S, const p3_frame *fr, const p3_g
 {
   if (fr->mode != 1 || fr->mode_ext == 0) return;
   unsigned sf = fr->sfreq;
+  if (fr->flags & P3_FRAME_ISO) {
+    /* ISO mode (not the reference): a band starting at or above the right channel's count1 whose intensity position
+     * (RIGHT channel's scalefactor) is below 7 is intensity coded, short blocks with the ratio multiply as well; every
+     * other line below max(count1) takes MS if that is on.  Same band walk as the reference otherwise. */
+    unsigned c0 = S->count1[gr][0], c1r = S->count1[gr][1], msn = (fr->mode_ext & 2) ? (c0 > c1r ? c0 : c1r) : 0;
+    unsigned char done[576]; memset(done, 0, sizeof done);
+    if (fr->mode_ext & 1) {
+      int sh = P3_GC_WINSW(*g0) && P3_GC_BTYPE(*g0) == 2;
+      unsigned lim = sh ? (P3_GC_MIXED(*g0) ? 8 : 0) : 21, first = sh ? (P3_GC_MIXED(*g0) ? 3 : 0) : 12;
+      for (unsigned sfb = 0; sfb < lim; sfb++) if (T->sfb_l[sf][sfb] >= c1r) {
+        unsigned p = S->scf_l[gr][1][sfb]; if (p >= 7) continue;
+        for (unsigned i = T->sfb_l[sf][sfb]; i < T->sfb_l[sf][sfb + 1]; i++) { float x = l[i]; l[i] = T->is_l[p] * x; r[i] = T->is_r[p] * x; done[i] = 1; }
+      }
+      for (unsigned sfb = first; sfb < 12; sfb++) if (3u * T->sfb_s[sf][sfb] >= c1r) {
+        unsigned wl = T->sfb_s[sf][sfb + 1] - T->sfb_s[sf][sfb];
+        for (unsigned win = 0; win < 3; win++) {
+          unsigned p = S->scf_s[gr][1][sfb][win]; if (p >= 7) continue;
+          for (unsigned i = 3 * T->sfb_s[sf][sfb] + wl * win, e = i + wl; i < e; i++) { float x = l[i]; l[i] = T->is_l[p] * x; r[i] = T->is_r[p] * x; done[i] = 1; }
+        }
+      }
+    }
+    for (unsigned i = 0; i < msn && i < 576; i++) if (!done[i]) {
+      float a = l[i] + r[i], b = l[i] - r[i];
+      l[i] = (float)(a * 0.70710678118654752440);
+      r[i] = (float)(b * 0.70710678118654752440);
+    }
+    return;
+  }
   if (fr->mode_ext & 2) {
     unsigned n = S->count1[gr][0] > S->count1[gr][1] ? S->count1[gr][1] : S->count1[gr][0];   /* min, sic (1920) */
     for (unsigned i = 0; i < n && i < 576; i++) {

@@ -30,7 +30,7 @@ class P3ParseState(C.Structure):
 
 
 class P3ParseOpts(C.Structure):
-    _fields_ = [("max_frames", C.c_int64), ("lookahead", C.c_uint32), ("nthreads", C.c_int32), ("warmup_frames", C.c_uint32), ("hop_only", C.c_uint32)]
+    _fields_ = [("max_frames", C.c_int64), ("lookahead", C.c_uint32), ("nthreads", C.c_int32), ("warmup_frames", C.c_uint32), ("hop_only", C.c_uint32), ("iso", C.c_uint32)]
 
 
 class P3Parsed(C.Structure):
@@ -105,11 +105,11 @@ def _check(rc, what):
 class Parsed:
     """Owns a p3_parsed (host descriptors of one batch)."""
 
-    def __init__(self, stream, lookahead=0, max_frames=0, warmup=0, nthreads=0, state=None, hop_only=False):
+    def __init__(self, stream, lookahead=0, max_frames=0, warmup=0, nthreads=0, state=None, hop_only=False, iso=False):
         self.stream = np.ascontiguousarray(stream, dtype=np.uint8)
         self.c = P3Parsed()
         self.state = state if state is not None else P3ParseState(0, 0, 0, -1, -1)
-        o = P3ParseOpts(max_frames, lookahead, nthreads, warmup, 1 if hop_only else 0)
+        o = P3ParseOpts(max_frames, lookahead, nthreads, warmup, 1 if hop_only else 0, 1 if iso else 0)   # iso: P3_FRAME_ISO on every frame
         _check(lib().p3_parse(self.stream.ctypes.data, len(self.stream), C.byref(o), C.byref(self.state), C.byref(self.c)), "p3_parse")
 
     n_frames = property(lambda s: s.c.n_frames)

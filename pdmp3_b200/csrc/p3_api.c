@@ -42,7 +42,7 @@ struct pdmp3_handle {
   size_t pend_pos, pend_end;                        /* undelivered PCM bytes of the queue: [pend_pos,pend_end) */
   int in_pinned;
   p3_frame *dfr[3]; p3_gc *dgc[3]; int dnext;       /* page-locked descriptor arrays, rotated over the in-flight batches */
-  p3_ctx *ctx; int device; int ctx_failed; int mode; int host_sideinfo;
+  p3_ctx *ctx; int device; int ctx_failed; int mode; int host_sideinfo; int iso;
   p3_parse_state ps;
   int new_header;                                   /* 0 none yet, 1 seen, -1 reported (pdmp3.c:1318,2470,2531) */
   int nch, sfreq;
@@ -62,6 +62,7 @@ pdmp3_handle *pdmp3_new(const char *decoder, int *error)
     if ((p = strstr(decoder, "device="))) id->device = atoi(p + 7);
     if (strstr(decoder, "mode=exact")) id->mode = P3_MODE_EXACT;   /* bit-identical PCM; default is FAST (<= 1 LSB) */
     if (strstr(decoder, "sideinfo=host")) id->host_sideinfo = 1;   /* parse the side info on the host instead of on the device */
+    if (strstr(decoder, "iso")) id->iso = 1;                       /* ISO 11172-3 semantics instead of the reference's quirks (P3_FRAME_ISO) */
   }
   if (id->cap > (1u << 20)) { id->in = (unsigned char *)p3_host_alloc(id->cap); id->in_pinned = id->in != NULL; }   /* page-locked: full-speed H2D */
   if (!id->in) id->in = (unsigned char *)malloc(id->cap);
@@ -163,7 +164,7 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
     int direct = outsize >= P3_API_DIRECT * fbytes;
     int64_t want = direct ? (int64_t)(outsize / fbytes) : P3_API_AHEAD;
     if (want > P3_API_CHUNK) want = P3_API_CHUNK;
-    p3_parse_opts po = {want, 2 * 576, want >= 8192 ? 4 : 1, 0, id->host_sideinfo ? 0u : 1u};   /* side info: parsed on the device */
+    p3_parse_opts po = {want, 2 * 576, want >= 8192 ? 4 : 1, 0, id->host_sideinfo ? 0u : 1u, (uint32_t)id->iso};   /* side info: parsed on the device */
     p3_parse_state ps = id->ps;
     p3_parsed pb;
     p3_frame *dfr = NULL; p3_gc *dgc = NULL;

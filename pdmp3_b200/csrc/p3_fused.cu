@@ -30,6 +30,7 @@ struct p3_fconst {
   float pretab[24];
 };
 __constant__ p3_fconst FC;
+static int p3_synthw_check_consts(const float *cs, const float *ca);   /* p3_synthw.cuh: its immediates against the table */
 
 extern "C" int p3_fused_upload_consts(const p3_tables *T, const float *dct4)
 {
@@ -41,6 +42,7 @@ extern "C" int p3_fused_upload_consts(const p3_tables *T, const float *dct4)
   memcpy(h.cs, T->cs, 32); memcpy(h.ca, T->ca, 32); memcpy(h.is_l, T->is_l, 32); memcpy(h.is_r, T->is_r, 32);
   memcpy(h.t1h, T->t1h, sizeof h.t1h); memcpy(h.t2, T->t2, sizeof h.t2);
   for (int i = 0; i < 24; i++) h.pretab[i] = (float)T->pretab[i];
+  { int rc = p3_synthw_check_consts(h.cs, h.ca); if (rc) return rc; }
   return (int)cudaMemcpyToSymbol(FC, &h, sizeof h);
 }
 
@@ -178,7 +180,9 @@ __device__ __forceinline__ void sf_stageAB(const synth_sm &S, int slot, const p3
         const int16_t *is0 = isbuf[2 * gr], *is1 = isbuf[2 * gr + 1];
         const float *sc0 = s_scale[2 * gr], *sc1 = s_scale[2 * gr + 1];
         const uint32_t cl = (uint32_t)p0.c1, c1r = (uint32_t)p1.c1;
-        const uint32_t msn = (st_on && (fr.mode_ext & 2)) ? (cl > c1r ? c1r : cl) : 0u;     /* min(count1), sic (pdmp3.c:1920) */
+        const bool iso = (fr.flags & P3_FRAME_ISO) != 0;        /* ISO semantics, see k_requant */
+        const uint32_t isc = iso ? 1u : 0u;
+        const uint32_t msn = (st_on && (fr.mode_ext & 2)) ? (iso ? (cl > c1r ? cl : c1r) : (cl > c1r ? c1r : cl)) : 0u;     /* reference: min(count1), sic (pdmp3.c:1920) */
         const uint32_t first_short0 = p0.first_short;
         const bool sh0 = first_short0 < 576;
         #pragma unroll
@@ -194,25 +198,29 @@ __device__ __forceinline__ void sf_stageAB(const synth_sm &S, int slot, const p3
             if (d >= p1.first_short) { const uint32_t s = s_reo[d], sw = s_sfbw_s[s]; r = fq_requant(T->pow43, is1[s], sc1[3 * (sw & 15u) + (sw >> 4)]); }
             else r = fq_requant(T->pow43, is1[d], sc1[s_sfb_l[d]]);
           }
-          if (d < msn) {
-            /* float sum times a double constant, rounded once to float (pdmp3.c:168,1923-1926) */
-            const float a = __fadd_rn(l, r), b = __fsub_rn(l, r);
-            l = __double2float_rn(__dmul_rn((double)a, 0.70710678118654752440));
-            r = __double2float_rn(__dmul_rn((double)b, 0.70710678118654752440));
-          } else if (is_on) {
+          bool is_done = false;
+          if (is_on && (iso || d >= msn)) {
             if (d >= first_short0) {
               /* short-block intensity (pdmp3.c:2190-2220) in reordered position; Q4: assignment through an `unsigned` */
               const uint32_t sw = s_sfbw_s[d], sfb = sw & 15u, win = sw >> 4;
-              if (sfb < 12 && 3u * T->sfb_s[fr.sfreq][sfb] >= c1r && scf4[2 * gr][P3_SCF_S_OFF + 3 * sfb + win] != 7) {
-                const float x = (float)(unsigned)(long long)l; l = x; r = x;
+              if (sfb < 12 && 3u * T->sfb_s[fr.sfreq][sfb] >= c1r) {
+                const uint32_t pp = scf4[2 * gr + isc][P3_SCF_S_OFF + 3 * sfb + win];
+                if (iso) { if (pp < 7) { const float x = l; l = __fmul_rn(FC.is_l[pp], x); r = __fmul_rn(FC.is_r[pp], x); is_done = true; } }
+                else if (pp != 7) { const float x = (float)(unsigned)(long long)l; l = x; r = x; }
               }
             } else {
               const uint32_t sfb = s_sfb_l[d], lim = sh0 ? 8u : 21u;                     /* mixed: long sfb 0..7 only (pdmp3.c:1944) */
               if (sfb < lim && T->sfb_l[fr.sfreq][sfb] >= c1r) {
-                const uint32_t pp = scf4[2 * gr][sfb];                                   /* channel-0 scalefactor, sic (pdmp3.c:2163) */
-                if (pp != 7) { const float x = l; l = __fmul_rn(FC.is_l[pp & 7], x); r = __fmul_rn(FC.is_r[pp & 7], x); }
+                const uint32_t pp = scf4[2 * gr + isc][sfb];                             /* reference: channel-0 scalefactor, sic (pdmp3.c:2163) */
+                if (iso ? pp < 7 : pp != 7) { const float x = l; l = __fmul_rn(FC.is_l[pp & 7], x); r = __fmul_rn(FC.is_r[pp & 7], x); is_done = true; }
               }
             }
+          }
+          if (d < msn && !is_done) {
+            /* float sum times a double constant, rounded once to float (pdmp3.c:168,1923-1926) */
+            const float a = __fadd_rn(l, r), b = __fsub_rn(l, r);
+            l = __double2float_rn(__dmul_rn((double)a, 0.70710678118654752440));
+            r = __double2float_rn(__dmul_rn((double)b, 0.70710678118654752440));
           }
           xs[2 * gr][d] = l; xs[2 * gr + 1][d] = r;
         }

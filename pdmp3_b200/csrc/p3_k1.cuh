@@ -165,11 +165,13 @@ __device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw /* the CTA's
       /* count1 quads (pdmp3.c:2091-2103) */
       uint32_t is_pos = bv2;
       const bool tabB = P3_GC_C1TAB(g);                  /* reference quirk Q1: table B = leaf 0011, no code bits */
+      const bool isoB = tabB && (fr.flags & P3_FRAME_ISO); /* ISO mode: table B is the 4-bit code it is, value = ~code */
       const uint32_t qbase = T->book_base[T->table_book[32]], qbits = T->book_pbits[T->table_book[32]];
       pos = bb.pos();
       while (is_pos <= 572 && pos <= bit_pos_end) {
         uint32_t w = bb.peek(), used = 0, leaf = 3;
         if (!tabB) { uint32_t e = lut[qbase + (w >> (32 - qbits))]; used = (e >> 8) & 31; leaf = e & 15; w <<= used; }
+        else if (isoB) { leaf = (~w) >> 28; used = 4; w <<= 4; }
         int v = (leaf >> 3) & 1, ww = (leaf >> 2) & 1, x = (leaf >> 1) & 1, y = leaf & 1;
         if (v) { if (w >> 31) v = -1; w <<= 1; used++; }
         if (ww) { if (w >> 31) ww = -1; w <<= 1; used++; }

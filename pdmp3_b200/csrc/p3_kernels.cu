@@ -226,35 +226,45 @@ k_requant(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, co
   if (nch == 2 && fr.mode == 1 && fr.mode_ext != 0) {
     const p3_gc g0 = gcs[4 * f + 2 * gr];
     const uint32_t c0 = (uint32_t)sc1[0], c1r = (uint32_t)sc1[1];
-    const uint32_t msn = (fr.mode_ext & 2) ? (c0 > c1r ? c1r : c0) : 0u;              /* min(count1), sic (pdmp3.c:1920) */
+    /* ISO mode (P3_FRAME_ISO): MS up to max(count1); intensity positions from the RIGHT channel's scalefactors, position 7
+     * (or above) = not intensity coded, such a band gets MS if that is on; short blocks multiply by the ratios too. */
+    const bool iso = (fr.flags & P3_FRAME_ISO) != 0;
+    const uint32_t isc = iso ? 1u : 0u;
+    const uint32_t msn = (fr.mode_ext & 2) ? (iso ? (c0 > c1r ? c0 : c1r) : (c0 > c1r ? c1r : c0)) : 0u;   /* reference: min(count1), sic (pdmp3.c:1920) */
     const bool is_on = fr.mode_ext & 1;
     const bool sh0 = P3_GC_WINSW(g0) && P3_GC_BTYPE(g0) == 2;
     const uint32_t first_short0 = sh0 ? (P3_GC_MIXED(g0) ? 36u : 0u) : 576u;
     for (uint32_t i = threadIdx.x; i < 576; i += K2_THREADS) {
       float l = xs[0][i], r = xs[1][i];
-      if (i < msn) {
-        /* float sum times a double constant, rounded once to float (pdmp3.c:168,1923-1926) */
-        float a = __fadd_rn(l, r), b = __fsub_rn(l, r);
-        l = __double2float_rn(__dmul_rn((double)a, 0.70710678118654752440));
-        r = __double2float_rn(__dmul_rn((double)b, 0.70710678118654752440));
-      } else if (is_on) {
+      bool is_done = false;
+      if (is_on && (iso || i >= msn)) {
         if (i >= first_short0) {
           /* short-block intensity (pdmp3.c:2190-2220) in REORDERED position: band sfb occupies
            * [3*s[sfb], 3*s[sfb+1]) and window `win` the win-th third of it (2201-2202) */
           const uint32_t sw = T->line_sfbw_s[sf][i], sfb = sw & 15u, win = sw >> 4;
-          if (sfb < 12 && 3u * T->sfb_s[sf][sfb] >= c1r && sscf[0][P3_SCF_S_OFF + 3 * sfb + win] != 7) {
-            /* Q4: assignment through an `unsigned` (pdmp3.c:2191,2212-2213) */
-            float x = (float)(unsigned)(long long)l;
-            l = x; r = x;
+          if (sfb < 12 && 3u * T->sfb_s[sf][sfb] >= c1r) {
+            const uint32_t p = sscf[isc][P3_SCF_S_OFF + 3 * sfb + win];
+            if (iso) { if (p < 7) { const float x = l; l = __fmul_rn(T->is_l[p], x); r = __fmul_rn(T->is_r[p], x); is_done = true; } }
+            else if (p != 7) {
+              /* Q4: assignment through an `unsigned` (pdmp3.c:2191,2212-2213) */
+              float x = (float)(unsigned)(long long)l;
+              l = x; r = x;
+            }
           }
         } else {
           const uint32_t sfb = T->line_sfb_l[sf][i];
           const uint32_t lim = sh0 ? 8u : 21u;                                      /* mixed: long sfb 0..7 only (pdmp3.c:1944) */
           if (sfb < lim && T->sfb_l[sf][sfb] >= c1r) {
-            const uint32_t p = sscf[0][sfb];                                        /* channel-0 scalefactor, sic (pdmp3.c:2163) */
-            if (p != 7) { float x = l; l = __fmul_rn(T->is_l[p & 7], x); r = __fmul_rn(T->is_r[p & 7], x); }
+            const uint32_t p = sscf[isc][sfb];                                      /* reference: channel-0 scalefactor, sic (pdmp3.c:2163) */
+            if (iso ? p < 7 : p != 7) { float x = l; l = __fmul_rn(T->is_l[p & 7], x); r = __fmul_rn(T->is_r[p & 7], x); is_done = true; }
           }
         }
+      }
+      if (i < msn && !is_done) {
+        /* float sum times a double constant, rounded once to float (pdmp3.c:168,1923-1926) */
+        float a = __fadd_rn(l, r), b = __fsub_rn(l, r);
+        l = __double2float_rn(__dmul_rn((double)a, 0.70710678118654752440));
+        r = __double2float_rn(__dmul_rn((double)b, 0.70710678118654752440));
       }
       xs[0][i] = l; xs[1][i] = r;
     }
@@ -527,7 +537,7 @@ k_sideinfo(const uint8_t *__restrict__ raw, p3_frame *__restrict__ frames, p3_gc
 extern "C" __global__ void __launch_bounds__(1024)
 k_q6_chain(const p3_frame *__restrict__ frames, p3_gc *__restrict__ gcs, int64_t n_frames, const int *__restrict__ any_empty)
 {
-  if (!*any_empty) return;
+  if (!*any_empty || (frames[0].flags & P3_FRAME_ISO)) return;      /* ISO mode: an empty part has count1 = 0, nothing to chain */
   __shared__ int64_t s_last[1024][4];
   const int t = threadIdx.x;
   const int64_t per = (n_frames + 1023) / 1024, lo = (int64_t)t * per, hi = min(lo + per, n_frames);

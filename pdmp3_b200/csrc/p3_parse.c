@@ -111,7 +111,7 @@ int p3_parse(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_parse_s
 int p3_parse_into(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_parse_state *st, p3_parsed *out,
                   p3_frame *frames_buf, p3_gc *gcs_buf, int64_t buf_cap)
 {
-  p3_parse_opts od = {0, 0, 0, 0, 0};
+  p3_parse_opts od = {0, 0, 0, 0, 0, 0};
   p3_parse_state sd = {0, 0, 0, -1, -1};
   if (!data || !out) return P3_EINVAL;
   if (!o) o = &od;
@@ -151,7 +151,7 @@ int p3_parse_into(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_pa
     f->main_pos = st->main_pos;
     f->nch = (uint8_t)nch; f->mode = (uint8_t)mode; f->mode_ext = (uint8_t)mext; f->sfreq = (uint8_t)sf;
     f->scfsi = 0; f->bitrate_kbps = k_bitrate[br];
-    f->flags = 0;
+    f->flags = o->iso ? P3_FRAME_ISO : 0;
     /* reservoir rule of Get_Main_Data (pdmp3.c:1101-1120) */
     if (f->main_begin > st->top) { f->flags |= P3_FRAME_NODATA; st->top += f->main_size; }
     else st->top = (uint32_t)f->main_begin + f->main_size;
@@ -187,8 +187,9 @@ int p3_parse_into(const uint8_t *data, uint64_t n, const p3_parse_opts *o, p3_pa
     for (int t = 0; t < nt; t++) { if (th[t]) pthread_join(th[t], NULL); any_empty |= jb[t].any_empty; }
   }
   /* Q6 (pdmp3.c:2057-2061): a zero-length part leaves count1 of its [gr][ch] slot stale.  Record how
-   * many frames back the slot was last written so the device can fetch that count1 (w3 = 0: own). */
-  if (any_empty) {
+   * many frames back the slot was last written so the device can fetch that count1 (w3 = 0: own).
+   * ISO mode: an empty part simply has count1 = 0 (w3 stays 0). */
+  if (any_empty && !o->iso) {
     int64_t last[4] = {-1, -1, -1, -1};
     for (int64_t f = 0; f < nf; f++) for (unsigned k = 0; k < 4; k++) {
       if ((k & 1) >= fr[f].nch) continue;

@@ -93,6 +93,25 @@ __device__ __forceinline__ uint32_t sw_pcm2(f2 sum)
   return __vmaxs2(v, 0x80018001u);
 }
 
+/* One side of an antialias butterfly, in place and under a predicate: x = x*cs + nb*ca with the product nb*ca rounded
+ * and the other one kept exact inside the fma (what ptxas makes of the separately written products anyway).  The
+ * coefficients are immediates (cs/ca of pdmp3.c:573-574; p3_fused_upload_consts checks them against the table). */
+#define SW_CS_LIST {0.857493f, 0.881742f, 0.949629f, 0.983315f, 0.995518f, 0.999161f, 0.999899f, 0.999993f}
+#define SW_CA_LIST {-0.514496f, -0.471732f, -0.313377f, -0.181913f, -0.094574f, -0.040966f, -0.014199f, -0.003700f}
+__device__ __forceinline__ float sw_cs(int i) { constexpr float t[8] = SW_CS_LIST; return t[i]; }
+__device__ __forceinline__ float sw_ca(int i) { constexpr float t[8] = SW_CA_LIST; return t[i]; }
+/* x = c - a under a predicate, as fma(a, -1, c) */
+__device__ __forceinline__ void sw_fnma_if(f2 &x, f2 a, f2 c, bool on)
+{
+  asm("{\n .reg .pred p;\n .reg .b64 m;\n setp.ne.s32 p, %3, 0;\n mov.b64 m, {0fBF800000, 0fBF800000};\n @p fma.rn.f32x2 %0, %1, m, %2;\n}"
+      : "+l"(x.v) : "l"(a.v), "l"(c.v), "r"((int)on));
+}
+__device__ __forceinline__ void sw_aa(f2 &x, f2 nb, float cs, float ca, bool on)
+{
+  asm("{\n .reg .pred p;\n .reg .b64 t, c;\n setp.ne.s32 p, %2, 0;\n mov.b64 c, {%4, %4};\n mul.rn.f32x2 t, %1, c;\n mov.b64 c, {%3, %3};\n @p fma.rn.f32x2 %0, %0, c, t;\n}"
+      : "+l"(x.v) : "l"(nb.v), "r"((int)on), "f"(cs), "f"(ca));
+}
+
 extern "C" __global__ void __launch_bounds__(SW_WPB * 32, SW_MINB)
 k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
              int64_t f_first, int64_t f_end, int frames_per_warp,
@@ -123,6 +142,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   /* ---- per-lane constants ---- */
   float ce[8], co[8]; int ia, ib;
   synth_window_coeffs(T, ce, co, ia, ib);
+  const uint32_t pretab_l = (lane >= 11 && lane < 21) ? (0xbfa55u >> (2 * (lane - 11))) & 3u : 0u;   /* pretab[sfb = lane] (pdmp3.c:2123) */
   uint32_t sfbp[3] = {0, 0, 0};                            /* long-block sfb of this subband's 18 lines, 5 bits each */
   #pragma unroll
   for (int m = 0; m < 18; m++) sfbp[m / 6] |= (uint32_t)T->line_sfb_l[sf][18 * sb + m] << (5 * (m % 6));
@@ -185,7 +205,16 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       /* ---- band scales fl(t1*t2) (pdmp3.c:2127-2128, 2144-2146); same table layout as k_synth_fast: long blocks
        *      index = sfb (0..21), short 3*sfb+win (0..38), mixed: long bands 0..7 sit in the unused short slots 0..7.
        *      The scalefactor byte of short band 3*sfb+win is byte 24 + 3*sfb + win of the row. ---- */
-      #pragma unroll
+      if (__builtin_expect(p0.first_short == 576 && p1.first_short == 576, 1)) {
+        /* long blocks in both channels (the usual case): lane = sfb for both channels, one pass, one 8-byte store */
+        if (lane < 22) {
+          const uint32_t s0 = lane < 21 ? scf2[0][lane] : 0u, s1 = lane < 21 ? scf2[1][lane] : 0u;
+          const float v0 = __fmul_rn(s_t1h[p0.mult * (s0 + p0.pre * pretab_l)], s_t2[p0.gg + P3_T2_BIAS]);
+          const float v1 = __fmul_rn(s_t1h[p1.mult * (s1 + p1.pre * pretab_l)], s_t2[p1.gg + P3_T2_BIAS]);
+          *reinterpret_cast<float2 *>(&W->scale[lane][0]) = make_float2(v0, v1);
+        }
+      } else
+      #pragma unroll 1
       for (int k = 0; k < 3; k++) {
         const uint32_t e = lane + 32 * k;
         if (e < 80) {
@@ -250,8 +279,13 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
 
       /* ---- B: stereo (pdmp3.c:1916-1971) ---- */
       const uint32_t c1r = (uint32_t)p1.c1;
-      const uint32_t msn = (st_on && (mode_ext & 2)) ? min((uint32_t)p0.c1, c1r) : 0u;      /* min(count1), sic (pdmp3.c:1920) */
+      const bool iso = ((frq.z >> 8) & P3_FRAME_ISO) != 0;     /* ISO semantics of MS / intensity stereo, see k_requant */
+      const uint32_t msn_all = (st_on && (mode_ext & 2)) ? (iso ? max((uint32_t)p0.c1, c1r) : min((uint32_t)p0.c1, c1r)) : 0u;   /* reference: min(count1), sic (pdmp3.c:1920) */
+      /* ISO mode with intensity stereo on: bands starting at or above the right channel's count1 may be intensity coded
+       * instead, so only the lines below it take MS here; the line-by-line pass below decides the rest */
+      const uint32_t msn = (iso && is_on) ? min(msn_all, c1r) : msn_all;
       if (18 * sb < msn) {
+        const int32_t msrem = (int32_t)msn - 18 * (int32_t)sb;     /* lines of this subband below msn */
         /* the reference multiplies the float sum by the DOUBLE constant 1/sqrt 2 and rounds once to float (pdmp3.c:168,
          * 1923-1926).  Same result from packed fp32: with C = Ch + Cl (two floats), p = fl(a*Ch), e = a*Ch - p (exact, one
          * fma), t = fl(a*Cl + e), result = fl(p + t).  It can differ from the double-precision product only when that
@@ -264,8 +298,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
           const f2 p = vmul(ad, Ch);
           const f2 ne = vfma(ad, -Ch, p);                          /* -(a*Ch - p), exact */
           const f2 nt = vfma(ad, -Cl, ne);                         /* -(a*Cl + e) */
-          const f2 ms = vfma(nt, -1.0f, p);                        /* p + t; written as an fma so that nothing can be contracted into it */
-          if (18 * sb + m < msn) in[m] = ms;
+          sw_fnma_if(in[m], nt, p, m < msrem);                     /* p + t, written as an fma so that nothing can be contracted into it; in place, lines below msn only */
         }
       }
 #ifndef SW_NOSLOW
@@ -276,6 +309,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       if (is_on) {                                            /* first line of the last band it can touch: long sfb 20, long sfb 7 (mixed), short sfb 11 (x3) */
         const uint32_t ll = T->sfb_l[sf][first_short0 == 576 ? 20 : 7], ls = 3u * T->sfb_s[sf][11];
         is_any = (first_short0 != 0 && ll >= c1r) || (first_short0 != 576 && ls >= c1r);
+        if (iso && msn_all > msn) is_any = true;             /* MS lines at or above the right channel's count1 are done below as well */
       }
       if (__builtin_expect(is_any, 0)) {                                           /* line by line through the scratch block, rare */
         f2 *scr = blk;                                           /* [576] */
@@ -284,21 +318,30 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
         __syncwarp();
         const bool sh0 = first_short0 < 576;
         #pragma unroll 1
+        const uint32_t isc = iso ? 1u : 0u;
         for (uint32_t d = (c1r & ~31u) + lane; d < 576; d += 32) {   /* a line below count1 is in a band that starts below it */
           if (d < msn) continue;
           float l = f2_x(scr[d]), r = f2_y(scr[d]);
+          bool is_done = false;
           if (d >= first_short0) {
             /* short-block intensity (pdmp3.c:2190-2220) in reordered position; Q4: assignment through an `unsigned` */
             const uint32_t sw = s_sfbw[d], sfb = sw & 15u, win = sw >> 4;
-            if (sfb < 12 && 3u * T->sfb_s[sf][sfb] >= c1r && scf2[0][P3_SCF_S_OFF + 3 * sfb + win] != 7) {
-              const float x = (float)(unsigned)(long long)l; l = x; r = x;
+            if (sfb < 12 && 3u * T->sfb_s[sf][sfb] >= c1r) {
+              const uint32_t pp = scf2[isc][P3_SCF_S_OFF + 3 * sfb + win];
+              if (iso) { if (pp < 7) { const float x = l; l = __fmul_rn(FC.is_l[pp], x); r = __fmul_rn(FC.is_r[pp], x); is_done = true; } }
+              else if (pp != 7) { const float x = (float)(unsigned)(long long)l; l = x; r = x; }
             }
           } else {
             const uint32_t sfb = T->line_sfb_l[sf][d], lim = sh0 ? 8u : 21u;                /* mixed: long sfb 0..7 only (pdmp3.c:1944) */
             if (sfb < lim && T->sfb_l[sf][sfb] >= c1r) {
-              const uint32_t pp = scf2[0][sfb];                                             /* channel-0 scalefactor, sic (pdmp3.c:2163) */
-              if (pp != 7) { const float x = l; l = __fmul_rn(FC.is_l[pp & 7], x); r = __fmul_rn(FC.is_r[pp & 7], x); }
+              const uint32_t pp = scf2[isc][sfb];                                           /* reference: channel-0 scalefactor, sic (pdmp3.c:2163) */
+              if (iso ? pp < 7 : pp != 7) { const float x = l; l = __fmul_rn(FC.is_l[pp & 7], x); r = __fmul_rn(FC.is_r[pp & 7], x); is_done = true; }
             }
+          }
+          if (d < msn_all && !is_done) {                         /* ISO mode only (msn_all == msn otherwise): MS for a line that is not intensity coded */
+            const float a = __fadd_rn(l, r), b = __fsub_rn(l, r);
+            l = __double2float_rn(__dmul_rn((double)a, 0.70710678118654752440));
+            r = __double2float_rn(__dmul_rn((double)b, 0.70710678118654752440));
           }
           scr[d] = f2_make(l, r);
         }
@@ -328,9 +371,8 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
           if (__builtin_expect(p0.sblim == p1.sblim, 1))
 #endif
           {
-            const f2 u = in[i], l = in[17 - i];
-            if (lo0) in[i] = vadd(vmul(u, FC.cs[i]), vmul(f2_make(bx, by), FC.ca[i]));           /* ub (pdmp3.c:1726) */
-            if (hi0) in[17 - i] = vsub(vmul(l, FC.cs[i]), vmul(f2_make(ax, ay), FC.ca[i]));      /* lb (pdmp3.c:1725) */
+            sw_aa(in[i], f2_make(bx, by), sw_cs(i), sw_ca(i), lo0);                              /* ub (pdmp3.c:1726) */
+            sw_aa(in[17 - i], f2_make(ax, ay), sw_cs(i), -sw_ca(i), hi0);                        /* lb (pdmp3.c:1725) */
           }
 #ifndef SW_NOSLOW
           else {
@@ -468,6 +510,13 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       st_out->xhist[0][age - 1][lane] = f2_x(v); st_out->xhist[1][age - 1][lane] = f2_y(v);
     }
   }
+}
+
+static int p3_synthw_check_consts(const float *cs, const float *ca)
+{
+  const float k_cs[8] = SW_CS_LIST, k_ca[8] = SW_CA_LIST;
+  for (int i = 0; i < 8; i++) if (cs[i] != k_cs[i] || ca[i] != k_ca[i]) return -1000 - i;
+  return 0;
 }
 
 extern "C" size_t p3_synthw_smem_bytes(void) { return SW_LUT_BYTES + SW_WPB * sizeof(sw_warp_sm); }

@@ -8,10 +8,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 class SynthCfg(C.Structure):
     _fields_ = [("seed", C.c_uint64)] + [(n, C.c_int32) for n in (
         "bitrate_index", "mode", "mode_ext", "sfreq", "blocks", "reservoir", "scalefacs", "gain",
-        "fill_pm", "crc", "count1_b_pm", "overrun_pm", "max_table", "garbage_pm")]
+        "fill_pm", "crc", "count1_b_pm", "overrun_pm", "max_table", "garbage_pm", "iso")]
 
 _DEF = dict(seed=1, bitrate_index=9, mode=0, mode_ext=0, sfreq=0, blocks=0, reservoir=1, scalefacs=1,
-            gain=172, fill_pm=850, crc=0, count1_b_pm=0, overrun_pm=0, max_table=31, garbage_pm=0)
+            gain=172, fill_pm=850, crc=0, count1_b_pm=0, overrun_pm=0, max_table=31, garbage_pm=0, iso=0)
 
 # the BASELINE.json configurations
 CONFIGS = {
@@ -92,7 +92,7 @@ class P3Gc(C.Structure):
 class P3ParseState(C.Structure):
     _fields_ = [("main_pos", C.c_uint64), ("top", C.c_uint32), ("pcm_index", C.c_uint32), ("nch", C.c_int32), ("sfreq", C.c_int32)]
 class P3ParseOpts(C.Structure):
-    _fields_ = [("max_frames", C.c_int64), ("lookahead", C.c_uint32), ("nthreads", C.c_int32), ("warmup_frames", C.c_uint32), ("hop_only", C.c_uint32)]
+    _fields_ = [("max_frames", C.c_int64), ("lookahead", C.c_uint32), ("nthreads", C.c_int32), ("warmup_frames", C.c_uint32), ("hop_only", C.c_uint32), ("iso", C.c_uint32)]
 class P3Parsed(C.Structure):
     _fields_ = [("n_frames", C.c_int64), ("frames", C.POINTER(P3Frame)), ("gcs", C.POINTER(P3Gc)),
                 ("consumed", C.c_uint64), ("n_pcm_frames", C.c_int64), ("external", C.c_int32), ("stop", C.c_int32),
@@ -117,11 +117,11 @@ def oracle_lib():
         _orc.p3o_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(OTaps), C.c_void_p]
     return _orc
 
-def parse(stream, lookahead=1152, max_frames=0, warmup=0, nthreads=1, lib=None):
+def parse(stream, lookahead=1152, max_frames=0, warmup=0, nthreads=1, lib=None, iso=False):
     """Run the host parser; returns (frames structured array, gcs uint32 [n,4,4], P3Parsed copy info)."""
     lib = lib or oracle_lib()
     stream = np.ascontiguousarray(stream, dtype=np.uint8)
-    o = P3ParseOpts(max_frames, lookahead, nthreads, warmup); st = P3ParseState(0, 0, 0, -1, -1); out = P3Parsed()
+    o = P3ParseOpts(max_frames, lookahead, nthreads, warmup, 0, 1 if iso else 0); st = P3ParseState(0, 0, 0, -1, -1); out = P3Parsed()
     rc = lib.p3_parse(stream.ctypes.data, len(stream), C.byref(o), C.byref(st), C.byref(out))
     assert rc == 0, rc
     n = out.n_frames
@@ -131,11 +131,11 @@ def parse(stream, lookahead=1152, max_frames=0, warmup=0, nthreads=1, lib=None):
     lib.p3_parsed_free(C.byref(out))
     return fr, gc, info
 
-def oracle_decode(stream, lookahead=1152, taps=True, warmup=0):
+def oracle_decode(stream, lookahead=1152, taps=True, warmup=0, iso=False):
     """Parse with the product parser, decode with the oracle restatement."""
     lib = oracle_lib()
     stream = np.ascontiguousarray(stream, dtype=np.uint8)
-    fr, gc, info = parse(stream, lookahead, warmup=warmup)
+    fr, gc, info = parse(stream, lookahead, warmup=warmup, iso=iso)
     n = info["n_frames"]; nch = int(fr["nch"][0]) if n else 2
     shapes = dict(is_huff=((n, 2, 2, 576), np.int16), count1=((n, 2, 2), np.int32), scf_l=((n, 2, 2, 21), np.uint8),
                   scf_s=((n, 2, 2, 12, 3), np.uint8), xr_req=((n, 2, 2, 576), np.float32), xr_reo=((n, 2, 2, 576), np.float32),

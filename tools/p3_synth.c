@@ -256,7 +256,7 @@ int64_t p3_synth(const p3_synth_cfg *cfg, int64_t n_frames, uint8_t *out, uint64
       }
     }
     /* G6: no intensity stereo when channel 0 of a granule is short */
-    if ((mode_ext & 1) && ((gi[0][0].bt == 2) || (gi[1][0].bt == 2))) mode_ext &= 2;
+    if (!cfg->iso && (mode_ext & 1) && ((gi[0][0].bt == 2) || (gi[1][0].bt == 2))) mode_ext &= 2;
     for (int ch = 0; ch < nch; ch++)
       if (gi[0][ch].bt != 2 && gi[1][ch].bt != 2 && cfg->scalefacs) scfsi[ch] = rndn(&rg, 4) == 0 ? rndn(&rg, 16) : 0;
     uint64_t frame_start_bit = w.pos;
@@ -273,6 +273,7 @@ int64_t p3_synth(const p3_synth_cfg *cfg, int64_t n_frames, uint8_t *out, uint64
         if (budget > room) budget = (unsigned)room;
       }
       if (budget > 4000) budget = 4000;
+      if (cfg->iso && rndn(&rg, 1000) < 30) budget = 0;       /* an empty part */
       int intensity = (mode_ext & 1) && cfg->mode == 1;
       /* side-info fields */
       g->gain = (unsigned)(cfg->gain + (int)rndn(&rg, 13) - 6);
@@ -300,7 +301,7 @@ int64_t p3_synth(const p3_synth_cfg *cfg, int64_t n_frames, uint8_t *out, uint64
       }
       unsigned c1 = 0; int mx = 0;
       if (budget == 0) { g->p23l = 0; g->bigv = 0; }        /* cannot happen with sane fill; kept for safety (violates G5) */
-      else encode_gc(&rg, cfg, &w, g, budget, gr, (unsigned)ch, scfsi[ch], intensity && ch == 0, sf,
+      else encode_gc(&rg, cfg, &w, g, budget, gr, (unsigned)ch, scfsi[ch], intensity && ch == (cfg->iso ? 1 : 0), sf,
                      gr == 0 ? scf0[ch] : NULL, is_out ? is_out + (((size_t)f * 2 + gr) * 2 + (size_t)ch) * 576 : NULL, &c1, &mx);
       if (mx > 1) {   /* keep the loudest line below ~0.3 of full scale so that clipping stays rare */
         int lim = 210 + (int)floor(4.0 * log2(0.30 / pow((double)mx, 4.0 / 3.0)));

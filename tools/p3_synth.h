@@ -21,6 +21,9 @@ typedef struct {
   int32_t overrun_pm;      /* per-mille of granules whose part2_3_length ends inside the last quad  */
   int32_t max_table;       /* highest big_values table number to use (e.g. 31; 15 = no linbits)    */
   int32_t garbage_pm;      /* per-mille of frames preceded by 1..40 junk bytes (resync test)       */
+  int32_t iso;             /* 1: stream for the ISO mode of the decoder (P3_FRAME_ISO), outside the reference's envelope:
+                              intensity stereo also with short blocks in channel 0 (G6 lifted), intensity positions <= 7 in
+                              the RIGHT channel's scalefactors, 3 % of the parts empty (part2_3_length = 0, G5 lifted)      */
 } p3_synth_cfg;
 
 /* Writes n_frames frames.  Returns bytes written or <0 if `cap` is too small.
