@@ -12,6 +12,8 @@
  * pdmp3_feed()+pdmp3_read() pair push a whole stream through the GPU in one batch.
  * `mode` = fast (default: fused kernel with fast transforms, PCM within 1 LSB of the reference) or
  * exact (direct-form transforms in the reference's summation order, PCM bit-identical).
+ * `iso` = decode by ISO 11172-3 where pdmp3.c deviates from it (count1 table B, MS stereo range, intensity
+ * stereo positions, empty parts: P3_FRAME_ISO in pdmp3_b200.h); without it the output is that of pdmp3.c.
  */
 #ifndef PDMP3_H
 #define PDMP3_H
