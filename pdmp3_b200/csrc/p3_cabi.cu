@@ -14,6 +14,8 @@ extern "C" size_t p3_synthw_smem_bytes(void);
 extern "C" int p3_synthw_warps_per_cta(void);
 extern "C" __global__ void k_synth_warp(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_warp,
     const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, const float *pow43s);
+extern "C" __global__ void k_synth_warp_iso(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_warp,
+    const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, const float *pow43s);
 extern "C" __global__ void k_synth_fast(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_cta,
     const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, float *xr_tap, float *y_tap);
 
@@ -45,6 +47,7 @@ struct p3_slot {
   uint64_t ms_bytes;
   uint8_t *d_tail; uint8_t *h_tail;       /* 512 main-data bytes in front of the batch (pinned host copy) */
   int *d_any_empty; int hop_only;         /* device side-info parser: flag for the Q6 chain; pending for this slot */
+  int iso;                                /* the staged batch is flagged P3_FRAME_ISO */
   cudaEvent_t h2d_done, compute_done, d2h_done;
   p3_parsed keep; int have_keep;          /* host descriptors owned until the upload has completed */
   int busy;
@@ -105,6 +108,7 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
   c->chunk_frames = 1 << 18; c->fpc = 32;
   { const char *e = getenv("P3_FPC"); if (e && atoi(e) >= 1) c->fpc = atoi(e); }   /* tuning: frames per run (warp of k_synth_warp / CTA of k_synth_fast) */
   CK(cudaFuncSetAttribute(k_synth_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
+  CK(cudaFuncSetAttribute(k_synth_warp_iso, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
   {
     /* pow43s[8207 + v] = sign(v) * |v|^(4/3): requantization without abs / sign fix-up (pdmp3.c:2125-2132) */
     static float h[2 * 8207 + 1];
@@ -228,6 +232,7 @@ static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_
   CK(cudaMemcpyAsync(sl->raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(sl->frames.p, b->frames, (size_t)nf * sizeof(p3_frame), cudaMemcpyHostToDevice, st));
   sl->hop_only = b->hop_only;
+  sl->iso = b->n_frames > 0 && (b->frames[0].flags & P3_FRAME_ISO) != 0;
   if (!b->hop_only) CK(cudaMemcpyAsync(sl->gcs.p, b->gcs, (size_t)nf * 4 * sizeof(p3_gc), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(sl->d_tail, sl->h_tail, 512, cudaMemcpyHostToDevice, st));
   compute_tail(raw, b, c->h_tail, c->next_tail); c->have_next_tail = 1;
@@ -253,7 +258,7 @@ static void launch_synth(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, const i
   if (c->nch == 2 && !c->taps && c->synth_kernel == 0) {
     const int wpb = p3_synthw_warps_per_cta();
     const int64_t warps = (nf + c->fpc - 1) / c->fpc;
-    k_synth_warp<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
+    (sl->iso ? k_synth_warp_iso : k_synth_warp)<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
         is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207);
   } else
     k_synth_fast<<<(unsigned)((nf + c->fpc - 1) / c->fpc), 128, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc, is16, c1, scf, si, so,

@@ -29,7 +29,7 @@
 #define SW_MINB   3                 /* CTAs per SM the register allocation aims at */
 #endif
 #define SW_PITCH  33                /* f2 elements per DCT row: 66 words -> conflict-free for row-per-lane and column-per-lane access */
-#define SW_LUT_BYTES (1728 + 1440)  /* CTA-shared: reorder_src u16[576] | line_sfbw_s u8[576] | t1h f32[40] | t2 f32[320] */
+#define SW_LUT_BYTES (1728 + 1440 + 656)  /* CTA-shared: reorder_src u16[576] | line_sfbw_s u8[576] | t1h f32[40] | t2 f32[320] | line_sfb_l u8[576] | sfb_l u16[24] | sfb_s u16[16] */
 
 struct __align__(16) sw_warp_sm {
   uint8_t isb[SW_NBUF][2304];             /* [buffer][ch][576] int16: Huffman output of one granule (TMA destination) */
@@ -112,12 +112,14 @@ __device__ __forceinline__ void sw_aa(f2 &x, f2 nb, float cs, float ca, bool on)
       : "+l"(x.v) : "l"(nb.v), "r"((int)on), "f"(cs), "f"(ca));
 }
 
-extern "C" __global__ void __launch_bounds__(SW_WPB * 32, SW_MINB)
-k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
-             int64_t f_first, int64_t f_end, int frames_per_warp,
-             const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf,
-             const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm,
-             const float *__restrict__ pow43s /* signed |is|^(4/3) table, indexable -8207..8207 */)
+/* The kernel body; ISO = the batch is flagged P3_FRAME_ISO (a batch is uniform in that: the parser flags every frame or
+ * none).  Two instantiations, k_synth_warp and k_synth_warp_iso, so that the default kernel carries no code for the switch. */
+template <bool ISO> __device__ __forceinline__ void
+sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
+        int64_t f_first, int64_t f_end, int frames_per_warp,
+        const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf,
+        const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm,
+        const float *__restrict__ pow43s /* signed |is|^(4/3) table, indexable -8207..8207 */)
 {
   extern __shared__ __align__(16) uint8_t sw_dsm[];
   uint16_t *s_reo = reinterpret_cast<uint16_t *>(sw_dsm);
@@ -127,7 +129,11 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   sw_warp_sm *W = reinterpret_cast<sw_warp_sm *>(sw_dsm + SW_LUT_BYTES) + warp;
 
   const uint32_t sf = frames[f_first].sfreq;               /* a batch never mixes sample rates */
-  for (uint32_t i = threadIdx.x; i < 576; i += blockDim.x) { s_reo[i] = T->reorder_src[sf][i]; s_sfbw[i] = T->line_sfbw_s[sf][i]; }
+  uint8_t *s_lsfb = sw_dsm + 3168;                              /* intensity stereo: long sfb of a line, band starts (long / short) */
+  uint16_t *s_sfbl = reinterpret_cast<uint16_t *>(sw_dsm + 3168 + 576), *s_sfbs = s_sfbl + 24;
+  for (uint32_t i = threadIdx.x; i < 576; i += blockDim.x) { s_reo[i] = T->reorder_src[sf][i]; s_sfbw[i] = T->line_sfbw_s[sf][i]; s_lsfb[i] = T->line_sfb_l[sf][i]; }
+  if (threadIdx.x < 23) s_sfbl[threadIdx.x] = T->sfb_l[sf][threadIdx.x];
+  if (threadIdx.x >= 32 && threadIdx.x < 46) s_sfbs[threadIdx.x - 32] = T->sfb_s[sf][threadIdx.x - 32];
   for (uint32_t i = threadIdx.x; i < 360; i += blockDim.x) s_t1h[i] = i < 40 ? T->t1h[i] : T->t2[i - 40];
   __syncthreads();                                         /* the only CTA-wide barrier */
 
@@ -142,7 +148,6 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
   /* ---- per-lane constants ---- */
   float ce[8], co[8]; int ia, ib;
   synth_window_coeffs(T, ce, co, ia, ib);
-  const uint32_t pretab_l = (lane >= 11 && lane < 21) ? (0xbfa55u >> (2 * (lane - 11))) & 3u : 0u;   /* pretab[sfb = lane] (pdmp3.c:2123) */
   uint32_t sfbp[3] = {0, 0, 0};                            /* long-block sfb of this subband's 18 lines, 5 bits each */
   #pragma unroll
   for (int m = 0; m < 18; m++) sfbp[m / 6] |= (uint32_t)T->line_sfb_l[sf][18 * sb + m] << (5 * (m % 6));
@@ -208,6 +213,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       if (__builtin_expect(p0.first_short == 576 && p1.first_short == 576, 1)) {
         /* long blocks in both channels (the usual case): lane = sfb for both channels, one pass, one 8-byte store */
         if (lane < 22) {
+          const uint32_t pretab_l = (lane >= 11 && lane < 21) ? (0xbfa55u >> (2 * (lane - 11))) & 3u : 0u;   /* pretab[sfb = lane] (pdmp3.c:2123) */
           const uint32_t s0 = lane < 21 ? scf2[0][lane] : 0u, s1 = lane < 21 ? scf2[1][lane] : 0u;
           const float v0 = __fmul_rn(s_t1h[p0.mult * (s0 + p0.pre * pretab_l)], s_t2[p0.gg + P3_T2_BIAS]);
           const float v1 = __fmul_rn(s_t1h[p1.mult * (s1 + p1.pre * pretab_l)], s_t2[p1.gg + P3_T2_BIAS]);
@@ -258,11 +264,11 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
         float *scr = reinterpret_cast<float *>(blk);             /* [2][576] */
         #pragma unroll 1
         for (int c = 0; c < 2; c++) {
-          const uint32_t fsh = c ? p1.first_short : p0.first_short;
+          const uint32_t fsh = c ? p1.first_short : p0.first_short;      /* 576 (a long channel: nothing to do), 36 or 0 */
           const int16_t *isc = reinterpret_cast<const int16_t *>(W->isb[b]) + 576 * c;
           #pragma unroll 1
-          for (uint32_t d = lane; d < 576; d += 32)
-            if (d >= fsh) { const uint32_t s = s_reo[d], sw = s_sfbw[s]; scr[576 * c + d] = fq_requant(T->pow43, isc[s], W->scale[3 * (sw & 15u) + (sw >> 4)][c]); }
+          for (uint32_t d = (fsh & ~31u) + lane; d < 576; d += 32)
+            if (d >= fsh) { const uint32_t s = s_reo[d], sw = s_sfbw[s]; scr[576 * c + d] = __fmul_rn(W->scale[3 * (sw & 15u) + (sw >> 4)][c], __ldg(pow43s + isc[s])); }
         }
         __syncwarp();
         const bool sh0 = 18 * sb >= p0.first_short, sh1 = 18 * sb >= p1.first_short;
@@ -279,7 +285,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
 
       /* ---- B: stereo (pdmp3.c:1916-1971) ---- */
       const uint32_t c1r = (uint32_t)p1.c1;
-      const bool iso = ((frq.z >> 8) & P3_FRAME_ISO) != 0;     /* ISO semantics of MS / intensity stereo, see k_requant */
+      constexpr bool iso = ISO;                                /* ISO semantics of MS / intensity stereo, see k_requant */
       const uint32_t msn_all = (st_on && (mode_ext & 2)) ? (iso ? max((uint32_t)p0.c1, c1r) : min((uint32_t)p0.c1, c1r)) : 0u;   /* reference: min(count1), sic (pdmp3.c:1920) */
       /* ISO mode with intensity stereo on: bands starting at or above the right channel's count1 may be intensity coded
        * instead, so only the lines below it take MS here; the line-by-line pass below decides the rest */
@@ -307,7 +313,7 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
       const uint32_t first_short0 = p0.first_short;
       bool is_any = false;
       if (is_on) {                                            /* first line of the last band it can touch: long sfb 20, long sfb 7 (mixed), short sfb 11 (x3) */
-        const uint32_t ll = T->sfb_l[sf][first_short0 == 576 ? 20 : 7], ls = 3u * T->sfb_s[sf][11];
+        const uint32_t ll = s_sfbl[first_short0 == 576 ? 20 : 7], ls = 3u * s_sfbs[11];
         is_any = (first_short0 != 0 && ll >= c1r) || (first_short0 != 576 && ls >= c1r);
         if (iso && msn_all > msn) is_any = true;             /* MS lines at or above the right channel's count1 are done below as well */
       }
@@ -326,14 +332,14 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
           if (d >= first_short0) {
             /* short-block intensity (pdmp3.c:2190-2220) in reordered position; Q4: assignment through an `unsigned` */
             const uint32_t sw = s_sfbw[d], sfb = sw & 15u, win = sw >> 4;
-            if (sfb < 12 && 3u * T->sfb_s[sf][sfb] >= c1r) {
+            if (sfb < 12 && 3u * s_sfbs[sfb] >= c1r) {
               const uint32_t pp = scf2[isc][P3_SCF_S_OFF + 3 * sfb + win];
               if (iso) { if (pp < 7) { const float x = l; l = __fmul_rn(FC.is_l[pp], x); r = __fmul_rn(FC.is_r[pp], x); is_done = true; } }
               else if (pp != 7) { const float x = (float)(unsigned)(long long)l; l = x; r = x; }
             }
           } else {
-            const uint32_t sfb = T->line_sfb_l[sf][d], lim = sh0 ? 8u : 21u;                /* mixed: long sfb 0..7 only (pdmp3.c:1944) */
-            if (sfb < lim && T->sfb_l[sf][sfb] >= c1r) {
+            const uint32_t sfb = s_lsfb[d], lim = sh0 ? 8u : 21u;                           /* mixed: long sfb 0..7 only (pdmp3.c:1944) */
+            if (sfb < lim && s_sfbl[sfb] >= c1r) {
               const uint32_t pp = scf2[isc][sfb];                                           /* reference: channel-0 scalefactor, sic (pdmp3.c:2163) */
               if (iso ? pp < 7 : pp != 7) { const float x = l; l = __fmul_rn(FC.is_l[pp & 7], x); r = __fmul_rn(FC.is_r[pp & 7], x); is_done = true; }
             }
@@ -511,6 +517,15 @@ k_synth_warp(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
     }
   }
 }
+
+#define SW_KERNEL(NAME, ISO) \
+extern "C" __global__ void __launch_bounds__(SW_WPB * 32, SW_MINB) \
+NAME(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T, int64_t f_first, int64_t f_end, int frames_per_warp, \
+     const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf, \
+     const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm, const float *__restrict__ pow43s) \
+{ sw_body<ISO>(frames, gcs, T, f_first, f_end, frames_per_warp, is_in, count1, scf, st_in, st_out, pcm, pow43s); }
+SW_KERNEL(k_synth_warp, false)
+SW_KERNEL(k_synth_warp_iso, true)
 
 static int p3_synthw_check_consts(const float *cs, const float *ca)
 {
