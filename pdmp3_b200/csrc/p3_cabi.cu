@@ -12,10 +12,9 @@
 extern "C" int p3_fused_upload_consts(const p3_tables *T, const float *dct4);
 extern "C" size_t p3_synthw_smem_bytes(void);
 extern "C" int p3_synthw_warps_per_cta(void);
-extern "C" __global__ void k_synth_warp(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_warp,
-    const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, const float *pow43s);
-extern "C" __global__ void k_synth_warp_iso(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_warp,
-    const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, const float *pow43s);
+#define SW_DECL(NAME) extern "C" __global__ void NAME(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_warp, \
+    const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, const float *pow43s)
+SW_DECL(k_synth_warp); SW_DECL(k_synth_warp_lean); SW_DECL(k_synth_warp_iso); SW_DECL(k_synth_warp_iso_lean);
 extern "C" __global__ void k_synth_fast(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_cta,
     const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, float *xr_tap, float *y_tap);
 
@@ -108,7 +107,9 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
   c->chunk_frames = 1 << 18; c->fpc = 32;
   { const char *e = getenv("P3_FPC"); if (e && atoi(e) >= 1) c->fpc = atoi(e); }   /* tuning: frames per run (warp of k_synth_warp / CTA of k_synth_fast) */
   CK(cudaFuncSetAttribute(k_synth_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
+  CK(cudaFuncSetAttribute(k_synth_warp_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
   CK(cudaFuncSetAttribute(k_synth_warp_iso, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
+  CK(cudaFuncSetAttribute(k_synth_warp_iso_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
   {
     /* pow43s[8207 + v] = sign(v) * |v|^(4/3): requantization without abs / sign fix-up (pdmp3.c:2125-2132) */
     static float h[2 * 8207 + 1];
@@ -258,8 +259,13 @@ static void launch_synth(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, const i
   if (c->nch == 2 && !c->taps && c->synth_kernel == 0) {
     const int wpb = p3_synthw_warps_per_cta();
     const int64_t warps = (nf + c->fpc - 1) / c->fpc;
-    (sl->iso ? k_synth_warp_iso : k_synth_warp)<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
+    /* the same grid twice: every CTA classifies its frames and only the kernel of that class decodes them (p3_synthw.cuh) */
+    const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
+    (sl->iso ? k_synth_warp_iso_lean : k_synth_warp_lean)<<<grid, wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
         is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207);
+    (sl->iso ? k_synth_warp_iso : k_synth_warp)<<<grid, wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
+        is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207);
+    c->launches += 1;
   } else
     k_synth_fast<<<(unsigned)((nf + c->fpc - 1) / c->fpc), 128, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc, is16, c1, scf, si, so,
         (int16_t *)sl->pcm.p, c->taps ? (float *)c->xr.p : NULL, c->taps ? (float *)c->y.p : NULL);

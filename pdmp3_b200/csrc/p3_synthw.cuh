@@ -112,9 +112,18 @@ __device__ __forceinline__ void sw_aa(f2 &x, f2 nb, float cs, float ca, bool on)
       : "+l"(x.v) : "l"(nb.v), "r"((int)on), "f"(cs), "f"(ca));
 }
 
-/* The kernel body; ISO = the batch is flagged P3_FRAME_ISO (a batch is uniform in that: the parser flags every frame or
- * none).  Two instantiations, k_synth_warp and k_synth_warp_iso, so that the default kernel carries no code for the switch. */
-template <bool ISO> __device__ __forceinline__ void
+/* The kernel body, instantiated four times.
+ * ISO  = the batch is flagged P3_FRAME_ISO (a batch is uniform in that: the parser flags every frame or none), so the default
+ *        kernels carry no code for the switch.
+ * LEAN = content class of the CTA's frames.  Every launch sequence runs the LEAN and the full kernel over the same grid; a CTA
+ *        first classifies the frames of its runs (one frame per lane: long blocks of the same type in both channels, no
+ *        intensity-stereo flag -- the usual case by far) and returns at once if they are not of its kernel's class.  The LEAN
+ *        kernel has no test, branch, register or instruction-cache line of the rare paths (short / mixed blocks, different
+ *        block types in the two channels, intensity stereo) in its way: 6.0 -> 5.2 ms per 10^6 frames of the long-block
+ *        benchmark stream.  The same split INSIDE one kernel (two bodies chosen granule by granule, or with hysteresis) was
+ *        measured too: 80 KB of code that the warps of an SM walk in different places thrash the instruction caches (mixed-
+ *        block VBR stream 9.3 -> 16.2 / 10.6 ms), hence whole CTAs and two kernels. */
+template <bool ISO, bool LEAN> __device__ __forceinline__ void
 sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
         int64_t f_first, int64_t f_end, int frames_per_warp,
         const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf,
@@ -128,6 +137,24 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   sw_warp_sm *W = reinterpret_cast<sw_warp_sm *>(sw_dsm + SW_LUT_BYTES) + warp;
 
+  {                                                        /* content class of this CTA's frames (warm-up frames included) */
+    const int64_t gw_ = (int64_t)blockIdx.x * SW_WPB + warp, c0_ = f_first + gw_ * frames_per_warp;
+    bool simple = true;
+    if (c0_ < f_end) {
+      const int64_t hi = min(c0_ + (int64_t)frames_per_warp, f_end);
+      for (int64_t f = c0_ - (gw_ > 0 ? 1 : 0) + lane; f < hi; f += 32) {
+        const uint4 fq = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(frames + f) + 16);   /* size, begin, nch, mode, mode_ext, ... */
+        if (((fq.y >> 8) & 0xffu) == 1u && ((fq.y >> 16) & 1u)) simple = false;          /* joint stereo with the intensity bit */
+        const uint4 *g = reinterpret_cast<const uint4 *>(gcs + 4 * f);
+        #pragma unroll
+        for (int gr = 0; gr < 2; gr++) {
+          const uint32_t a = (g[2 * gr].y >> 4) & 7u, bb = (g[2 * gr + 1].y >> 4) & 7u;  /* win_switch | block_type << 1 */
+          if (a != bb || a == 5u) simple = false;                                         /* different types, or short (1 | 2 << 1) */
+        }
+      }
+    }
+    if ((__syncthreads_and(simple) != 0) != LEAN) return;
+  }
   const uint32_t sf = frames[f_first].sfreq;               /* a batch never mixes sample rates */
   uint8_t *s_lsfb = sw_dsm + 3168;                              /* intensity stereo: long sfb of a line, band starts (long / short) */
   uint16_t *s_sfbl = reinterpret_cast<uint16_t *>(sw_dsm + 3168 + 576), *s_sfbs = s_sfbl + 24;
@@ -207,10 +234,26 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
       sw_mbar_wait(&W->mbar[b], SW_NBUF == 2 ? (q >> 1) & 1 : q & 1);
       const uint8_t (*scf2)[P3_SCF_STRIDE] = reinterpret_cast<const uint8_t (*)[P3_SCF_STRIDE]>(W->scf[b]);
 
+      /* ---- stereo ranges (pdmp3.c:1916-1971) and the choice of the body ---- */
+      const uint32_t c1r = (uint32_t)p1.c1;
+      constexpr bool iso = ISO;                                /* ISO semantics of MS / intensity stereo, see k_requant */
+      const uint32_t msn_all = (st_on && (mode_ext & 2)) ? (iso ? max((uint32_t)p0.c1, c1r) : min((uint32_t)p0.c1, c1r)) : 0u;   /* reference: min(count1), sic (pdmp3.c:1920) */
+      /* ISO mode with intensity stereo on: bands starting at or above the right channel's count1 may be intensity coded
+       * instead, so only the lines below it take MS in registers; the line-by-line pass decides the rest */
+      const uint32_t msn = (iso && is_on) ? min(msn_all, c1r) : msn_all;
+      /* intensity stereo touches a band only if it starts at or above the right channel's count1: with count1 beyond the
+       * start of the last eligible band there is nothing to do (the usual case at high bit rates) */
+      const uint32_t first_short0 = p0.first_short;
+      bool is_any = false;
+      if (is_on) {                                            /* first line of the last band it can touch: long sfb 20, long sfb 7 (mixed), short sfb 11 (x3) */
+        const uint32_t ll = s_sfbl[first_short0 == 576 ? 20 : 7], ls = 3u * s_sfbs[11];
+        is_any = (first_short0 != 0 && ll >= c1r) || (first_short0 != 576 && ls >= c1r);
+        if (iso && msn_all > msn) is_any = true;             /* MS lines at or above the right channel's count1 are done line by line as well */
+      }
       /* ---- band scales fl(t1*t2) (pdmp3.c:2127-2128, 2144-2146); same table layout as k_synth_fast: long blocks
        *      index = sfb (0..21), short 3*sfb+win (0..38), mixed: long bands 0..7 sit in the unused short slots 0..7.
        *      The scalefactor byte of short band 3*sfb+win is byte 24 + 3*sfb + win of the row. ---- */
-      if (__builtin_expect(p0.first_short == 576 && p1.first_short == 576, 1)) {
+      if (LEAN || (p0.first_short == 576 && p1.first_short == 576)) {
         /* long blocks in both channels (the usual case): lane = sfb for both channels, one pass, one 8-byte store */
         if (lane < 22) {
           const uint32_t pretab_l = (lane >= 11 && lane < 21) ? (0xbfa55u >> (2 * (lane - 11))) & 3u : 0u;   /* pretab[sfb = lane] (pdmp3.c:2123) */
@@ -219,7 +262,7 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
           const float v1 = __fmul_rn(s_t1h[p1.mult * (s1 + p1.pre * pretab_l)], s_t2[p1.gg + P3_T2_BIAS]);
           *reinterpret_cast<float2 *>(&W->scale[lane][0]) = make_float2(v0, v1);
         }
-      } else
+      } else if constexpr (!LEAN) {
       #pragma unroll 1
       for (int k = 0; k < 3; k++) {
         const uint32_t e = lane + 32 * k;
@@ -238,6 +281,7 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
           const float v = __fmul_rn(s_t1h[mult * sc], s_t2[qq + P3_T2_BIAS]);
           W->scale[bnd][c] = active ? v : 0.0f;
         }
+      }
       }
       __syncwarp();
 
@@ -259,7 +303,7 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
           }
         }
       }
-#ifndef SW_NOSLOW
+      if constexpr (!LEAN)
       if (p0.first_short < 576 || p1.first_short < 576) {          /* a short (or mixed) block in either channel: reordered gather, rare */
         float *scr = reinterpret_cast<float *>(blk);             /* [2][576] */
         #pragma unroll 1
@@ -281,15 +325,8 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
         }
         __syncwarp();
       }
-#endif
 
-      /* ---- B: stereo (pdmp3.c:1916-1971) ---- */
-      const uint32_t c1r = (uint32_t)p1.c1;
-      constexpr bool iso = ISO;                                /* ISO semantics of MS / intensity stereo, see k_requant */
-      const uint32_t msn_all = (st_on && (mode_ext & 2)) ? (iso ? max((uint32_t)p0.c1, c1r) : min((uint32_t)p0.c1, c1r)) : 0u;   /* reference: min(count1), sic (pdmp3.c:1920) */
-      /* ISO mode with intensity stereo on: bands starting at or above the right channel's count1 may be intensity coded
-       * instead, so only the lines below it take MS here; the line-by-line pass below decides the rest */
-      const uint32_t msn = (iso && is_on) ? min(msn_all, c1r) : msn_all;
+      /* ---- B: stereo (pdmp3.c:1916-1971): MS in registers ---- */
       if (18 * sb < msn) {
         const int32_t msrem = (int32_t)msn - 18 * (int32_t)sb;     /* lines of this subband below msn */
         /* the reference multiplies the float sum by the DOUBLE constant 1/sqrt 2 and rounds once to float (pdmp3.c:168,
@@ -307,24 +344,15 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
           sw_fnma_if(in[m], nt, p, m < msrem);                     /* p + t, written as an fma so that nothing can be contracted into it; in place, lines below msn only */
         }
       }
-#ifndef SW_NOSLOW
-      /* intensity stereo touches a band only if it starts at or above the right channel's count1: with count1 beyond the
-       * start of the last eligible band there is nothing to do (the usual case at high bit rates) */
-      const uint32_t first_short0 = p0.first_short;
-      bool is_any = false;
-      if (is_on) {                                            /* first line of the last band it can touch: long sfb 20, long sfb 7 (mixed), short sfb 11 (x3) */
-        const uint32_t ll = s_sfbl[first_short0 == 576 ? 20 : 7], ls = 3u * s_sfbs[11];
-        is_any = (first_short0 != 0 && ll >= c1r) || (first_short0 != 576 && ls >= c1r);
-        if (iso && msn_all > msn) is_any = true;             /* MS lines at or above the right channel's count1 are done below as well */
-      }
-      if (__builtin_expect(is_any, 0)) {                                           /* line by line through the scratch block, rare */
+      if constexpr (!LEAN)
+      if (is_any) {                                            /* intensity stereo: line by line through the scratch block */
         f2 *scr = blk;                                           /* [576] */
         #pragma unroll
         for (int m = 0; m < 18; m++) scr[18 * sb + m] = in[m];
         __syncwarp();
         const bool sh0 = first_short0 < 576;
-        #pragma unroll 1
         const uint32_t isc = iso ? 1u : 0u;
+        #pragma unroll 1
         for (uint32_t d = (c1r & ~31u) + lane; d < 576; d += 32) {   /* a line below count1 is in a band that starts below it */
           if (d < msn) continue;
           float l = f2_x(scr[d]), r = f2_y(scr[d]);
@@ -356,7 +384,6 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
         for (int m = 0; m < 18; m++) in[m] = scr[18 * sb + m];
         __syncwarp();
       }
-#endif
 
       /* every lane is done with this buffer: bring in the granule after the next one */
       __syncwarp();
@@ -373,22 +400,16 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
           const float ux = f2_x(in[i]), uy = f2_y(in[i]), lx = f2_x(in[17 - i]), ly = f2_y(in[17 - i]);
           const float bx = __shfl_up_sync(0xffffffffu, lx, 1), by = __shfl_up_sync(0xffffffffu, ly, 1);       /* line 18sb-1-i */
           const float ax = __shfl_down_sync(0xffffffffu, ux, 1), ay = __shfl_down_sync(0xffffffffu, uy, 1);   /* line 18(sb+1)+i */
-#ifndef SW_NOSLOW
-          if (__builtin_expect(p0.sblim == p1.sblim, 1))
-#endif
-          {
+          if (LEAN || p0.sblim == p1.sblim) {
             sw_aa(in[i], f2_make(bx, by), sw_cs(i), sw_ca(i), lo0);                              /* ub (pdmp3.c:1726) */
             sw_aa(in[17 - i], f2_make(ax, ay), sw_cs(i), -sw_ca(i), hi0);                        /* lb (pdmp3.c:1725) */
-          }
-#ifndef SW_NOSLOW
-          else {
+          } else if constexpr (!LEAN) {
             const float nux = lo0 ? __fadd_rn(__fmul_rn(ux, FC.cs[i]), __fmul_rn(bx, FC.ca[i])) : ux;
             const float nuy = lo1 ? __fadd_rn(__fmul_rn(uy, FC.cs[i]), __fmul_rn(by, FC.ca[i])) : uy;
             const float nlx = hi0 ? __fsub_rn(__fmul_rn(lx, FC.cs[i]), __fmul_rn(ax, FC.ca[i])) : lx;
             const float nly = hi1 ? __fsub_rn(__fmul_rn(ly, FC.cs[i]), __fmul_rn(ay, FC.ca[i])) : ly;
             in[i] = f2_make(nux, nuy); in[17 - i] = f2_make(nlx, nly);
           }
-#endif
         }
       }
 
@@ -397,10 +418,7 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
       {
         const uint32_t bt0 = (p0.ws && p0.mixed && sb < 2) ? 0u : p0.bt, bt1 = (p1.ws && p1.mixed && sb < 2) ? 0u : p1.bt;
         const float sgn = (sb & 1) ? -1.0f : 1.0f;
-#ifndef SW_NOSLOW
-        if (__builtin_expect(bt0 == bt1 && bt0 != 2, 1))
-#endif
-        {
+        if (LEAN || (bt0 == bt1 && bt0 != 2)) {
           f2 t[18];
           dct4_18<f2>(in, t);
           /* 36-point IMDCT from the DCT-IV by symmetry (signs folded into swin): output p < 18 is overlap-added with
@@ -415,9 +433,8 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
           #pragma unroll
           for (int k = 0; k < 9; k++) { tail[8 - k] = vmul(t[k], FC.swin[bt0][26 - k]); tail[9 + k] = vmul(t[k], FC.swin[bt0][27 + k]); }
         }
-#ifndef SW_NOSLOW
-#ifndef SW_NO_PSHORT
-        else if (bt0 == bt1) {                                      /* short windows in both channels: three 12-point IMDCTs, packed */
+        else if constexpr (!LEAN) {
+        if (bt0 == bt1) {                                      /* short windows in both channels: three 12-point IMDCTs, packed */
           f2 raw[36];
           imdct_short<f2>(in, raw);
           #pragma unroll
@@ -428,7 +445,6 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
             tail[ss] = raw[18 + ss];
           }
         }
-#endif
         else {                                                      /* different block types in the two channels: one channel at a time */
           float *blkf = reinterpret_cast<float *>(blk);
           #pragma unroll 1
@@ -459,7 +475,7 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
             }
           }
         }
-#endif
+        }
       }
       __syncwarp();
 
@@ -518,14 +534,16 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
   }
 }
 
-#define SW_KERNEL(NAME, ISO) \
+#define SW_KERNEL(NAME, ISO, LEAN) \
 extern "C" __global__ void __launch_bounds__(SW_WPB * 32, SW_MINB) \
 NAME(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T, int64_t f_first, int64_t f_end, int frames_per_warp, \
      const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf, \
      const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm, const float *__restrict__ pow43s) \
-{ sw_body<ISO>(frames, gcs, T, f_first, f_end, frames_per_warp, is_in, count1, scf, st_in, st_out, pcm, pow43s); }
-SW_KERNEL(k_synth_warp, false)
-SW_KERNEL(k_synth_warp_iso, true)
+{ sw_body<ISO, LEAN>(frames, gcs, T, f_first, f_end, frames_per_warp, is_in, count1, scf, st_in, st_out, pcm, pow43s); }
+SW_KERNEL(k_synth_warp, false, false)
+SW_KERNEL(k_synth_warp_lean, false, true)
+SW_KERNEL(k_synth_warp_iso, true, false)
+SW_KERNEL(k_synth_warp_iso_lean, true, true)
 
 static int p3_synthw_check_consts(const float *cs, const float *ca)
 {
