@@ -158,6 +158,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the decoder has no CPU fallback")
     torch.cuda.set_device(local)
+    # stdout carries exactly ONE JSON line: whatever libraries print there meanwhile (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush(); _stdout_fd = os.dup(1); os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nf = a.frames
@@ -262,6 +264,7 @@ def main():
         if r:
             cpu = {"value": r[0], "unit": "sample-frames/s", "cores": ncores, "kind": r[3],
                    "sample": "%d forked processes x 4096 frames of the same stream type, reference API loop, %.2f s wall" % (ncores, r[2])}
+    sys.stdout.flush(); os.dup2(_stdout_fd, 1)
     print(json.dumps({"metric": "decoded_pcm_sample_frames_per_sec", "value": value, "unit": "sample-frames/s",
                       "x_realtime_44k1": value / 44100.0, "int16_samples_per_sec": 2 * value, "frames_per_sec": value / 1152,
                       "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
@@ -271,6 +274,7 @@ def main():
                                  "parallelism": "frame-sharded x%d, no data-path collective" % world, "host_parse_s": t_parse},
                       "clocks": clocks, "e2e": e2e, "gpu_launches": launches * a.steps, "roofline": roof, "cpu_baseline": cpu,
                       "gather_to_rank0": gather}))
+    sys.stdout.flush()
     if world > 1: dist.destroy_process_group()
     return 0
 
