@@ -125,7 +125,8 @@ int  p3_ctx_reset(p3_ctx *c);                 /* zero overlap / FIFO / reservoir
 int  p3_ctx_set_mode(p3_ctx *c, int mode);
 int  p3_ctx_set_taps(p3_ctx *c, int on);              /* keep stage taps of the next batches on the device */
 int  p3_ctx_set_frames_per_cta(p3_ctx *c, int n);     /* FAST mode: frames each CTA (k_synth_fast) / warp (k_synth_warp) walks (default 32) */
-int  p3_ctx_set_synth_kernel(p3_ctx *c, int which);   /* FAST mode: 0 = k_synth_warp for stereo batches (default), 1 = always k_synth_fast */
+int  p3_ctx_set_synth_kernel(p3_ctx *c, int which);   /* FAST mode: 0 = k_synth_warp(_lean) for stereo batches (default), 1 = always k_synth_fast,
+                                                         2 = k_synth_warp only, no content classes (check: same bits as 0) */
 const char *p3_last_error(void);
 
 /* Tap buffers (device side, optional; for stage-level parity tests). NULL = not captured. */

@@ -155,7 +155,7 @@ class Context:
         _check(lib().p3_ctx_set_frames_per_cta(self.h, n), "p3_ctx_set_frames_per_cta")
 
     def set_synth_kernel(self, which):
-        """FAST mode: 0 = k_synth_warp for stereo batches (default), 1 = always k_synth_fast."""
+        """FAST mode: 0 = k_synth_warp / k_synth_warp_lean by content class (default), 1 = always k_synth_fast, 2 = k_synth_warp only (no classes)."""
         _check(lib().p3_ctx_set_synth_kernel(self.h, which), "p3_ctx_set_synth_kernel")
 
     def reset(self):

@@ -13,7 +13,7 @@ extern "C" int p3_fused_upload_consts(const p3_tables *T, const float *dct4);
 extern "C" size_t p3_synthw_smem_bytes(void);
 extern "C" int p3_synthw_warps_per_cta(void);
 #define SW_DECL(NAME) extern "C" __global__ void NAME(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_warp, \
-    const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, const float *pow43s)
+    const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, const float *pow43s, int classify)
 SW_DECL(k_synth_warp); SW_DECL(k_synth_warp_lean); SW_DECL(k_synth_warp_iso); SW_DECL(k_synth_warp_iso_lean);
 extern "C" __global__ void k_synth_fast(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_cta,
     const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, float *xr_tap, float *y_tap);
@@ -66,7 +66,7 @@ struct p3_ctx {
   int64_t n_frames, n_pcm_frames; uint32_t nch; uint64_t raw_bytes;
   uint32_t k1_smem_words; int64_t chunk_frames;
   int launches; int launches_parse; int taps; int fpc;
-  float *d_pow43s; int synth_kernel;      /* signed |is|^(4/3) table (k_synth_warp); 0 = pick, 1 = always k_synth_fast */
+  float *d_pow43s; int synth_kernel;      /* signed |is|^(4/3) table (k_synth_warp); 0 = pick, 1 = always k_synth_fast, 2 = k_synth_warp without content classes */
   uint8_t next_tail[512]; int have_next_tail;
 };
 
@@ -176,7 +176,7 @@ extern "C" int p3_ctx_set_mode(p3_ctx *c, int mode)
 }
 extern "C" int p3_ctx_set_taps(p3_ctx *c, int on) { if (!c) return P3_EINVAL; c->taps = on; return P3_OK; }
 extern "C" int p3_ctx_set_frames_per_cta(p3_ctx *c, int n) { if (!c || n < 1) return P3_EINVAL; c->fpc = n; return P3_OK; }
-extern "C" int p3_ctx_set_synth_kernel(p3_ctx *c, int which) { if (!c || which < 0 || which > 1) return P3_EINVAL; c->synth_kernel = which; return P3_OK; }
+extern "C" int p3_ctx_set_synth_kernel(p3_ctx *c, int which) { if (!c || which < 0 || which > 2) return P3_EINVAL; c->synth_kernel = which; return P3_OK; }
 extern "C" void *p3_ctx_stream(p3_ctx *c) { return c ? (void *)c->stream : NULL; }
 extern "C" int p3_kernel_launch_count(p3_ctx *c) { return c ? c->launches : 0; }
 
@@ -256,15 +256,16 @@ static void launch_synth(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, const i
 {
   const p3_frame *fr = (const p3_frame *)sl->frames.p; const p3_gc *gc = (const p3_gc *)sl->gcs.p;
   const int64_t nf = f1 - f0;
-  if (c->nch == 2 && !c->taps && c->synth_kernel == 0) {
+  if (c->nch == 2 && !c->taps && c->synth_kernel != 1) {
+    const int classify = c->synth_kernel == 0;
     const int wpb = p3_synthw_warps_per_cta();
     const int64_t warps = (nf + c->fpc - 1) / c->fpc;
     /* the same grid twice: every CTA classifies its frames and only the kernel of that class decodes them (p3_synthw.cuh) */
     const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
     (sl->iso ? k_synth_warp_iso_lean : k_synth_warp_lean)<<<grid, wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
-        is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207);
+        is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207, classify);
     (sl->iso ? k_synth_warp_iso : k_synth_warp)<<<grid, wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
-        is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207);
+        is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207, classify);
     c->launches += 1;
   } else
     k_synth_fast<<<(unsigned)((nf + c->fpc - 1) / c->fpc), 128, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc, is16, c1, scf, si, so,

@@ -128,7 +128,8 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
         int64_t f_first, int64_t f_end, int frames_per_warp,
         const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf,
         const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm,
-        const float *__restrict__ pow43s /* signed |is|^(4/3) table, indexable -8207..8207 */)
+        const float *__restrict__ pow43s /* signed |is|^(4/3) table, indexable -8207..8207 */,
+        int classify /* 0: every CTA is of the full class (the LEAN kernel returns): the check that both kernels give the same bits */)
 {
   extern __shared__ __align__(16) uint8_t sw_dsm[];
   uint16_t *s_reo = reinterpret_cast<uint16_t *>(sw_dsm);
@@ -139,8 +140,8 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
 
   {                                                        /* content class of this CTA's frames (warm-up frames included) */
     const int64_t gw_ = (int64_t)blockIdx.x * SW_WPB + warp, c0_ = f_first + gw_ * frames_per_warp;
-    bool simple = true;
-    if (c0_ < f_end) {
+    bool simple = classify != 0;
+    if (simple && c0_ < f_end) {
       const int64_t hi = min(c0_ + (int64_t)frames_per_warp, f_end);
       for (int64_t f = c0_ - (gw_ > 0 ? 1 : 0) + lane; f < hi; f += 32) {
         const uint4 fq = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(frames + f) + 16);   /* size, begin, nch, mode, mode_ext, ... */
@@ -538,8 +539,8 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
 extern "C" __global__ void __launch_bounds__(SW_WPB * 32, SW_MINB) \
 NAME(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T, int64_t f_first, int64_t f_end, int frames_per_warp, \
      const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf, \
-     const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm, const float *__restrict__ pow43s) \
-{ sw_body<ISO, LEAN>(frames, gcs, T, f_first, f_end, frames_per_warp, is_in, count1, scf, st_in, st_out, pcm, pow43s); }
+     const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm, const float *__restrict__ pow43s, int classify) \
+{ sw_body<ISO, LEAN>(frames, gcs, T, f_first, f_end, frames_per_warp, is_in, count1, scf, st_in, st_out, pcm, pow43s, classify); }
 SW_KERNEL(k_synth_warp, false, false)
 SW_KERNEL(k_synth_warp_lean, false, true)
 SW_KERNEL(k_synth_warp_iso, true, false)

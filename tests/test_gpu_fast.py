@@ -146,3 +146,19 @@ def test_one_million_frames_vbr_mixed(fast_ctx):
     ex.close()
     d = np.abs(two.astype(np.int32) - ref.astype(np.int32))
     assert d.max() <= 1 and (d == 0).mean() > 0.9
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "k48", "crc", "c1b", "lowrate"])
+def test_content_classes_give_the_same_bits(fast_ctx, name):
+    """The synthesis runs as two kernels: every CTA classifies its frames (long blocks of one type in both channels, no
+    intensity bit) and k_synth_warp_lean -- the body without the rare paths -- or the full k_synth_warp decodes them.
+    Whatever the split, the PCM must be bit-identical to the full kernel decoding everything (set_synth_kernel(2)); the
+    run lengths 32 / 4 / 1 move the CTA boundaries, so the same frame is decoded by either kernel."""
+    s, _ = H.synth(400, seed=23, **VARIANTS[name])
+    fast_ctx.reset(); fast_ctx.set_synth_kernel(2); full = fast_ctx.decode(s, lookahead=0)
+    fast_ctx.set_synth_kernel(0)
+    for fpw in (32, 4, 1):
+        fast_ctx.reset(); fast_ctx.set_frames_per_cta(fpw)
+        got = fast_ctx.decode(s, lookahead=0)
+        assert np.array_equal(got, full), "content classes change the result (run length %d)" % fpw
+    fast_ctx.set_frames_per_cta(32)
