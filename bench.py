@@ -240,9 +240,9 @@ def main():
     peak, peak_src = peaks()
     frame_bytes = len(stream) / parsed.n_frames
     alg_bytes = (frame_bytes + 4608.0) * n_frames
-    # stereo workloads: the packed-FFMA2 warp kernels; the long-block cbr320 stream is decoded by the LEAN content class (k_synth_warp_lean),
-    # the mixed-block vbr stream by the full kernel (both are launched over the same grid, the CTAs of the other class return at once)
-    synth = "k_synth_fast" if os.environ.get("P3_SYNTH") == "cta" else ("k_synth_warp_lean" if a.workload == "cbr320" else "k_synth_warp")
+    # stereo workloads: the packed-FFMA2 warp kernels, one per content class, all launched over the same grid (the CTAs of the other classes
+    # return at once): the long-block cbr320 stream is decoded by k_synth_warp_lean, the mixed-block vbr stream by k_synth_warp_same
+    synth = "k_synth_fast" if os.environ.get("P3_SYNTH") == "cta" else ("k_synth_warp_lean" if a.workload == "cbr320" else "k_synth_warp_same")
     names = ["k_compact", "k_huffman", synth, "-", "-"] if a.mode == "fast" else ["k_compact", "k_huffman", "k_requant", "k_imdct", "k_polyphase"]
     staged = sum(ms_stage) > 0                              # per-kernel times exist when the batch ran as one launch sequence
     dom = int(np.argmax(ms_stage)) if staged else 0

@@ -14,7 +14,7 @@ extern "C" size_t p3_synthw_smem_bytes(void);
 extern "C" int p3_synthw_warps_per_cta(void);
 #define SW_DECL(NAME) extern "C" __global__ void NAME(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_warp, \
     const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, const float *pow43s, int classify)
-SW_DECL(k_synth_warp); SW_DECL(k_synth_warp_lean); SW_DECL(k_synth_warp_iso); SW_DECL(k_synth_warp_iso_lean);
+SW_DECL(k_synth_warp); SW_DECL(k_synth_warp_same); SW_DECL(k_synth_warp_lean); SW_DECL(k_synth_warp_iso); SW_DECL(k_synth_warp_iso_same); SW_DECL(k_synth_warp_iso_lean);
 extern "C" __global__ void k_synth_fast(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_cta,
     const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, float *xr_tap, float *y_tap);
 
@@ -108,6 +108,8 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
   { const char *e = getenv("P3_FPC"); if (e && atoi(e) >= 1) c->fpc = atoi(e); }   /* tuning: frames per run (warp of k_synth_warp / CTA of k_synth_fast) */
   CK(cudaFuncSetAttribute(k_synth_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
   CK(cudaFuncSetAttribute(k_synth_warp_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
+  CK(cudaFuncSetAttribute(k_synth_warp_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
+  CK(cudaFuncSetAttribute(k_synth_warp_iso_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
   CK(cudaFuncSetAttribute(k_synth_warp_iso, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
   CK(cudaFuncSetAttribute(k_synth_warp_iso_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
   {
@@ -260,13 +262,15 @@ static void launch_synth(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, const i
     const int classify = c->synth_kernel == 0;
     const int wpb = p3_synthw_warps_per_cta();
     const int64_t warps = (nf + c->fpc - 1) / c->fpc;
-    /* the same grid twice: every CTA classifies its frames and only the kernel of that class decodes them (p3_synthw.cuh) */
+    /* the same grid three times: every CTA classifies its frames and only the kernel of that class decodes them (p3_synthw.cuh) */
     const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
     (sl->iso ? k_synth_warp_iso_lean : k_synth_warp_lean)<<<grid, wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
         is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207, classify);
+    (sl->iso ? k_synth_warp_iso_same : k_synth_warp_same)<<<grid, wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
+        is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207, classify);
     (sl->iso ? k_synth_warp_iso : k_synth_warp)<<<grid, wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
         is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207, classify);
-    c->launches += 1;
+    c->launches += 2;
   } else
     k_synth_fast<<<(unsigned)((nf + c->fpc - 1) / c->fpc), 128, 0, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc, is16, c1, scf, si, so,
         (int16_t *)sl->pcm.p, c->taps ? (float *)c->xr.p : NULL, c->taps ? (float *)c->y.p : NULL);

@@ -112,25 +112,32 @@ __device__ __forceinline__ void sw_aa(f2 &x, f2 nb, float cs, float ca, bool on)
       : "+l"(x.v) : "l"(nb.v), "r"((int)on), "f"(cs), "f"(ca));
 }
 
-/* The kernel body, instantiated four times.
- * ISO  = the batch is flagged P3_FRAME_ISO (a batch is uniform in that: the parser flags every frame or none), so the default
- *        kernels carry no code for the switch.
- * LEAN = content class of the CTA's frames.  Every launch sequence runs the LEAN and the full kernel over the same grid; a CTA
- *        first classifies the frames of its runs (one frame per lane: long blocks of the same type in both channels, no
- *        intensity-stereo flag -- the usual case by far) and returns at once if they are not of its kernel's class.  The LEAN
- *        kernel has no test, branch, register or instruction-cache line of the rare paths (short / mixed blocks, different
- *        block types in the two channels, intensity stereo) in its way: 6.0 -> 5.2 ms per 10^6 frames of the long-block
- *        benchmark stream.  The same split INSIDE one kernel (two bodies chosen granule by granule, or with hysteresis) was
- *        measured too: 80 KB of code that the warps of an SM walk in different places thrash the instruction caches (mixed-
- *        block VBR stream 9.3 -> 16.2 / 10.6 ms), hence whole CTAs and two kernels. */
-template <bool ISO, bool LEAN> __device__ __forceinline__ void
+/* The kernel body, instantiated six times.
+ * ISO = the batch is flagged P3_FRAME_ISO (a batch is uniform in that: the parser flags every frame or none), so the default
+ *       kernels carry no code for the switch.
+ * CLS = content class of the CTA's frames.  Every launch sequence runs the kernels of all three classes over the same grid; a CTA
+ *       first classifies the frames of its runs from the descriptors (one frame per lane, one __syncthreads_and per class) and
+ *       returns at once unless they are of its kernel's class:
+ *         2 LEAN  every granule has the same win_switch / block_type / mixed flag in both channels, no short block, and no frame
+ *                 has the intensity bit set -- the usual case by far; the body has no test, branch, register or instruction-
+ *                 cache line of the rare paths in its way: 6.0 -> 5.3 ms per 10^6 frames of the long-block benchmark stream;
+ *         1 SAME  the two channels of every granule agree in those flags (short / mixed blocks and intensity stereo allowed):
+ *                 the body lacks the one-channel-at-a-time IMDCT and antialias paths, 13 KB of code that cost the mixed-block
+ *                 VBR stream 10 % (9.3 -> 8.3 ms) just by being in the kernel;
+ *         0       anything.
+ *       All three give the same bits for a frame they can decode (tests/test_gpu_fast.py compares every split with class 0
+ *       alone).  The same split INSIDE one kernel was measured too: two bodies chosen granule by granule are 80 KB of code that
+ *       the warps of an SM walk in different places, and the instruction caches thrash (mixed-block VBR stream 9.3 -> 16.2 ms,
+ *       with a hysteresis 10.6 ms) -- hence whole CTAs and separate kernels. */
+template <bool ISO, int CLS> __device__ __forceinline__ void
 sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T,
         int64_t f_first, int64_t f_end, int frames_per_warp,
         const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf,
         const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm,
         const float *__restrict__ pow43s /* signed |is|^(4/3) table, indexable -8207..8207 */,
-        int classify /* 0: every CTA is of the full class (the LEAN kernel returns): the check that both kernels give the same bits */)
+        int classify /* 0: every CTA is of class 0 (the other kernels return): the check that all kernels give the same bits */)
 {
+  constexpr bool LEAN = CLS == 2, SAME = CLS >= 1;
   extern __shared__ __align__(16) uint8_t sw_dsm[];
   uint16_t *s_reo = reinterpret_cast<uint16_t *>(sw_dsm);
   uint8_t *s_sfbw = sw_dsm + 1152;
@@ -140,8 +147,8 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
 
   {                                                        /* content class of this CTA's frames (warm-up frames included) */
     const int64_t gw_ = (int64_t)blockIdx.x * SW_WPB + warp, c0_ = f_first + gw_ * frames_per_warp;
-    bool simple = classify != 0;
-    if (simple && c0_ < f_end) {
+    bool same = classify != 0, simple = same;
+    if (same && c0_ < f_end) {
       const int64_t hi = min(c0_ + (int64_t)frames_per_warp, f_end);
       for (int64_t f = c0_ - (gw_ > 0 ? 1 : 0) + lane; f < hi; f += 32) {
         const uint4 fq = *reinterpret_cast<const uint4 *>(reinterpret_cast<const uint8_t *>(frames + f) + 16);   /* size, begin, nch, mode, mode_ext, ... */
@@ -149,12 +156,14 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
         const uint4 *g = reinterpret_cast<const uint4 *>(gcs + 4 * f);
         #pragma unroll
         for (int gr = 0; gr < 2; gr++) {
-          const uint32_t a = (g[2 * gr].y >> 4) & 7u, bb = (g[2 * gr + 1].y >> 4) & 7u;  /* win_switch | block_type << 1 */
-          if (a != bb || a == 5u) simple = false;                                         /* different types, or short (1 | 2 << 1) */
+          const uint32_t a = (g[2 * gr].y >> 4) & 15u, bb = (g[2 * gr + 1].y >> 4) & 15u;  /* win_switch | block_type << 1 | mixed << 3 */
+          if (a != bb) same = false;
+          if ((a & 7u) == 5u) simple = false;                                              /* short: win_switch with block_type 2 */
         }
       }
     }
-    if ((__syncthreads_and(simple) != 0) != LEAN) return;
+    const int all_same = __syncthreads_and(same), all_simple = __syncthreads_and(same && simple);
+    if ((all_simple ? 2 : all_same ? 1 : 0) != CLS) return;
   }
   const uint32_t sf = frames[f_first].sfreq;               /* a batch never mixes sample rates */
   uint8_t *s_lsfb = sw_dsm + 3168;                              /* intensity stereo: long sfb of a line, band starts (long / short) */
@@ -305,26 +314,23 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
         }
       }
       if constexpr (!LEAN)
-      if (p0.first_short < 576 || p1.first_short < 576) {          /* a short (or mixed) block in either channel: reordered gather, rare */
-        float *scr = reinterpret_cast<float *>(blk);             /* [2][576] */
-        #pragma unroll 1
-        for (int c = 0; c < 2; c++) {
-          const uint32_t fsh = c ? p1.first_short : p0.first_short;      /* 576 (a long channel: nothing to do), 36 or 0 */
-          const int16_t *isc = reinterpret_cast<const int16_t *>(W->isb[b]) + 576 * c;
-          #pragma unroll 1
-          for (uint32_t d = (fsh & ~31u) + lane; d < 576; d += 32)
-            if (d >= fsh) { const uint32_t s = s_reo[d], sw = s_sfbw[s]; scr[576 * c + d] = __fmul_rn(W->scale[3 * (sw & 15u) + (sw >> 4)][c], __ldg(pow43s + isc[s])); }
-        }
-        __syncwarp();
+      if (p0.first_short < 576 || p1.first_short < 576) {          /* a short (or mixed) block in either channel */
+        /* lane = subband also here: line d = 18 sb + m of the REORDERED spectrum is bitstream line reorder_src[d], its scale that
+         * of (sfb, window) of that line (pdmp3.c:1786-1823, 2140-2152); first_short is 0 or 36, i.e. whole subbands */
         const bool sh0 = 18 * sb >= p0.first_short, sh1 = 18 * sb >= p1.first_short;
-        #pragma unroll
-        for (int m = 0; m < 18; m++) {
-          float l = f2_x(in[m]), r = f2_y(in[m]);
-          if (sh0) l = scr[18 * sb + m];
-          if (sh1) r = scr[576 + 18 * sb + m];
-          in[m] = f2_make(l, r);
+        if (sh0 || sh1) {
+          const int16_t *is0 = reinterpret_cast<const int16_t *>(W->isb[b]), *is1 = is0 + 576;
+          const float2 *scl = reinterpret_cast<const float2 *>(&W->scale[0][0]);
+          #pragma unroll
+          for (int m = 0; m < 18; m++) {
+            const uint32_t s = s_reo[18 * sb + m], sw = s_sfbw[s];
+            const float2 sc = scl[3 * (sw & 15u) + (sw >> 4)];
+            float l = f2_x(in[m]), r = f2_y(in[m]);
+            if (sh0) l = __fmul_rn(sc.x, __ldg(pow43s + is0[s]));
+            if (sh1) r = __fmul_rn(sc.y, __ldg(pow43s + is1[s]));
+            in[m] = f2_make(l, r);
+          }
         }
-        __syncwarp();
       }
 
       /* ---- B: stereo (pdmp3.c:1916-1971): MS in registers ---- */
@@ -401,10 +407,10 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
           const float ux = f2_x(in[i]), uy = f2_y(in[i]), lx = f2_x(in[17 - i]), ly = f2_y(in[17 - i]);
           const float bx = __shfl_up_sync(0xffffffffu, lx, 1), by = __shfl_up_sync(0xffffffffu, ly, 1);       /* line 18sb-1-i */
           const float ax = __shfl_down_sync(0xffffffffu, ux, 1), ay = __shfl_down_sync(0xffffffffu, uy, 1);   /* line 18(sb+1)+i */
-          if (LEAN || p0.sblim == p1.sblim) {
+          if (SAME || p0.sblim == p1.sblim) {
             sw_aa(in[i], f2_make(bx, by), sw_cs(i), sw_ca(i), lo0);                              /* ub (pdmp3.c:1726) */
             sw_aa(in[17 - i], f2_make(ax, ay), sw_cs(i), -sw_ca(i), hi0);                        /* lb (pdmp3.c:1725) */
-          } else if constexpr (!LEAN) {
+          } else if constexpr (!SAME) {
             const float nux = lo0 ? __fadd_rn(__fmul_rn(ux, FC.cs[i]), __fmul_rn(bx, FC.ca[i])) : ux;
             const float nuy = lo1 ? __fadd_rn(__fmul_rn(uy, FC.cs[i]), __fmul_rn(by, FC.ca[i])) : uy;
             const float nlx = hi0 ? __fsub_rn(__fmul_rn(lx, FC.cs[i]), __fmul_rn(ax, FC.ca[i])) : lx;
@@ -419,7 +425,7 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
       {
         const uint32_t bt0 = (p0.ws && p0.mixed && sb < 2) ? 0u : p0.bt, bt1 = (p1.ws && p1.mixed && sb < 2) ? 0u : p1.bt;
         const float sgn = (sb & 1) ? -1.0f : 1.0f;
-        if (LEAN || (bt0 == bt1 && bt0 != 2)) {
+        if (LEAN || (bt0 != 2 && (SAME || bt0 == bt1))) {
           f2 t[18];
           dct4_18<f2>(in, t);
           /* 36-point IMDCT from the DCT-IV by symmetry (signs folded into swin): output p < 18 is overlap-added with
@@ -435,7 +441,7 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
           for (int k = 0; k < 9; k++) { tail[8 - k] = vmul(t[k], FC.swin[bt0][26 - k]); tail[9 + k] = vmul(t[k], FC.swin[bt0][27 + k]); }
         }
         else if constexpr (!LEAN) {
-        if (bt0 == bt1) {                                      /* short windows in both channels: three 12-point IMDCTs, packed */
+        if (SAME || bt0 == bt1) {                                      /* short windows in both channels: three 12-point IMDCTs, packed */
           f2 raw[36];
           imdct_short<f2>(in, raw);
           #pragma unroll
@@ -446,7 +452,7 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
             tail[ss] = raw[18 + ss];
           }
         }
-        else {                                                      /* different block types in the two channels: one channel at a time */
+        else if constexpr (!SAME) {                                 /* different block types in the two channels: one channel at a time */
           float *blkf = reinterpret_cast<float *>(blk);
           #pragma unroll 1
           for (int c = 0; c < 2; c++) {
@@ -535,16 +541,18 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
   }
 }
 
-#define SW_KERNEL(NAME, ISO, LEAN) \
+#define SW_KERNEL(NAME, ISO, CLS) \
 extern "C" __global__ void __launch_bounds__(SW_WPB * 32, SW_MINB) \
 NAME(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T, int64_t f_first, int64_t f_end, int frames_per_warp, \
      const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf, \
      const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm, const float *__restrict__ pow43s, int classify) \
-{ sw_body<ISO, LEAN>(frames, gcs, T, f_first, f_end, frames_per_warp, is_in, count1, scf, st_in, st_out, pcm, pow43s, classify); }
-SW_KERNEL(k_synth_warp, false, false)
-SW_KERNEL(k_synth_warp_lean, false, true)
-SW_KERNEL(k_synth_warp_iso, true, false)
-SW_KERNEL(k_synth_warp_iso_lean, true, true)
+{ sw_body<ISO, CLS>(frames, gcs, T, f_first, f_end, frames_per_warp, is_in, count1, scf, st_in, st_out, pcm, pow43s, classify); }
+SW_KERNEL(k_synth_warp, false, 0)
+SW_KERNEL(k_synth_warp_same, false, 1)
+SW_KERNEL(k_synth_warp_lean, false, 2)
+SW_KERNEL(k_synth_warp_iso, true, 0)
+SW_KERNEL(k_synth_warp_iso_same, true, 1)
+SW_KERNEL(k_synth_warp_iso_lean, true, 2)
 
 static int p3_synthw_check_consts(const float *cs, const float *ca)
 {

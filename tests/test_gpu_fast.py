@@ -148,12 +148,15 @@ def test_one_million_frames_vbr_mixed(fast_ctx):
     assert d.max() <= 1 and (d == 0).mean() > 0.9
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "k48", "crc", "c1b", "lowrate"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "k48", "crc", "c1b", "lowrate", "dual", "garbage", "loud"])
 def test_content_classes_give_the_same_bits(fast_ctx, name):
-    """The synthesis runs as two kernels: every CTA classifies its frames (long blocks of one type in both channels, no
-    intensity bit) and k_synth_warp_lean -- the body without the rare paths -- or the full k_synth_warp decodes them.
-    Whatever the split, the PCM must be bit-identical to the full kernel decoding everything (set_synth_kernel(2)); the
-    run lengths 32 / 4 / 1 move the CTA boundaries, so the same frame is decoded by either kernel."""
+    """The synthesis runs as three kernels over the same grid: every CTA classifies its frames and the kernel of that class
+    decodes them -- k_synth_warp_lean (long blocks of one type in both channels, no intensity bit: the body without any of
+    the rare paths), k_synth_warp_same (both channels of every granule agree in win_switch / block_type / mixed: no
+    one-channel-at-a-time paths) or the full k_synth_warp.  Whatever the split, the PCM must be bit-identical to the full
+    kernel decoding everything (set_synth_kernel(2)); the run lengths 32 / 4 / 1 move the CTA boundaries, so the same frame
+    is decoded by different kernels.  (joint-stereo streams of the generator share the block types between the channels,
+    "dual" / "garbage" / "loud" do not: all three classes occur.)"""
     s, _ = H.synth(400, seed=23, **VARIANTS[name])
     fast_ctx.reset(); fast_ctx.set_synth_kernel(2); full = fast_ctx.decode(s, lookahead=0)
     fast_ctx.set_synth_kernel(0)
