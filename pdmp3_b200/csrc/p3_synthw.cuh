@@ -17,7 +17,7 @@
  *     (a 36-slot ring: the 16-slot FIFO of the reference, pdmp3.c:1983) that the window stage slides over;
  *   - a warp never waits for another warp: no __syncthreads() in the frame loop, only __syncwarp();
  *   - the Huffman output of the next granules (2304 B of spectra + 128 B of scalefactors) is brought in by the
- *     TMA engine (cp.async.bulk, completion on an mbarrier) two granules ahead, no registers involved.
+ *     TMA engine (cp.async.bulk, completion on an mbarrier) while the current granule is transformed, no registers involved.
  */
 #ifndef SW_WPB
 #define SW_WPB    4                 /* warps per CTA (each one independent) */
