@@ -62,7 +62,8 @@ pdmp3_handle *pdmp3_new(const char *decoder, int *error)
     if ((p = strstr(decoder, "device="))) id->device = atoi(p + 7);
     if (strstr(decoder, "mode=exact")) id->mode = P3_MODE_EXACT;   /* bit-identical PCM; default is FAST (<= 1 LSB) */
     if (strstr(decoder, "sideinfo=host")) id->host_sideinfo = 1;   /* parse the side info on the host instead of on the device */
-    if (strstr(decoder, "iso")) id->iso = 1;                       /* ISO 11172-3 semantics instead of the reference's quirks (P3_FRAME_ISO) */
+    for (p = decoder; (p = strstr(p, "iso")) != NULL; p += 3)     /* "iso" as an option of its own: ISO 11172-3 semantics instead of the reference's quirks (P3_FRAME_ISO) */
+      if ((p == decoder || p[-1] == ':' || p[-1] == ',') && (p[3] == 0 || p[3] == ',')) id->iso = 1;
   }
   if (id->cap > (1u << 20)) { id->in = (unsigned char *)p3_host_alloc(id->cap); id->in_pinned = id->in != NULL; }   /* page-locked: full-speed H2D */
   if (!id->in) id->in = (unsigned char *)malloc(id->cap);
