@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/dbg/t_f2 tools/dbg/t_f2.cu ; run on a B200 (gpurun)
 // packed (f2) vs scalar transforms on random data: must be bit-identical
 #include <cstdio>
 #include <cstdlib>
