@@ -7,14 +7,22 @@ import p3harness as H
 ISO = dict(iso=1, mode=1, mode_ext=-1, blocks=1, count1_b_pm=400, bitrate_index=11)
 
 
-def test_table_b_and_empty_parts_round_trip():
-    s, enc = H.synth(120, seed=5, want_is=True, **ISO)
+import pytest
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(sfreq=1), dict(sfreq=2, bitrate_index=8), dict(mode=3, bitrate_index=6), dict(bitrate_index=0),
+                                dict(crc=1, garbage_pm=100)], ids=["44k", "48k", "32k", "mono", "vbr", "crc_junk"])
+def test_table_b_and_empty_parts_round_trip(kw):
+    cfg = dict(ISO); cfg.update(kw)
+    s, enc = H.synth(120, seed=5, want_is=True, **cfg)
     o = H.oracle_decode(s, lookahead=0, iso=True)
-    n = o["n_frames"]
-    f = H.gc_fields(o["gcs"]).reshape(n, 2, 2, 20)
+    n = o["n_frames"]; nch = 1 if cfg["mode"] == 3 else 2
+    f = H.gc_fields(o["gcs"]).reshape(n, 2, 2, 20)[:, :, :nch]
     assert (f[..., 17] == 1).any() and (f[..., 0] == 0).any(), "stream must hold table-B granules and empty parts"
-    assert np.array_equal(o["is_huff"], enc[:n]), "decoded spectra != encoded spectra"
-    assert (o["count1"][f[..., 0] == 0] == 0).all(), "an empty part has count1 = 0 in ISO mode"
+    assert np.array_equal(o["is_huff"][:, :, :nch], enc[:n, :, :nch]), "decoded spectra != encoded spectra"
+    assert (o["count1"][:, :, :nch][f[..., 0] == 0] == 0).all(), "an empty part has count1 = 0 in ISO mode"
+    if kw:
+        return
     # the same stream decoded the reference's way differs (table B quads are garbage there, Q1)
     c = H.oracle_decode(s, lookahead=0, iso=False)
     assert not np.array_equal(c["is_huff"], enc[:n])
