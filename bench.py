@@ -21,7 +21,7 @@ Metric: decoded PCM sample-frames per second (1152 per MP3 frame), whole job ove
 import argparse, ctypes as C, json, os, subprocess, sys, tempfile, threading, time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))       # tools/p3synth.py: the stream generator (never the test harness / oracle in the GPU arm)
 import numpy as np
 
 BLOCK = 15625
@@ -33,9 +33,9 @@ WORKLOAD_VBR = "1M-frame 44.1kHz VBR 32-320kbps joint-stereo synthetic stream, m
 
 
 def make_stream(n_frames, seed=1):
-    import p3harness as H
+    import p3synth
     nblk = (n_frames + BLOCK - 1) // BLOCK
-    blk, _ = H.synth(min(BLOCK, n_frames), seed=seed, **CFG)
+    blk, _ = p3synth.synth(min(BLOCK, n_frames), seed=seed, **CFG)
     if nblk == 1:
         return blk
     return np.tile(blk, nblk)
@@ -78,8 +78,16 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def _harness():
+    """the test harness (oracle / compiled-reference bindings): ONLY the CPU-baseline legs import it"""
+    t = os.path.join(ROOT, "tests")
+    if t not in sys.path: sys.path.insert(0, t)
+    import p3harness
+    return p3harness
+
+
 def _port_worker(args):
-    import p3harness as H
+    H = _harness()
     seed, n = args
     s, _ = H.synth(n + 2, seed=seed, **CFG)
     t0 = time.perf_counter(); o = H.oracle_decode(s, lookahead=1152, taps=False); dt = time.perf_counter() - t0
@@ -90,7 +98,7 @@ def ref_cpu_throughput(stream_block_frames, nprocs, frames_per_proc):
     """CPU arm: the unmodified reference (oracle/_ref/ref_bench, kind 'reference') on `nprocs` forked processes;
     if it did not travel with the repo, the oracle restatement (kind 'port') in a process pool.
     -> (sample-frames/s, frames, seconds, kind)"""
-    import p3harness as H
+    import p3synth
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
     if not os.path.exists(exe):
         import multiprocessing as mp
@@ -98,7 +106,7 @@ def ref_cpu_throughput(stream_block_frames, nprocs, frames_per_proc):
             t0 = time.perf_counter(); res = pool.map(_port_worker, [(3, min(frames_per_proc, 1024))] * nprocs); wall = time.perf_counter() - t0
         frames = sum(r[0] for r in res); secs = max(r[1] for r in res)
         return frames * 1152 / secs, frames, wall, "port"
-    s, _ = H.synth(frames_per_proc + 2, seed=3, **CFG)
+    s, _ = p3synth.synth(frames_per_proc + 2, seed=3, **CFG)
     d = tempfile.mkdtemp(prefix="p3bench", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     sp, op = os.path.join(d, "s.mp3"), os.path.join(d, "off.bin")
     big = np.tile(s, nprocs); big.tofile(sp)

@@ -111,6 +111,7 @@ int  p3_find_header(const uint8_t *data, uint64_t n, int *nch, int *sfreq);   /*
 
 /* page-locked host memory for stream / PCM buffers (NULL if no device is usable) */
 void *p3_host_alloc(size_t bytes);
+void *p3_host_alloc_dev(int device, size_t bytes);   /* same, after selecting `device` (no stray context on device 0) */
 void  p3_host_free(void *p);
 
 /* ---- device context ------------------------------------------------------------------------ */

@@ -5,7 +5,7 @@
  * batch descriptors of include/pdmp3_b200.h (so it also checks the host parser).  Each stage
  * cites the reference lines whose ARITHMETIC (operand order, float/double width, rounding
  * points) it follows, because the parity target is bit-exact agreement with the reference
- * compiled -O2 without FMA.  It is pinned by tests/test_oracle_vs_ref.py against the compiled
+ * compiled -O2 without FMA.  It is pinned by tests/test_cpu_oracle.py against the compiled
  * reference itself (oracle/_ref) and by the committed fixtures in tests/golden/.
  *
  * Deliberate differences from the reference (all outside the parity envelope):
@@ -76,6 +76,12 @@ typedef struct {
 static void read_scalefacs(rd_t *r, const p3_tables *T, ostate *S, const p3_frame *fr, const p3_gc *g, unsigned gr, unsigned ch)
 {
   unsigned slen1 = T->slen[P3_GC_SFCOMP(*g)][0], slen2 = T->slen[P3_GC_SFCOMP(*g)][1];
+  /* the reference reads the scalefactor bits even of a part with part2_3_length == 0 (1379-1435 run before Read_Huffman's
+   * early return, 2057-2061); ISO mode: such a part has no bits, its scalefactors are 0 */
+  if (P3_GC_P23L(*g) == 0 && (fr->flags & P3_FRAME_ISO)) {
+    memset(S->scf_l[gr][ch], 0, sizeof S->scf_l[gr][ch]); memset(S->scf_s[gr][ch], 0, sizeof S->scf_s[gr][ch]);
+    return;
+  }
   if (P3_GC_WINSW(*g) && P3_GC_BTYPE(*g) == 2) {
     unsigned first = 0;
     if (P3_GC_MIXED(*g)) { for (unsigned sfb = 0; sfb < 8; sfb++) S->scf_l[gr][ch][sfb] = rd_bits(r, slen1); first = 3; }

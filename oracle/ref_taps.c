@@ -19,7 +19,7 @@
 
 typedef struct {
   /* every pointer may be NULL; arrays are [max_frames][...] */
-  int32_t  *side;     /* [f][2][2][20] parsed side info, layout documented in tests/refharness.py */
+  int32_t  *side;     /* [f][2][2][20] parsed side info, layout documented in tests/p3harness.py (gc_fields) */
   int32_t  *hdr;      /* [f][8]  mode, mode_ext, sfreq, bitrate_index, padding, protection, main_data_begin, nch */
   uint8_t  *scf_l;    /* [f][2][2][21] */
   uint8_t  *scf_s;    /* [f][2][2][12][3] */

@@ -65,7 +65,7 @@ pdmp3_handle *pdmp3_new(const char *decoder, int *error)
     for (p = decoder; (p = strstr(p, "iso")) != NULL; p += 3)     /* "iso" as an option of its own: ISO 11172-3 semantics instead of the reference's quirks (P3_FRAME_ISO) */
       if ((p == decoder || p[-1] == ':' || p[-1] == ',') && (p[3] == 0 || p[3] == ',')) id->iso = 1;
   }
-  if (id->cap > (1u << 20)) { id->in = (unsigned char *)p3_host_alloc(id->cap); id->in_pinned = id->in != NULL; }   /* page-locked: full-speed H2D */
+  if (id->cap > (1u << 20)) { id->in = (unsigned char *)p3_host_alloc_dev(id->device, id->cap); id->in_pinned = id->in != NULL; }   /* page-locked: full-speed H2D */
   if (!id->in) id->in = (unsigned char *)malloc(id->cap);
   if (!id->in) { free(id); if (error) *error = PDMP3_ERR; return NULL; }
   id->ps.nch = id->ps.sfreq = -1; id->nch = 2; id->sfreq = 0;
@@ -170,7 +170,7 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
     p3_parsed pb;
     p3_frame *dfr = NULL; p3_gc *dgc = NULL;
     if (direct && want >= 1024) {                                             /* big batches: descriptors in page-locked memory, no allocation */
-      const int k = id->dnext; id->dnext = (k + 1) % 3;
+      const int k = id->dnext;                                                /* rotated only once the batch has been submitted (below) */
       if (!id->dfr[k]) { id->dfr[k] = (p3_frame *)p3_host_alloc(sizeof(p3_frame) * P3_API_CHUNK); id->dgc[k] = (p3_gc *)p3_host_alloc(sizeof(p3_gc) * 4 * P3_API_CHUNK); }
       if (id->dfr[k] && id->dgc[k]) { dfr = id->dfr[k]; dgc = id->dgc[k]; }
     }
@@ -208,6 +208,7 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
     p3_parsed_free(&pb);                                                     /* (the async call took the arrays over) */
     if (rc != P3_OK) { fprintf(stderr, "pdmp3_b200: %s\n", p3_last_error()); res = PDMP3_ERR; break; }
     inflight |= direct;
+    if (dfr) id->dnext = (id->dnext + 1) % 3;                                /* this descriptor buffer now belongs to an in-flight batch */
     id->ps = ps; id->ps.pcm_index = 0;
     id->sfreq = sf_last;
     if (!id->new_header) id->new_header = 1;                                 /* pdmp3.c:1318 */

@@ -70,8 +70,13 @@ struct p3_ctx {
   uint8_t next_tail[512]; int have_next_tail;
 };
 
-extern "C" void *p3_host_alloc(size_t bytes) { void *p = NULL; return cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess ? p : NULL; }
+extern "C" void *p3_host_alloc(size_t bytes) { void *p = NULL; return cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess ? p : NULL; }
+/* same, after selecting `device`: the allocation then does not create a primary context on device 0 for a decoder that runs on device N */
+extern "C" void *p3_host_alloc_dev(int device, size_t bytes) { if (cudaSetDevice(device) != cudaSuccess) return NULL; return p3_host_alloc(bytes); }
 extern "C" void p3_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+static int ctx_init(p3_ctx *c, int n_sm);
+extern "C" void p3_ctx_destroy(p3_ctx *c);
 
 extern "C" int p3_ctx_create(int device, p3_ctx **out)
 {
@@ -86,10 +91,18 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
   p3_ctx *c = (p3_ctx *)calloc(1, sizeof *c);
   if (!c) return fail(P3_ENOMEM, "calloc");
   c->device = device; c->mode = P3_MODE_EXACT;
+  const int rc = ctx_init(c, prop.multiProcessorCount);
+  if (rc != P3_OK) { char keep[sizeof g_err]; memcpy(keep, g_err, sizeof keep); p3_ctx_destroy(c); memcpy(g_err, keep, sizeof keep); return rc; }   /* nothing leaks; the caller may retry */
+  *out = c;
+  return P3_OK;
+}
+
+static int ctx_init(p3_ctx *c, int n_sm)
+{
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
-  c->n_sm = prop.multiProcessorCount;
+  c->n_sm = n_sm;
   for (int i = 0; i < 2; i++) {
     p3_slot *sl = &c->slot[i];
     CK(cudaEventCreateWithFlags(&sl->h2d_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sl->compute_done, cudaEventDisableTiming));
@@ -126,7 +139,6 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
     for (int k = 0; k < 18; k++) for (int m = 0; m < 18; m++) dct4[k * 18 + m] = (float)cos(3.14159265358979323846 / 18.0 * (k + 0.5) * (m + 0.5));
     if (p3_fused_upload_consts(p3_tables_get(), dct4) != 0) return fail(P3_ECUDA, "constant upload failed");
   }
-  *out = c;
   return P3_OK;
 }
 
@@ -139,21 +151,28 @@ static void slot_release(p3_slot *sl)
 extern "C" void p3_ctx_destroy(p3_ctx *c)
 {
   if (!c) return;
-  cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_d2h);
+  cudaSetDevice(c->device);                                /* (every member may still be NULL: p3_ctx_create cleans up through here) */
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
+  if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
   for (int i = 0; i < 2; i++) {
     p3_slot *sl = &c->slot[i];
     slot_release(sl);
     dbuf *bs[] = {&sl->raw, &sl->frames, &sl->gcs, &sl->pcm, &sl->ms};
     for (dbuf *b : bs) if (b->p) cudaFree(b->p);
-    cudaFree(sl->d_tail); cudaFree(sl->d_any_empty); cudaFreeHost(sl->h_tail);
-    cudaEventDestroy(sl->h2d_done); cudaEventDestroy(sl->compute_done); cudaEventDestroy(sl->d2h_done);
+    cudaFree(sl->d_tail); cudaFree(sl->d_any_empty); if (sl->h_tail) cudaFreeHost(sl->h_tail);
+    if (sl->h2d_done) cudaEventDestroy(sl->h2d_done);
+    if (sl->compute_done) cudaEventDestroy(sl->compute_done);
+    if (sl->d2h_done) cudaEventDestroy(sl->d2h_done);
   }
   dbuf *bs[] = {&c->is16, &c->count1, &c->scf, &c->xr, &c->y};
   for (dbuf *b : bs) if (b->p) cudaFree(b->p);
   cudaFree(c->d_tables); cudaFree(c->d_state[0]); cudaFree(c->d_state[1]); cudaFree(c->d_pow43s);
-  for (int i = 0; i < 10; i++) cudaEventDestroy(c->ev[i]);
-  cudaStreamDestroy(c->stream); cudaStreamDestroy(c->s_h2d); cudaStreamDestroy(c->s_d2h);
+  for (int i = 0; i < 10; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+  cudaGetLastError();
   free(c);
 }
 
@@ -174,6 +193,9 @@ extern "C" int p3_ctx_set_mode(p3_ctx *c, int mode)
   /* frames per kernel-sequence launch: EXACT keeps fp32 intermediates of every stage in HBM (28 KB/frame), FAST only the int16 spectra */
   c->chunk_frames = mode == P3_MODE_FAST ? (1 << 21) : (1 << 18);
   { const char *e = getenv("P3_CHUNK"); if (e && atoi(e) >= 64) c->chunk_frames = atoi(e); }
+  /* K1's shared-memory window is sized over groups of K1_FPB frames aligned to the batch start (stage_batch); a launch
+   * sequence must start on such a boundary, or a group could span more bytes than the window */
+  c->chunk_frames -= c->chunk_frames % K1_FPB;
   return P3_OK;
 }
 extern "C" int p3_ctx_set_taps(p3_ctx *c, int on) { if (!c) return P3_EINVAL; c->taps = on; return P3_OK; }

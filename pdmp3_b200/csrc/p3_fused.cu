@@ -239,7 +239,7 @@ __device__ __forceinline__ void sf_hist(const synth_sm &S)
   }
 }
 
-__device__ __forceinline__ void sf_tapC(const synth_sm &S, int slot, float *xr_tap)
+__device__ __forceinline__ void sf_tapC(const synth_sm &S, int slot, float *xr_tap, bool store)
 {
   SF_LOCALS
     /* ---- C: antialias (pdmp3.c:1706-1732).  Normally folded into stage D (below); as a separate pass only
@@ -260,7 +260,7 @@ __device__ __forceinline__ void sf_tapC(const synth_sm &S, int slot, float *xr_t
         }
       }
       __syncthreads();
-      for (int e = tid; e < 4 * 576; e += FT) xr_tap[e] = (&xs[0][0])[e];
+      if (store) for (int e = tid; e < 4 * 576; e += FT) xr_tap[e] = (&xs[0][0])[e];
     }
 
 }
@@ -478,7 +478,10 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
     const int64_t o0 = (f - f_first) * 4;
     sf_stageAB<0>(S, slot, fr, T, nch);
     __syncthreads();
-    if (xr_tap) sf_tapC(S, slot, xr_tap + o0 * 576);       /* tests only: separate antialias pass + tap (has its own barrier) */
+    /* tests only: separate antialias pass + tap (has its own barrier).  The warm-up frame of a run (decoded from zero state,
+     * its overlap is not the real one) belongs to the previous CTA: that CTA writes its taps, this one must not. */
+    const bool tap_here = !(warm && n == 0);
+    if (xr_tap) sf_tapC(S, slot, xr_tap + o0 * 576, tap_here);
     sf_hist(S);
     p3_frame frn = fr;
     if (f + 1 < c1) {
@@ -489,7 +492,7 @@ k_synth_fast(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs,
     sf_stageD(S, slot, n, xr_tap);
     __syncthreads();
     if (f + 1 < c1) sf_scale(S, slot ^ 1);
-    sf_stageE(S, n, nch, y_tap ? y_tap + o0 * 576 : NULL);
+    sf_stageE(S, n, nch, (y_tap && tap_here) ? y_tap + o0 * 576 : NULL);
     __syncthreads();
     sf_stageF<false>(S, fr, nch, emit, pcm, ce, co, ia, ib);
     fr = frn;

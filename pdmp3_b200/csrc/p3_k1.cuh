@@ -96,9 +96,12 @@ __device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw /* the CTA's
     uint32_t pos = fstart + P3_GC_START(g);
     const uint32_t part2_start = pos;
     const bool is_short = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
-    /* ---- part 2: scalefactors (pdmp3.c:1382-1435); a zero-length part carries none ---- */
+    /* ---- part 2: scalefactors (pdmp3.c:1382-1435).  The reference reads them whatever part2_3_length says: a zero-length
+     *      part still takes its slen bits from the stream (and the next part starts behind them: the parsers' part-start
+     *      rule).  ISO mode: a zero-length part carries no bits, its scalefactors are 0. ---- */
     if (ok) {
-      const uint32_t slen1 = p23l ? T->slen[P3_GC_SFCOMP(g)][0] : 0u, slen2 = p23l ? T->slen[P3_GC_SFCOMP(g)][1] : 0u;
+      const bool has2 = p23l != 0 || !(fr.flags & P3_FRAME_ISO);
+      const uint32_t slen1 = has2 ? T->slen[P3_GC_SFCOMP(g)][0] : 0u, slen2 = has2 ? T->slen[P3_GC_SFCOMP(g)][1] : 0u;
       if (is_short) {
         uint32_t first = 0;
         if (P3_GC_MIXED(g)) { for (int sfb = 0; sfb < 8; sfb++) scf[sfb] = (uint8_t)p3_getbits(sw, pos, slen1); first = 3; }
@@ -108,7 +111,9 @@ __device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw /* the CTA's
         const uint32_t scfsi = gr == 1 ? (fr.scfsi >> (4 * ch)) & 15u : 0u;
         /* granule 1 may reuse granule 0's scalefactors (scfsi): re-read them from granule 0's part 2 */
         const p3_gc g0 = gcs[4 * f + ch];
-        const bool g0_ok = !(P3_GC_WINSW(g0) && P3_GC_BTYPE(g0) == 2) && P3_GC_P23L(g0) != 0;
+        /* (granule 0 a short block: the reference copies whatever an earlier frame left in scalefac_l[0]; ISO forbids scfsi
+         *  there, and 0 is what this decoder uses -- documented deviation) */
+        const bool g0_ok = !(P3_GC_WINSW(g0) && P3_GC_BTYPE(g0) == 2) && (P3_GC_P23L(g0) != 0 || !(fr.flags & P3_FRAME_ISO)) && has2;
         const uint32_t a1 = T->slen[P3_GC_SFCOMP(g0)][0], a2 = T->slen[P3_GC_SFCOMP(g0)][1];
         const uint32_t g0pos = fstart + P3_GC_START(g0);
         #pragma unroll

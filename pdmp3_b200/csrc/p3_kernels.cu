@@ -467,6 +467,16 @@ __device__ __forceinline__ uint32_t si_get(const uint32_t (&w)[9], int pos, int 
   return v >> (32 - n);
 }
 
+/* bits of part 2 of a granule-channel, as part2_bits() of p3_parse.c (the empty-part rule of pdmp3.c:2057-2061) */
+__device__ __forceinline__ uint32_t si_part2_bits(uint32_t sfc, uint32_t ws, uint32_t bt, uint32_t mixed, uint32_t gr, uint32_t scfsi4)
+{
+  /* slen1 / slen2 (pdmp3.c:530-533), 3 bits per entry */
+  const uint32_t s1 = (uint32_t)((0x91b69224b000ull >> (3 * sfc)) & 7ull), s2 = (uint32_t)((0x69a2d1688688ull >> (3 * sfc)) & 7ull);
+  if (ws && bt == 2) return mixed ? 17 * s1 + 18 * s2 : 18 * s1 + 18 * s2;
+  if (gr == 0) scfsi4 = 0;
+  return ((scfsi4 & 1) ? 0 : 6 * s1) + ((scfsi4 & 2) ? 0 : 5 * s1) + ((scfsi4 & 4) ? 0 : 5 * s2) + ((scfsi4 & 8) ? 0 : 5 * s2);
+}
+
 template <int NCH>
 __device__ __forceinline__ void si_parse(const uint32_t (&w)[9], p3_frame &fr, p3_gc (&gc)[4], int &any_empty)
 {
@@ -499,8 +509,8 @@ __device__ __forceinline__ void si_parse(const uint32_t (&w)[9], p3_frame &fr, p
       p3_gc &g = gc[gr * 2 + ch];
       g.w0 = p23l | bigv << 12 | gain << 21 | pre << 29 | scale << 30 | c1t << 31;
       g.w1 = sfc | ws << 4 | bt << 5 | mixed << 7 | t0 << 8 | t1 << 13 | t2 << 18 | r0 << 23 | r1 << 27;
-      g.w2 = s0 | s1 << 3 | s2 << 6 | start << 9;
-      start += p23l;
+      g.w2 = s0 | s1 << 3 | s2 << 6 | (start & 0x3fffu) << 9;
+      start += p23l ? p23l : ((fr.flags & P3_FRAME_ISO) ? 0u : si_part2_bits(sfc, ws, bt, mixed, gr, ((uint32_t)fr.scfsi >> (4 * ch)) & 15u));
       if (p23l == 0) any_empty = 1;
     }
   if (start > 8u * ((uint32_t)fr.main_begin + fr.main_size)) bad = 1;          /* parts overrun the frame's data */

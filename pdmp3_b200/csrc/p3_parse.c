@@ -47,6 +47,19 @@ static inline unsigned getbits(bitrd *b, unsigned n)     /* MSB first, n <= 16 (
   return (w << sh) >> (32 - n);
 }
 
+static const uint8_t k_slen[16][2] = {{0,0},{0,1},{0,2},{0,3},{3,0},{1,1},{1,2},{1,3},{2,1},{2,2},{2,3},{3,1},{3,2},{3,3},{4,2},{4,3}};   /* pdmp3.c:530-533 */
+
+/* Bits of part 2 (scalefactors) that Read_Main_L3 reads for a granule-channel (pdmp3.c:1379-1435).  Needed for one case
+ * only: a part with part2_3_length == 0.  The reference still reads those bits and Read_Huffman returns without
+ * Set_Main_Pos (pdmp3.c:2057-2061), so the NEXT part of the frame starts behind them instead of at the prefix sum. */
+static unsigned part2_bits(unsigned sfc, unsigned ws, unsigned bt, unsigned mixed, unsigned gr, unsigned scfsi4)
+{
+  const unsigned s1 = k_slen[sfc][0], s2 = k_slen[sfc][1];
+  if (ws && bt == 2) return mixed ? 17 * s1 + 18 * s2 : 18 * s1 + 18 * s2;
+  if (gr == 0) scfsi4 = 0;
+  return ((scfsi4 & 1) ? 0 : 6 * s1) + ((scfsi4 & 2) ? 0 : 5 * s1) + ((scfsi4 & 4) ? 0 : 5 * s2) + ((scfsi4 & 8) ? 0 : 5 * s2);
+}
+
 /* side info of one frame -> 4 gc descriptors + scfsi + validation.  si points at the side info. */
 static void parse_side(const uint8_t *si, p3_frame *fr, p3_gc *gc)
 {
@@ -82,8 +95,10 @@ static void parse_side(const uint8_t *si, p3_frame *fr, p3_gc *gc)
     if (bigv > 288) bad = 1;
     g->w0 = p23l | bigv << 12 | gain << 21 | pre << 29 | scale << 30 | c1t << 31;
     g->w1 = sfc | ws << 4 | bt << 5 | mixed << 7 | ts[0] << 8 | ts[1] << 13 | ts[2] << 18 | r0 << 23 | r1 << 27;
-    g->w2 = sbg[0] | sbg[1] << 3 | sbg[2] << 6 | start << 9;
-    start += p23l;
+    g->w2 = sbg[0] | sbg[1] << 3 | sbg[2] << 6 | (start & 0x3fffu) << 9;
+    /* where the next part starts: behind this one -- or, for an empty part in reference-compatible mode, behind the
+     * scalefactor bits the reference reads regardless (ISO mode: an empty part has no bits at all) */
+    start += p23l ? p23l : ((fr->flags & P3_FRAME_ISO) ? 0u : part2_bits(sfc, ws, bt, mixed, gr, (scfsi >> (4 * ch)) & 15u));
   }
   if (start > 8u * ((unsigned)fr->main_begin + fr->main_size)) bad = 1;   /* parts overrun the frame's data */
   if (bad) fr->flags |= P3_FRAME_BAD;

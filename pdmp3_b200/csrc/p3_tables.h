@@ -2,7 +2,7 @@
  *
  * Plain C, host side.  Every floating-point table is REGENERATED here from a formula that
  * reproduces the reference's values bit for bit; nothing is pasted from
- * the reference.  tests/test_tables.py compares each table with the compiled reference
+ * the reference.  tests/test_cpu_tables.py compares each table with the compiled reference
  * (oracle/_ref/libref_taps.so).  The same struct is uploaded verbatim to the device.
  *
  * Reference data being reproduced (file:line in /root/reference/pdmp3.c):

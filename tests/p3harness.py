@@ -1,50 +1,18 @@
 """Test/bench helpers: ctypes wrappers for the synthetic stream generator (tools/libp3synth.so),
 the compiled reference with stage taps (oracle/_ref/libref_taps.so) and the oracle restatement
 (oracle/libp3_oracle.so).  TEST INFRASTRUCTURE ONLY -- nothing under pdmp3_b200/ imports this."""
-import ctypes as C, os, numpy as np
+import ctypes as C, os, sys, numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-class SynthCfg(C.Structure):
-    _fields_ = [("seed", C.c_uint64)] + [(n, C.c_int32) for n in (
-        "bitrate_index", "mode", "mode_ext", "sfreq", "blocks", "reservoir", "scalefacs", "gain",
-        "fill_pm", "crc", "count1_b_pm", "overrun_pm", "max_table", "garbage_pm", "iso")]
-
-_DEF = dict(seed=1, bitrate_index=9, mode=0, mode_ext=0, sfreq=0, blocks=0, reservoir=1, scalefacs=1,
-            gain=172, fill_pm=850, crc=0, count1_b_pm=0, overrun_pm=0, max_table=31, garbage_pm=0, iso=0)
-
-# the BASELINE.json configurations
-CONFIGS = {
-    "cfg1_128k_stereo_long": dict(bitrate_index=9, mode=0, blocks=0),
-    "cfg3_320k_js_ms":       dict(bitrate_index=14, mode=1, mode_ext=2, blocks=0),
-    "cfg4_vbr_mixed":        dict(bitrate_index=0, mode=1, mode_ext=-1, blocks=1, overrun_pm=30),
-}
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+from p3synth import synth, CONFIGS, SynthCfg          # the stream generator lives outside the test harness (bench.py uses it too)
 
 def _lib(path):
     p = os.path.join(ROOT, path)
     if not os.path.exists(p):
         return None
     return C.CDLL(p)
-
-_synth = None
-def synth(n_frames, want_is=False, **kw):
-    """-> (stream bytes as np.uint8, optional encoded spectra [n,2,2,576] int16)"""
-    global _synth
-    if _synth is None:
-        _synth = _lib("tools/libp3synth.so")
-        if _synth is None:
-            raise RuntimeError("tools/libp3synth.so missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
-        _synth.p3_synth.restype = C.c_int64
-        _synth.p3_synth.argtypes = [C.POINTER(SynthCfg), C.c_int64, C.c_void_p, C.c_uint64, C.c_void_p]
-    d = dict(_DEF); d.update(kw)
-    cfg = SynthCfg(**d)
-    cap = int(n_frames) * 1500 + 4096
-    buf = np.zeros(cap, dtype=np.uint8)
-    iso = np.zeros((n_frames, 2, 2, 576), dtype=np.int16) if want_is else None
-    n = _synth.p3_synth(C.byref(cfg), n_frames, buf.ctypes.data, cap, iso.ctypes.data if want_is else None)
-    if n < 0:
-        raise RuntimeError("p3_synth failed: %d" % n)
-    return buf[:n].copy(), iso
 
 class RefTaps(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("side", "hdr", "scf_l", "scf_s", "is_huff", "count1",
@@ -158,3 +126,19 @@ def gc_fields(gc):
     f[..., 13] = (w1 >> 23) & 15; f[..., 14] = (w1 >> 27) & 15
     f[..., 10] = w2 & 7; f[..., 11] = (w2 >> 3) & 7; f[..., 12] = (w2 >> 6) & 7
     return f
+
+
+def empty_some_parts(s, every=7):
+    """part2_3_length := 0 for a few granule-channels of a stereo stream, everything else untouched -- in particular
+    scalefac_compress, so the reference goes on reading that part's scalefactor bits and the following parts of the frame
+    start behind them (pdmp3.c:1379-1435 + 2057-2061), and count1 of the slot stays stale (Q6)."""
+    t = s.copy()
+    fr, _, _ = parse(s, lookahead=0)
+    for i, f in enumerate(fr):
+        if i % every != 3 or f["nch"] != 2: continue
+        si = int(f["main_off"]) - 32
+        k = (i // every) % 4
+        pos = 20 + 59 * k                                   # the 12 bits of part2_3_length of granule-channel k
+        for b in range(pos, pos + 12):
+            t[si + (b >> 3)] &= ~(0x80 >> (b & 7)) & 0xff
+    return t

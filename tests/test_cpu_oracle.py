@@ -37,6 +37,18 @@ def test_oracle_matches_golden(path):
     assert np.array_equal(o["frames"]["main_begin"], g["hdr"][:, 6])
 
 
+def test_oracle_matches_golden_empty_parts():
+    """integer stages of a stream with empty parts (part2_3_length == 0, scalefac_compress != 0) as the unmodified
+    reference decodes them (tests/golden/int_only/gi_empty.npz, tools/make_golden.py)"""
+    g = np.load(os.path.join(H.ROOT, "tests", "golden", "int_only", "gi_empty.npz"))
+    o = H.oracle_decode(g["stream"], lookahead=1152)
+    assert o["n_frames"] == int(g["n_frames"])
+    f = H.gc_fields(o["gcs"])
+    assert ((f[..., 0] == 0) & (f[..., 3] != 0)).sum() >= 5
+    for k in ("scf_l", "scf_s", "is_huff", "count1"):
+        assert np.array_equal(o[k], g[k]), k
+
+
 SWEEP = dict(
     cfg1=dict(H.CONFIGS["cfg1_128k_stereo_long"]), cfg3=dict(H.CONFIGS["cfg3_320k_js_ms"]), cfg4=dict(H.CONFIGS["cfg4_vbr_mixed"]),
     mono=dict(mode=3, blocks=1, bitrate_index=7), k48=dict(sfreq=1, mode=1, mode_ext=-1, blocks=1, bitrate_index=11),
@@ -44,6 +56,7 @@ SWEEP = dict(
     c1b=dict(count1_b_pm=500, mode=1, mode_ext=-1, blocks=1), garbage=dict(garbage_pm=200, blocks=1),
     nores=dict(reservoir=0, blocks=1, bitrate_index=5), dual=dict(mode=2, blocks=1, overrun_pm=200),
     loud=dict(gain=200, blocks=1), lowrate=dict(bitrate_index=1, blocks=1, mode=1, mode_ext=-1),
+    hot=dict(gain=208, peak_pm=600, blocks=1, mode=1, mode_ext=-1), fullscale=dict(gain=215, peak_pm=1000, blocks=1),
 )
 
 
@@ -60,6 +73,26 @@ def test_oracle_matches_compiled_reference(name):
         assert ok.all(), k
     nch = o["pcm"].shape[2]
     assert np.array_equal(r["pcm"][:, :, :nch], o["pcm"])
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built (reference sources absent)")
+@pytest.mark.parametrize("name", ["cfg3", "cfg4", "crc"])
+def test_empty_parts_follow_the_reference(name):
+    """A part with part2_3_length == 0 (outside the generator's envelope, G5): the reference still reads its scalefactor
+    bits (scalefac_compress is whatever the stream says) and does NOT reposition, so the following parts of the frame start
+    behind those bits; count1 of the slot stays stale (Q6).  Integer stages -- scalefactors, Huffman output, count1 --
+    must match the compiled reference bit for bit (the float stages are outside the envelope here: the shifted bits no
+    longer keep the sfb-0 scalefactors at 0, which is what makes Q5's out-of-bounds reads defined)."""
+    s, _ = H.synth(220, seed=33, **SWEEP[name])
+    t = H.empty_some_parts(s)
+    fr, gc, info = H.parse(t, lookahead=1152)
+    f = H.gc_fields(gc)
+    empties = (f[..., 0] == 0)
+    assert empties.sum() > 20 and (f[..., 3][empties] != 0).any(), "need empty parts with scalefac_compress != 0"
+    r = H.ref_decode(t); o = H.oracle_decode(t, lookahead=1152)
+    assert r["n_frames"] == o["n_frames"] > 200
+    for k in ("scf_l", "scf_s", "is_huff", "count1"):
+        assert np.array_equal(r[k], o[k]), k
 
 
 def test_generator_roundtrip():

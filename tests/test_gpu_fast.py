@@ -127,6 +127,30 @@ def test_one_million_frames_properties(fast_ctx):
     assert d.max() <= 1 and (d == 0).mean() > 0.9
 
 
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref did not travel with the repo")
+@pytest.mark.parametrize("workload", ["cbr320", "vbr"])
+def test_bench_block_against_the_compiled_reference(fast_ctx, workload):
+    """The exact block bench.py tiles its 1 M-frame workloads from (15 625 frames, seed 1; cbr320 = BASELINE configs[2],
+    vbr = configs[3]) decoded by the UNMODIFIED reference: FAST mode (the kernels the bench times) within 1 LSB on every
+    sample, EXACT mode bit-identical."""
+    import pdmp3_b200, bench
+    cfg = bench.CFG if workload == "cbr320" else bench.CFG_VBR
+    blk, _ = H.synth(bench.BLOCK, seed=1, **cfg)
+    r = H.ref_decode(blk, taps=False)
+    n = r["n_frames"]
+    assert n >= bench.BLOCK - 2                                   # the 1152-byte rule keeps the last frame(s) back (Q7)
+    fast_ctx.reset()
+    pcm = fast_ctx.decode(blk, lookahead=1152, hop_only=True)
+    assert pcm.shape[0] == n
+    d = np.abs(pcm.astype(np.int32) - r["pcm"].astype(np.int32))
+    assert d.max() <= PCM_TOL_LSB, "max |diff| = %d LSB" % d.max()
+    assert (d == 0).mean() > 0.90
+    ex = pdmp3_b200.Context(0, pdmp3_b200.MODE_EXACT)
+    two = ex.decode(blk, lookahead=1152)
+    ex.close()
+    assert np.array_equal(two, r["pcm"])
+
+
 def test_one_million_frames_vbr_mixed(fast_ctx):
     """BASELINE configs[3] at full size (divergence stress): 1 000 000 frames of VBR 32-320 kbps joint stereo with long,
     short and mixed blocks, MS and intensity stereo (a 15 625-frame block tiled 64x, 0.42 GB in, 4.6 GB of PCM out).

@@ -20,7 +20,26 @@ VARIANTS = dict(
     dual=dict(mode=2, blocks=1, overrun_pm=200),
     loud=dict(gain=200, blocks=1),
     lowrate=dict(bitrate_index=1, blocks=1, mode=1, mode_ext=-1),
+    # near full scale (table precision "matters for loud signals"): PCM rms 15.8k / 21k LSB, 7 % / 23 % of the samples clipped
+    hot=dict(gain=208, peak_pm=600, blocks=1, mode=1, mode_ext=-1),
+    fullscale=dict(gain=215, peak_pm=1000, blocks=1),
 )
+
+
+def live_scalefactors(gc, nch):
+    """masks [n,2,2,21] / [n,2,2,12,3] of the scalefactor cells Read_Main_L3 writes for each granule-channel
+    (pdmp3.c:1382-1435): long blocks l[0..20]; short s[0..11]; mixed l[0..7] + s[3..11].  The other cells keep
+    whatever an earlier frame left there in the reference (and in the oracle), while K1 writes zeros."""
+    f = H.gc_fields(gc)
+    short = (f[..., 4] == 1) & (f[..., 5] == 2)
+    mixed = short & (f[..., 6] == 1)
+    ml = np.zeros(gc.shape[:2] + (21,), bool); ms = np.zeros(gc.shape[:2] + (12, 3), bool)
+    ml[~short] = True; ml[mixed, :8] = True
+    ms[short & ~mixed] = True; ms[mixed, 3:] = True
+    n = gc.shape[0]
+    ml = ml.reshape(n, 2, 2, 21); ms = ms.reshape(n, 2, 2, 12, 3)
+    ml[:, :, nch:] = False; ms[:, :, nch:] = False
+    return ml, ms
 
 
 def feq(a, b):
@@ -39,6 +58,9 @@ def test_stage_taps_exact_vs_oracle(gpu_ctx, name):
     nch = pcm.shape[2]
     assert np.array_equal(t["is_huff"][:, :, :nch], o["is_huff"][:, :, :nch]), "Huffman output"
     assert np.array_equal(t["count1"][:, :, :nch], o["count1"][:, :, :nch]), "count1"
+    ml, ms = live_scalefactors(o["gcs"], nch)
+    assert np.array_equal(t["scf_l"][ml], o["scf_l"][ml]) and np.array_equal(t["scf_s"][ms], o["scf_s"][ms]), "scalefactors"
+    assert t["scf_l"][ml].any() and (name != "cfg4" or t["scf_s"][ms].any())
     assert feq(t["xr"][:, :, :nch], o["xr_ali"][:, :, :nch]).all(), "requantize/reorder/stereo/antialias"
     assert feq(t["y"][:, :, :nch], o["y_hyb"][:, :, :nch]).all(), "hybrid synthesis"
     assert np.array_equal(pcm, o["pcm"]), "PCM"
@@ -46,6 +68,22 @@ def test_stage_taps_exact_vs_oracle(gpu_ctx, name):
         r = H.ref_decode(s, taps=False)
         ref = r["pcm"] if nch == 2 else r["pcm"][:, :, :1]
         assert np.array_equal(pcm, ref), "PCM vs compiled reference"
+
+
+@pytest.mark.parametrize("name", ["cfg3", "cfg4", "crc"])
+def test_empty_parts_integer_stages(gpu_ctx, name):
+    """parts with part2_3_length == 0 but scalefac_compress != 0 (tests/test_cpu_oracle.py pins this rule to the compiled
+    reference): scalefactor bits are still read, the next part starts behind them, count1 stays stale -- K1's
+    scalefactors, spectra and count1 against the oracle, with the side info parsed on the host and on the device."""
+    s, _ = H.synth(220, seed=33, **VARIANTS[name])
+    t = H.empty_some_parts(s)
+    o = H.oracle_decode(t, lookahead=1152)
+    ml, ms = live_scalefactors(o["gcs"], 2)
+    for hop_only in (False, True):
+        gpu_ctx.reset()
+        pcm, tp = gpu_ctx.decode(t, lookahead=1152, taps=True, hop_only=hop_only)
+        assert np.array_equal(tp["is_huff"], o["is_huff"]) and np.array_equal(tp["count1"], o["count1"])
+        assert np.array_equal(tp["scf_l"][ml], o["scf_l"][ml]) and np.array_equal(tp["scf_s"][ms], o["scf_s"][ms])
 
 
 def test_exact_batches_with_carried_state(gpu_ctx):

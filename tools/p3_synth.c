@@ -304,7 +304,7 @@ int64_t p3_synth(const p3_synth_cfg *cfg, int64_t n_frames, uint8_t *out, uint64
       else encode_gc(&rg, cfg, &w, g, budget, gr, (unsigned)ch, scfsi[ch], intensity && ch == (cfg->iso ? 1 : 0), sf,
                      gr == 0 ? scf0[ch] : NULL, is_out ? is_out + (((size_t)f * 2 + gr) * 2 + (size_t)ch) * 576 : NULL, &c1, &mx);
       if (mx > 1) {   /* keep the loudest line below ~0.3 of full scale so that clipping stays rare */
-        int lim = 210 + (int)floor(4.0 * log2(0.30 / pow((double)mx, 4.0 / 3.0)));
+        int lim = 210 + (int)floor(4.0 * log2((cfg->peak_pm > 0 ? cfg->peak_pm * 1e-3 : 0.30) / pow((double)mx, 4.0 / 3.0)));
         if ((int)g->gain > lim) g->gain = (unsigned)(lim < 0 ? 0 : lim);
       }
     }

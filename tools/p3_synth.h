@@ -24,6 +24,8 @@ typedef struct {
   int32_t iso;             /* 1: stream for the ISO mode of the decoder (P3_FRAME_ISO), outside the reference's envelope:
                               intensity stereo also with short blocks in channel 0 (G6 lifted), intensity positions <= 7 in
                               the RIGHT channel's scalefactors, 3 % of the parts empty (part2_3_length = 0, G5 lifted)      */
+  int32_t peak_pm;         /* loudest spectral line allowed, per mille of full scale (0 = the default 300: clipping stays rare);
+                              ~2000-4000 with a high `gain` gives near-full-scale PCM with a clip fraction around 1e-3 */
 } p3_synth_cfg;
 
 /* Writes n_frames frames.  Returns bytes written or <0 if `cap` is too small.
