@@ -123,6 +123,61 @@ def ref_cpu_throughput(stream_block_frames, nprocs, frames_per_proc):
     return best[0] * 1152 / best[1], best[0], best[1], "reference"
 
 
+def bench_xr(a, rank, world, local):
+    """--workload xr = BASELINE configs[1]: 65 536 frames of 44.1 kHz 128 kbps stereo, Huffman .. antialias done beforehand, the
+    device runs the two transform kernels only (k_imdct + k_polyphase, P3_MODE_EXACT: bit-identical PCM).  `value`: spectra
+    [65536][2][2][576] fp32 resident in HBM; e2e: p3_synth_from_xr() with the spectra in pinned host memory (604 MB H2D + 302 MB D2H)."""
+    import torch, p3synth, pdmp3_b200
+    torch.cuda.set_device(local)
+    sys.stdout.flush(); _stdout_fd = os.dup(1); os.dup2(2, 1)
+    nf = min(a.frames, 65536)
+    blk, _ = p3synth.synth(min(4096, nf), seed=2, **p3synth.CONFIGS["cfg1_128k_stereo_long"])
+    stream = np.tile(blk, (nf + 4095) // 4096) if nf > 4096 else blk
+    ctx = pdmp3_b200.Context(local, pdmp3_b200.MODE_EXACT)
+    parsed = pdmp3_b200.parse_stream(stream, lookahead=0)
+    n_frames = parsed.n_pcm_frames
+    ctx.upload(parsed); ctx.run(); ctx.sync()                # fills the device-resident spectra (the xr tap buffer of EXACT mode)
+    ctx.time_xr(max(a.warmup, 3))
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    ms, st = ctx.time_xr(a.steps)
+    torch.cuda.synchronize()
+    e2e = None
+    if not a.no_e2e:
+        ctx.reset()
+        pcm, taps = ctx.decode_parsed(parsed, taps=True)
+        hx = torch.empty(taps["xr"].shape, dtype=torch.float32).pin_memory(); hx.numpy()[:] = taps["xr"]; del taps
+        hp = torch.empty(n_frames * 1152 * 2, dtype=torch.int16).pin_memory()
+        L = pdmp3_b200.lib(); times = []
+        for it in range(1 + a.steps):
+            ctx.reset(); torch.cuda.synchronize(); t0 = time.perf_counter()
+            rc = L.p3_synth_from_xr(ctx.h, hx.data_ptr(), C.byref(parsed.c), hp.data_ptr()); assert rc == 0, rc
+            dt = time.perf_counter() - t0
+            if it >= 1: times.append(dt)
+        assert np.array_equal(hp.numpy().reshape(pcm.shape), pcm)
+        dt = float(np.median(times))
+        e2e = {"value": n_frames * 1152 / dt, "unit": "sample-frames/s", "h2d_bytes_per_step": int(hx.numel() * 4 + n_frames * 96),
+               "d2h_bytes_per_step": int(hp.numel() * 2), "ms_per_step": 1e3 * dt,
+               "api": "p3_synth_from_xr() with pinned host spectra and PCM buffers; H2D, k_imdct, k_polyphase, D2H inside the timed region"}
+    clocks = sampler.stop()
+    peak, peak_src = peaks()
+    alg = 13824.0 * n_frames
+    names = ["k_imdct", "k_polyphase"]; dom = int(np.argmax(st))
+    roof = {"bound": "fp32 FFMA/LSU (direct-form transforms in the reference's summation order); labelled against HBM as SURVEY 8d asks",
+            "kernel": names[dom], "achieved": alg / (st[dom] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (st[dom] * 1e-3) / 1e9 / peak,
+            "traffic": None, "algorithmic_bytes": alg, "algorithmic_bytes_per_frame": 13824.0, "peak_source": peak_src,
+            "whole_path": {"achieved": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak}, "stage_ms": dict(zip(names, st))}
+    sys.stdout.flush(); os.dup2(_stdout_fd, 1)
+    v = n_frames * 1152 / (ms * 1e-3)
+    print(json.dumps({"metric": "decoded_pcm_sample_frames_per_sec", "value": v, "unit": "sample-frames/s", "x_realtime_44k1": v / 44100.0,
+                      "n_gpus": 1, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "65536-frame 44.1kHz 128kbps stereo batch, IMDCT+polyphase kernels only, spectra after antialias resident in HBM (BASELINE configs[1])",
+                                 "frames_per_gpu": int(n_frames), "mode": "exact", "l2": "604 MB in + 302 MB out per step exceed the 126 MB L2; no flush needed"},
+                      "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * a.steps, "roofline": roof, "cpu_baseline": None}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -133,7 +188,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["exact", "fast"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="cbr320", choices=["cbr320", "vbr"], help="cbr320 = BASELINE configs[2] (headline); vbr = configs[3]")
+    ap.add_argument("--workload", default="cbr320", choices=["cbr320", "vbr", "xr"], help="cbr320 = BASELINE configs[2] (headline); vbr = configs[3]; xr = configs[1] (transform kernels only)")
     a = ap.parse_args()
     global CFG, WORKLOAD
     if a.workload == "vbr": CFG, WORKLOAD = CFG_VBR, WORKLOAD_VBR
@@ -165,6 +220,8 @@ def main():
     import pdmp3_b200
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the decoder has no CPU fallback")
+    if a.workload == "xr":
+        return bench_xr(a, rank, world, local) if rank == 0 else 0
     torch.cuda.set_device(local)
     # stdout carries exactly ONE JSON line: whatever libraries print there meanwhile (NCCL's version banner ...) goes to stderr
     sys.stdout.flush(); _stdout_fd = os.dup(1); os.dup2(2, 1)

@@ -167,6 +167,7 @@ int p3_batch_download_desc(p3_ctx *c, p3_frame *frames, p3_gc *gcs);   /* the de
 void *p3_batch_pcm_device(p3_ctx *c, uint64_t *bytes);
 void *p3_ctx_stream(p3_ctx *c);                       /* cudaStream_t of the context */
 int  p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_stage /*[8]: k_compact, K1, K2 or the fused synthesis, K3, K4*/);  /* CUDA-event timing of p3_batch_run */
+int  p3_batch_time_xr(p3_ctx *c, int iters, float *ms_total, float *ms_stage /*[2]: k_imdct, k_polyphase*/);   /* BASELINE configs[1] resident in HBM: the two transform kernels over the spectra a P3_MODE_EXACT run of the batch left on the device */
 int  p3_kernel_launch_count(p3_ctx *c);               /* kernels launched by the last p3_batch_run */
 
 #ifdef __cplusplus

@@ -80,6 +80,7 @@ def lib():
     L.p3_ctx_stream.argtypes = [C.c_void_p]
     L.p3_ctx_stream.restype = C.c_void_p
     L.p3_batch_time.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.p3_batch_time_xr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.p3_kernel_launch_count.argtypes = [C.c_void_p]
     for name in ("pdmp3_new", "pdmp3_delete", "pdmp3_open_feed", "pdmp3_feed", "pdmp3_read", "pdmp3_decode", "pdmp3_getformat"):
         if not hasattr(L, name):
@@ -231,6 +232,12 @@ class Context:
         tot = C.c_float(); st = (C.c_float * 8)()
         _check(lib().p3_batch_time(self.h, iters, C.byref(tot), st), "p3_batch_time")
         return tot.value, [st[i] for i in range(5)]
+
+    def time_xr(self, iters=5):
+        """configs[1]: k_imdct + k_polyphase over the device-resident spectra of the last EXACT run -> (ms, [ms_imdct, ms_polyphase])"""
+        tot = C.c_float(); st = (C.c_float * 2)()
+        _check(lib().p3_batch_time_xr(self.h, iters, C.byref(tot), st), "p3_batch_time_xr")
+        return tot.value, [st[0], st[1]]
 
     def launch_count(self):
         return lib().p3_kernel_launch_count(self.h)

@@ -527,3 +527,42 @@ extern "C" int p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_st
   if (ms_stage) for (int k = 0; k < 5; k++) ms_stage[k] = st[k] / iters;
   return P3_OK;
 }
+
+/* BASELINE configs[1] with everything resident in HBM: the batch must have been run once in P3_MODE_EXACT as ONE launch
+ * sequence (n_frames <= chunk), so that c->xr holds the spectra after requantize / reorder / stereo / antialias; times
+ * k_imdct + k_polyphase reading them, `iters` times, from the same carried state.  ms_stage: [0] k_imdct, [1] k_polyphase. */
+extern "C" int p3_batch_time_xr(p3_ctx *c, int iters, float *ms_total, float *ms_stage)
+{
+  if (!c || iters <= 0) return fail(P3_EINVAL, "bad argument");
+  if (c->mode != P3_MODE_EXACT || c->n_frames == 0 || c->n_frames > c->chunk_frames || !c->xr.p || !c->y.p)
+    return fail(P3_EINVAL, "p3_batch_time_xr needs a batch run in P3_MODE_EXACT as one launch sequence");
+  CK(cudaSetDevice(c->device));
+  p3_slot *sl = &c->slot[c->cur_slot];
+  const p3_frame *fr = (const p3_frame *)sl->frames.p; const p3_gc *gc = (const p3_gc *)sl->gcs.p;
+  const int64_t nf = c->n_frames;
+  p3_state *save; CK(cudaMalloc(&save, sizeof(p3_state)));
+  CK(cudaMemsetAsync(save, 0, sizeof(p3_state), c->stream));
+  float tot = 0, st[2] = {0, 0};
+  const size_t smem4 = (size_t)(2048 + 512 + 2 * (15 + K4_SLOTS) * 96) * 4;
+  for (int it = 0; it < iters; it++) {
+    p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
+    CK(cudaMemcpyAsync(si, save, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(so, save, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    k_imdct<<<(unsigned)(4 * nf), K3_THREADS, 0, c->stream>>>(fr, gc, c->d_tables, 0, nf, (const float *)c->xr.p, si, so, (float *)c->y.p);
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    k_polyphase<<<(unsigned)((2 * nf + K4_GRAN - 1) / K4_GRAN), K4_THREADS, smem4, c->stream>>>(fr, c->d_tables, 0, nf, (const float *)c->y.p, si, so, (int16_t *)sl->pcm.p);
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[1])); st[0] += ms;
+    CK(cudaEventElapsedTime(&ms, c->ev[1], c->ev[2])); st[1] += ms;
+    CK(cudaEventElapsedTime(&ms, c->ev[0], c->ev[2])); tot += ms;
+  }
+  cudaFree(save);
+  c->launches = 2;
+  if (ms_total) *ms_total = tot / iters;
+  if (ms_stage) { ms_stage[0] = st[0] / iters; ms_stage[1] = st[1] / iters; }
+  return P3_OK;
+}
