@@ -160,6 +160,20 @@ int p3_decode_batch_async(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, p3_
 /* Device-resident variant used by the benchmark and the multi-GPU driver: upload once, run the
  * kernels any number of times, download once.  Pointers returned are DEVICE pointers. */
 int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *batch);
+/* Same, but from RAW BYTES: the frame hop (Search_Header / Read_Header, pdmp3.c:1322-1340, 1252-1320; frame length 1353-1368;
+ * reservoir rule of Get_Main_Data 1101-1120) runs ON THE DEVICE (p3_hop.cu) and produces the p3_frame[] array that p3_parse()
+ * computes on the host, byte for byte; the side info follows on the device as with hop_only.  raw: host memory, or device
+ * memory when raw_on_device.  opts (lookahead, max_frames, warmup_frames, iso) and *state as for p3_parse(); *info receives
+ * n_frames / n_pcm_frames / consumed / stop (frames and gcs stay NULL: the descriptors exist on the device only,
+ * p3_batch_download_desc() fetches them).  The state is not advanced: p3_decode_raw() does that. */
+int p3_batch_upload_raw(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, int raw_on_device, const p3_parse_opts *opts,
+                        const p3_parse_state *state, p3_parsed *info);
+int p3_batch_channels(p3_ctx *c);                     /* channels of the staged batch (1 or 2) */
+int p3_hop_rounds(p3_ctx *c);                         /* resolution rounds the last device hop needed (1 = every speculative chain met the true one) */
+/* device hop + decode + download in one call: the counterpart of p3_parse() + p3_decode_batch(); *state is advanced,
+ * info->consumed says where the next call continues; at most pcm_cap_frames frames are decoded (<= 0: no limit) */
+int p3_decode_raw(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parse_opts *opts, p3_parse_state *state, p3_parsed *info,
+                  int16_t *pcm, int64_t pcm_cap_frames, const p3_taps *host_taps);
 int p3_batch_run(p3_ctx *c);                          /* launches the kernel sequence on the ctx stream */
 int p3_batch_sync(p3_ctx *c);
 int p3_batch_download(p3_ctx *c, int16_t *pcm, const p3_taps *host_taps);

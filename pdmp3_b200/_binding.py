@@ -71,6 +71,11 @@ def lib():
     L.p3_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3Parsed), C.c_void_p, C.POINTER(P3Taps)]
     L.p3_synth_from_xr.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(P3Parsed), C.c_void_p]
     L.p3_batch_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3Parsed)]
+    L.p3_batch_upload_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(P3ParseOpts), C.POINTER(P3ParseState), C.POINTER(P3Parsed)]
+    L.p3_decode_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3ParseOpts), C.POINTER(P3ParseState), C.POINTER(P3Parsed),
+                                C.c_void_p, C.c_int64, C.POINTER(P3Taps)]
+    L.p3_hop_rounds.argtypes = [C.c_void_p]
+    L.p3_batch_channels.argtypes = [C.c_void_p]
     L.p3_batch_run.argtypes = [C.c_void_p]
     L.p3_batch_sync.argtypes = [C.c_void_p]
     L.p3_batch_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(P3Taps)]
@@ -204,6 +209,42 @@ class Context:
         pcm = np.zeros((parsed.n_pcm_frames, 1152, parsed.nch), np.int16)
         _check(lib().p3_synth_from_xr(self.h, xr.ctypes.data, C.byref(parsed.c), pcm.ctypes.data), "p3_synth_from_xr")
         return pcm
+
+    # batches staged from raw bytes: the frame hop runs on the device (p3_hop.cu)
+    def upload_raw(self, stream, lookahead=0, max_frames=0, warmup=0, iso=False, state=None):
+        """-> dict(n_frames, n_pcm_frames, consumed, stop, nch, rounds); the descriptors stay on the device (download_desc)"""
+        self._raw = np.ascontiguousarray(stream, dtype=np.uint8)
+        o = P3ParseOpts(max_frames, lookahead, 0, warmup, 1, 1 if iso else 0)
+        st = state if state is not None else P3ParseState(0, 0, 0, -1, -1)
+        info = P3Parsed()
+        _check(lib().p3_batch_upload_raw(self.h, self._raw.ctypes.data if len(self._raw) else None, len(self._raw), 0, C.byref(o), C.byref(st), C.byref(info)), "p3_batch_upload_raw")
+        self._up = None
+        return dict(n_frames=info.n_frames, n_pcm_frames=info.n_pcm_frames, consumed=info.consumed, stop=info.stop, rounds=lib().p3_hop_rounds(self.h),
+                    nch=lib().p3_batch_channels(self.h))
+
+    def download_raw(self, info):
+        """PCM of the batch staged by upload_raw() (after run())"""
+        pcm = np.zeros((info["n_pcm_frames"], 1152, info["nch"]), np.int16)
+        _check(lib().p3_batch_download(self.h, pcm.ctypes.data, None), "p3_batch_download")
+        return pcm
+
+    def decode_raw(self, stream, lookahead=0, max_frames=0, warmup=0, iso=False, state=None, taps=False):
+        """device hop + decode: -> (pcm [n_pcm_frames,1152,nch], info dict[, taps])"""
+        raw = np.ascontiguousarray(stream, dtype=np.uint8)
+        o = P3ParseOpts(max_frames, lookahead, 0, warmup, 1, 1 if iso else 0)
+        st = state if state is not None else P3ParseState(0, 0, 0, -1, -1)
+        info = P3Parsed()
+        cap = max_frames if max_frames > 0 else len(raw) // 96 + 16
+        pcm = np.zeros(cap * 1152 * 2, np.int16)
+        arrs, t = self._taps(cap) if taps else ({}, None)
+        _check(lib().p3_decode_raw(self.h, raw.ctypes.data if len(raw) else None, len(raw), C.byref(o), C.byref(st), C.byref(info), pcm.ctypes.data, cap,
+                                   C.byref(t) if taps else None), "p3_decode_raw")
+        nch = lib().p3_batch_channels(self.h)
+        d = dict(n_frames=info.n_frames, n_pcm_frames=info.n_pcm_frames, consumed=info.consumed, stop=info.stop, rounds=lib().p3_hop_rounds(self.h), nch=nch)
+        pcm = pcm[:info.n_pcm_frames * 1152 * nch].reshape(info.n_pcm_frames, 1152, nch)
+        if taps:
+            return pcm, d, {k: a[:info.n_frames] for k, a in arrs.items()}
+        return pcm, d
 
     # device-resident path (bench)
     def upload(self, parsed):

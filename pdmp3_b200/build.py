@@ -32,7 +32,7 @@ def build_product(force=False, verbose=False):
     gcc = shutil.which("gcc") or "gcc"
     out = os.path.join(ROOT, "pdmp3_b200", "libpdmp3_b200.so")
     srcs_c = ["p3_tables.c", "p3_parse.c", "p3_api.c"]
-    srcs_cu = ["p3_kernels.cu", "p3_fused.cu", "p3_cabi.cu"]
+    srcs_cu = ["p3_kernels.cu", "p3_fused.cu", "p3_hop.cu", "p3_cabi.cu"]
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
     if not force and not _newer(out, deps):
         return out

@@ -3,6 +3,7 @@
  * kernel launch sequence K1..K4, which is the device-side Decode_L3 (pdmp3.c:1024-1060). */
 #include "p3_device.cuh"
 #include "p3_kernels.h"
+#include "p3_hop.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -68,6 +69,9 @@ struct p3_ctx {
   int launches; int launches_parse; int taps; int fpc;
   float *d_pow43s; int synth_kernel;      /* signed |is|^(4/3) table (k_synth_warp); 0 = pick, 1 = always k_synth_fast, 2 = k_synth_warp without content classes */
   uint8_t next_tail[512]; int have_next_tail;
+  /* device-side frame hop (p3_hop.cu): scratch, and the reservoir carry kept on the device for batches staged from raw bytes */
+  p3_hop_work hop;
+  uint8_t *d_tail_cur, *d_tail_nxt; int tail_on_device, have_next_tail_dev;
 };
 
 extern "C" void *p3_host_alloc(size_t bytes) { void *p = NULL; return cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess ? p : NULL; }
@@ -112,6 +116,8 @@ static int ctx_init(p3_ctx *c, int n_sm)
     CK(cudaHostAlloc((void **)&sl->h_tail, 512, cudaHostAllocDefault)); memset(sl->h_tail, 0, 512);
   }
   for (int i = 0; i < 10; i++) CK(cudaEventCreate(&c->ev[i]));
+  CK(cudaMalloc(&c->d_tail_cur, 512)); CK(cudaMemset(c->d_tail_cur, 0, 512));
+  CK(cudaMalloc(&c->d_tail_nxt, 512)); CK(cudaMemset(c->d_tail_nxt, 0, 512));
   CK(cudaMalloc(&c->d_tables, sizeof(p3_tables)));
   CK(cudaMemcpy(c->d_tables, p3_tables_get(), sizeof(p3_tables), cudaMemcpyHostToDevice));
   for (int i = 0; i < 2; i++) { CK(cudaMalloc(&c->d_state[i], sizeof(p3_state))); CK(cudaMemset(c->d_state[i], 0, sizeof(p3_state))); }
@@ -168,6 +174,7 @@ extern "C" void p3_ctx_destroy(p3_ctx *c)
   dbuf *bs[] = {&c->is16, &c->count1, &c->scf, &c->xr, &c->y};
   for (dbuf *b : bs) if (b->p) cudaFree(b->p);
   cudaFree(c->d_tables); cudaFree(c->d_state[0]); cudaFree(c->d_state[1]); cudaFree(c->d_pow43s);
+  cudaFree(c->d_tail_cur); cudaFree(c->d_tail_nxt); p3_hop_work_free(&c->hop);
   for (int i = 0; i < 10; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
@@ -183,6 +190,7 @@ extern "C" int p3_ctx_reset(p3_ctx *c)
   CK(cudaStreamSynchronize(c->s_h2d)); CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(c->s_d2h));
   for (int i = 0; i < 2; i++) { slot_release(&c->slot[i]); CK(cudaMemset(c->d_state[i], 0, sizeof(p3_state))); }
   memset(c->h_tail, 0, 512); c->have_next_tail = 0;
+  CK(cudaMemset(c->d_tail_cur, 0, 512)); c->tail_on_device = 0; c->have_next_tail_dev = 0;
   return P3_OK;
 }
 
@@ -216,6 +224,41 @@ static void compute_tail(const uint8_t *raw, const p3_parsed *b, const uint8_t p
   if (filled < 512) memcpy(out, prev_tail + filled, (size_t)(512 - filled));
 }
 
+/* the batch just decoded becomes history: its last 512 main-data bytes are the reservoir of the next batch */
+static void commit_tail(p3_ctx *c)
+{
+  if (c->have_next_tail) { memcpy(c->h_tail, c->next_tail, 512); c->have_next_tail = 0; c->tail_on_device = 0; }
+  if (c->have_next_tail_dev) { uint8_t *t = c->d_tail_cur; c->d_tail_cur = c->d_tail_nxt; c->d_tail_nxt = t; c->have_next_tail_dev = 0; c->tail_on_device = 1; }
+}
+
+/* device buffers of a batch of nf frames (npcm of them with a PCM slot), K1's shared-memory window for groups spanning at
+ * most maxg bytes of main data, the compact main-data stream of total_ms bytes */
+static int size_batch(p3_ctx *c, p3_slot *sl, int64_t nf, int64_t npcm, uint64_t maxg, uint64_t total_ms, cudaStream_t st)
+{
+  int rc;
+  if ((rc = ensure(&sl->frames, (size_t)(nf ? nf : 1) * sizeof(p3_frame)))) return rc;
+  if ((rc = ensure(&sl->gcs, (size_t)(nf ? nf : 1) * 4 * sizeof(p3_gc)))) return rc;
+  if ((rc = ensure(&sl->pcm, (size_t)(npcm ? npcm : 1) * 1152 * c->nch * sizeof(int16_t)))) return rc;
+  const int64_t cf = nf < c->chunk_frames ? nf : c->chunk_frames;
+  if (cf) {
+    if ((rc = ensure(&c->is16, (size_t)cf * 4 * 576 * 2))) return rc;
+    if ((rc = ensure(&c->count1, (size_t)cf * 4 * 4))) return rc;
+    if ((rc = ensure(&c->scf, (size_t)cf * 4 * P3_SCF_STRIDE))) return rc;
+    if (c->mode == P3_MODE_EXACT || c->taps) {
+      if ((rc = ensure(&c->xr, (size_t)cf * 4 * 576 * 4))) return rc;
+      if ((rc = ensure(&c->y, (size_t)cf * 4 * 576 * 4))) return rc;
+    }
+  }
+  /* K1 shared-memory window: 512 reservoir bytes + the largest group of K1_FPB frames (+ alignment and read-ahead slack) */
+  c->k1_smem_words = (uint32_t)(((512 + maxg + 64 + 15) & ~(uint64_t)15) / 4);
+  if ((size_t)c->k1_smem_words * 4 + sizeof(((p3_tables *)0)->hlut) + 4 * K1_THREADS * 4 > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
+  /* compact main-data stream: 512 reservoir bytes + all main data of the batch, zero padded (the bit readers run a few words ahead) */
+  sl->ms_bytes = 512 + total_ms;
+  if ((rc = ensure(&sl->ms, sl->ms_bytes + 512))) return rc;
+  CK(cudaMemsetAsync((uint8_t *)sl->ms.p + (sl->ms_bytes & ~(uint64_t)3), 0, 128, st));
+  return P3_OK;
+}
+
 /* Stage a parsed batch in slot `sl`: allocate, size K1's window, enqueue the uploads on `st`. */
 static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_bytes, const p3_parsed *b, cudaStream_t st)
 {
@@ -226,33 +269,18 @@ static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_
   for (int64_t f = 1; f < nf; f++)
     if (b->frames[f].nch != c->nch) return fail(P3_EINVAL, "channel count changes inside a batch (frame %lld)", (long long)f);
   int rc;
+  if (c->tail_on_device) {                                 /* the previous batch was staged from raw bytes: its reservoir carry lives on the device */
+    CK(cudaMemcpyAsync(sl->h_tail, c->d_tail_cur, 512, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    memcpy(c->h_tail, sl->h_tail, 512); c->tail_on_device = 0;
+  }
   if ((rc = ensure(&sl->raw, raw_bytes + 64))) return rc;
-  if ((rc = ensure(&sl->frames, (size_t)nf * sizeof(p3_frame)))) return rc;
-  if ((rc = ensure(&sl->gcs, (size_t)nf * 4 * sizeof(p3_gc)))) return rc;
-  if ((rc = ensure(&sl->pcm, (size_t)(b->n_pcm_frames ? b->n_pcm_frames : 1) * 1152 * c->nch * sizeof(int16_t)))) return rc;
-  int64_t cf = nf < c->chunk_frames ? nf : c->chunk_frames;
-  if (cf) {
-  if ((rc = ensure(&c->is16, (size_t)cf * 4 * 576 * 2))) return rc;
-  if ((rc = ensure(&c->count1, (size_t)cf * 4 * 4))) return rc;
-  if ((rc = ensure(&c->scf, (size_t)cf * 4 * P3_SCF_STRIDE))) return rc;
-  if (c->mode == P3_MODE_EXACT || c->taps) {
-    if ((rc = ensure(&c->xr, (size_t)cf * 4 * 576 * 4))) return rc;
-    if ((rc = ensure(&c->y, (size_t)cf * 4 * 576 * 4))) return rc;
-  }
-  }
-  /* K1 shared-memory window: 512 reservoir bytes + the largest group of K1_FPB frames (+ alignment and read-ahead slack) */
   uint64_t maxg = 0;
   for (int64_t f0 = 0; f0 < nf; f0 += K1_FPB) {
     int64_t f1 = f0 + K1_FPB < nf ? f0 + K1_FPB : nf;
     uint64_t span = b->frames[f1 - 1].main_pos + b->frames[f1 - 1].main_size - b->frames[f0].main_pos;
     if (span > maxg) maxg = span;
   }
-  c->k1_smem_words = (uint32_t)(((512 + maxg + 64 + 15) & ~(uint64_t)15) / 4);
-  if ((size_t)c->k1_smem_words * 4 + sizeof(((p3_tables *)0)->hlut) + 4 * K1_THREADS * 4 > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
-  /* compact main-data stream: 512 reservoir bytes + all main data of the batch, zero padded (the bit readers run a few words ahead) */
-  sl->ms_bytes = 512 + (b->frames[nf - 1].main_pos + b->frames[nf - 1].main_size - b->frames[0].main_pos);
-  if ((rc = ensure(&sl->ms, sl->ms_bytes + 512))) return rc;
-  CK(cudaMemsetAsync((uint8_t *)sl->ms.p + (sl->ms_bytes & ~(uint64_t)3), 0, 128, st));
+  if ((rc = size_batch(c, sl, nf, b->n_pcm_frames, maxg, b->frames[nf - 1].main_pos + b->frames[nf - 1].main_size - b->frames[0].main_pos, st))) return rc;
   memcpy(sl->h_tail, c->h_tail, 512);
   CK(cudaMemcpyAsync(sl->raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(sl->frames.p, b->frames, (size_t)nf * sizeof(p3_frame), cudaMemcpyHostToDevice, st));
@@ -422,7 +450,7 @@ extern "C" int p3_decode_batch(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes
   if ((rc = p3_batch_upload(c, raw, raw_bytes, b))) return rc;
   if ((rc = p3_batch_run(c))) return rc;
   if ((rc = p3_batch_download(c, pcm, t))) return rc;
-  if (c->have_next_tail) { memcpy(c->h_tail, c->next_tail, 512); c->have_next_tail = 0; }   /* reservoir for the next batch */
+  commit_tail(c);                                          /* reservoir for the next batch */
   return P3_OK;
 }
 
@@ -495,7 +523,7 @@ extern "C" int p3_decode_batch_async(p3_ctx *c, const uint8_t *raw, uint64_t raw
   /* the other slot's kernels must not start before this download has its data: ordering on c->stream is implicit;
    * its next stage_batch() waits for d2h_done through slot_release() */
   sl->busy = 1;
-  if (c->have_next_tail) { memcpy(c->h_tail, c->next_tail, 512); c->have_next_tail = 0; }
+  commit_tail(c);
   if (g_trace) { g_tr_wait += t1 - t0; g_tr_stage += t2 - t1; g_tr_launch += now_ms() - t2; }
   return P3_OK;
 }
@@ -564,5 +592,69 @@ extern "C" int p3_batch_time_xr(p3_ctx *c, int iters, float *ms_total, float *ms
   c->launches = 2;
   if (ms_total) *ms_total = tot / iters;
   if (ms_stage) { ms_stage[0] = st[0] / iters; ms_stage[1] = st[1] / iters; }
+  return P3_OK;
+}
+
+/* ---- batches staged from RAW BYTES: the frame hop runs on the device (p3_hop.cu) ---------------------------------- */
+
+/* Stage the frames found in raw[0, raw_bytes) (host memory, or device memory when raw_on_device) in the current slot: copy
+ * the bytes, hop on the device, size the buffers.  *st (may be NULL) is the parser state in and, when the batch is
+ * committed by p3_decode_raw(), out; *info receives n_frames / n_pcm_frames / consumed / stop as p3_parse() would report
+ * them (its frames / gcs pointers stay NULL: the descriptors exist on the device only). */
+static int stage_raw(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_bytes, int raw_on_device, const p3_parse_opts *o, const p3_parse_state *st_in, p3_parsed *info, cudaStream_t st)
+{
+  p3_parse_opts od; memset(&od, 0, sizeof od);
+  p3_parse_state sd = {0, 0, 0, -1, -1};
+  if (!o) o = &od;
+  if (!st_in) st_in = &sd;
+  int rc;
+  if ((rc = ensure(&sl->raw, raw_bytes + 64))) return rc;
+  if (raw_bytes) CK(cudaMemcpyAsync(sl->raw.p, raw, raw_bytes, raw_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync((uint8_t *)sl->raw.p + raw_bytes, 0, 64, st));
+  if (c->tail_on_device) CK(cudaMemcpyAsync(sl->d_tail, c->d_tail_cur, 512, cudaMemcpyDeviceToDevice, st));
+  else { memcpy(sl->h_tail, c->h_tail, 512); CK(cudaMemcpyAsync(sl->d_tail, sl->h_tail, 512, cudaMemcpyHostToDevice, st)); }
+  if ((rc = p3_hop_count(&c->hop, st, (const uint8_t *)sl->raw.p, raw_bytes, o, st_in, 0))) return fail(rc, "device frame hop failed");
+  const p3_hop_result *r = c->hop.h_res;
+  c->n_frames = r->n_frames; c->n_pcm_frames = r->n_pcm_frames; c->raw_bytes = raw_bytes; c->nch = (uint32_t)r->nch;
+  if ((rc = ensure(&sl->frames, (size_t)(r->n_frames ? r->n_frames : 1) * sizeof(p3_frame)))) return rc;
+  if ((rc = p3_hop_emit(&c->hop, st, (const uint8_t *)sl->raw.p, raw_bytes, o, st_in, (p3_frame *)sl->frames.p, sl->d_tail, c->d_tail_nxt))) return fail(rc, "device frame hop failed");
+  c->have_next_tail_dev = 1; c->have_next_tail = 0;
+  if ((rc = size_batch(c, sl, r->n_frames, r->n_pcm_frames, r->maxg, r->total_ms, st))) return rc;
+  sl->hop_only = 1; sl->iso = o->iso != 0;
+  if (info) {
+    memset(info, 0, sizeof *info);
+    info->n_frames = r->n_frames; info->n_pcm_frames = r->n_pcm_frames; info->consumed = r->consumed; info->stop = r->stop; info->hop_only = 1; info->external = 1;
+  }
+  return P3_OK;
+}
+
+extern "C" int p3_batch_upload_raw(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, int raw_on_device, const p3_parse_opts *o, const p3_parse_state *st, p3_parsed *info)
+{
+  if (!c || (!raw && raw_bytes)) return fail(P3_EINVAL, "null argument");
+  CK(cudaSetDevice(c->device));
+  p3_slot *sl = &c->slot[c->cur_slot];
+  slot_release(sl);
+  return stage_raw(c, sl, raw, raw_bytes, raw_on_device, o, st, info, c->stream);
+}
+
+extern "C" int p3_batch_channels(p3_ctx *c) { return c ? (int)c->nch : 0; }
+extern "C" int p3_hop_rounds(p3_ctx *c) { return c && c->hop.h_res ? c->hop.h_res->changed : 0; }
+
+/* Decode raw[0, raw_bytes) in one call, hop included: the device-side counterpart of p3_parse() + p3_decode_batch().
+ * *st is updated to the parser state after the decoded frames; info->consumed tells where the next call continues. */
+extern "C" int p3_decode_raw(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parse_opts *o, p3_parse_state *st, p3_parsed *info,
+                             int16_t *pcm, int64_t pcm_cap_frames, const p3_taps *t)
+{
+  int rc;
+  if (!c) return fail(P3_EINVAL, "null ctx");
+  c->taps = t != NULL;
+  if ((rc = p3_batch_sync(c))) return rc;
+  p3_parse_opts oo; if (o) oo = *o; else memset(&oo, 0, sizeof oo);
+  if (pcm_cap_frames > 0 && (oo.max_frames <= 0 || oo.max_frames > pcm_cap_frames + oo.warmup_frames)) oo.max_frames = pcm_cap_frames + oo.warmup_frames;
+  if ((rc = p3_batch_upload_raw(c, raw, raw_bytes, 0, &oo, st, info))) return rc;
+  if ((rc = p3_batch_run(c))) return rc;
+  if ((rc = p3_batch_download(c, pcm, t))) return rc;
+  commit_tail(c);
+  if (st && c->hop.h_res->n_frames > 0) *st = c->hop.h_res->st;
   return P3_OK;
 }

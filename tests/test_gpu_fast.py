@@ -7,7 +7,24 @@ from test_gpu_parity import VARIANTS, feq
 
 pytestmark = pytest.mark.gpu
 
-PCM_TOL_LSB = 1          # |pcm - pcm_ref| <= 1 LSB of int16, every sample
+PCM_TOL_LSB = 1          # |pcm - pcm_ref| <= 1 LSB of int16, every sample of every granule-channel the reference does not drive into saturation
+PCM_TOL_SATURATED = 8    # granule-channels in which the reference clips at +-32767 (an unclipped waveform several times full scale): the
+                         # reference's 6-decimal cosine tables differ from exact cosines by up to 6.8e-6, which times the overdrive
+                         # exceeds 1 LSB on ~1e-5 of the samples -- with the fp32 direct-form sums of the reference itself just as with the fast
+                         # transforms (measured on the CPU: DESIGN.md 5b); P3_MODE_EXACT is bit-identical there too
+
+
+def check_pcm(pcm, ref, min_equal=0.90):
+    """the FAST-mode tolerance: <= 1 LSB everywhere except in granule-channels the reference saturates (<= 8 LSB there; worst seen: 5)"""
+    assert pcm.shape == ref.shape
+    n, _, nch = pcm.shape
+    d = np.abs(pcm.astype(np.int32) - ref.astype(np.int32)).reshape(n, 2, 576, nch)
+    sat = (np.abs(ref.astype(np.int32)) == 32767).reshape(n, 2, 576, nch).any(axis=2)        # [frame, granule, ch]
+    worst = d.max(axis=2)
+    assert (worst[~sat] <= PCM_TOL_LSB).all(), "max |diff| = %d LSB in a granule-channel without saturation" % worst[~sat].max()
+    assert (worst <= PCM_TOL_SATURATED).all(), "max |diff| = %d LSB" % worst.max()
+    assert (d == 0).mean() > min_equal, "only %.3f of samples exactly equal" % (d == 0).mean()
+    return int(worst.max())
 
 
 @pytest.fixture(scope="module")
@@ -30,9 +47,7 @@ def test_fast_within_one_lsb(fast_ctx, name):
     ya, yb = t["y"][:, :, :nch].astype(np.float64), o["y_hyb"][:, :, :nch].astype(np.float64)
     scale = np.abs(yb).max() + 1e-30
     assert np.abs(ya - yb).max() <= 3e-5 * scale, "hybrid synthesis (fast IMDCT) drifted"
-    d = np.abs(pcm.astype(np.int32) - o["pcm"].astype(np.int32))
-    assert d.max() <= PCM_TOL_LSB, "max |diff| = %d LSB" % d.max()
-    assert (d == 0).mean() > 0.90, "only %.3f of samples exactly equal" % (d == 0).mean()
+    check_pcm(pcm, o["pcm"])
 
 
 def test_fast_partition_independent(fast_ctx):
@@ -84,9 +99,7 @@ def test_warp_kernel(fast_ctx, name):
         fast_ctx.reset(); fast_ctx.set_frames_per_cta(fpw); got[fpw] = fast_ctx.decode(s, lookahead=0)
     fast_ctx.set_frames_per_cta(32)
     assert np.array_equal(got[32], got[5]) and np.array_equal(got[32], got[1]), "result depends on the run length"
-    d = np.abs(got[32].astype(np.int32) - o["pcm"].astype(np.int32))
-    assert d.max() <= PCM_TOL_LSB, "max |diff| vs oracle = %d LSB" % d.max()
-    assert (d == 0).mean() > 0.90
+    check_pcm(got[32], o["pcm"])
     assert np.abs(got[32].astype(np.int32) - cta.astype(np.int32)).max() <= 1
 
 
@@ -142,9 +155,7 @@ def test_bench_block_against_the_compiled_reference(fast_ctx, workload):
     fast_ctx.reset()
     pcm = fast_ctx.decode(blk, lookahead=1152, hop_only=True)
     assert pcm.shape[0] == n
-    d = np.abs(pcm.astype(np.int32) - r["pcm"].astype(np.int32))
-    assert d.max() <= PCM_TOL_LSB, "max |diff| = %d LSB" % d.max()
-    assert (d == 0).mean() > 0.90
+    assert check_pcm(pcm, r["pcm"]) <= PCM_TOL_LSB
     ex = pdmp3_b200.Context(0, pdmp3_b200.MODE_EXACT)
     two = ex.decode(blk, lookahead=1152)
     ex.close()
