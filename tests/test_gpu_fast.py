@@ -100,7 +100,7 @@ def test_warp_kernel(fast_ctx, name):
     fast_ctx.set_frames_per_cta(32)
     assert np.array_equal(got[32], got[5]) and np.array_equal(got[32], got[1]), "result depends on the run length"
     check_pcm(got[32], o["pcm"])
-    assert np.abs(got[32].astype(np.int32) - cta.astype(np.int32)).max() <= 1
+    check_pcm(got[32], cta)                                   # the two FAST kernels: same tolerance between them
 
 
 def test_warp_kernel_batches_with_carried_state(fast_ctx):

@@ -60,7 +60,7 @@ def test_stage_taps_exact_vs_oracle(gpu_ctx, name):
     assert np.array_equal(t["count1"][:, :, :nch], o["count1"][:, :, :nch]), "count1"
     ml, ms = live_scalefactors(o["gcs"], nch)
     assert np.array_equal(t["scf_l"][ml], o["scf_l"][ml]) and np.array_equal(t["scf_s"][ms], o["scf_s"][ms]), "scalefactors"
-    assert t["scf_l"][ml].any() and (name != "cfg4" or t["scf_s"][ms].any())
+    if name in ("cfg3", "cfg4"): assert t["scf_l"][ml].any() and (name != "cfg4" or t["scf_s"][ms].any())     # (low bit rates: scalefac_compress 0)
     assert feq(t["xr"][:, :, :nch], o["xr_ali"][:, :, :nch]).all(), "requantize/reorder/stereo/antialias"
     assert feq(t["y"][:, :, :nch], o["y_hyb"][:, :, :nch]).all(), "hybrid synthesis"
     assert np.array_equal(pcm, o["pcm"]), "PCM"
@@ -79,10 +79,11 @@ def test_empty_parts_integer_stages(gpu_ctx, name):
     t = H.empty_some_parts(s)
     o = H.oracle_decode(t, lookahead=1152)
     ml, ms = live_scalefactors(o["gcs"], 2)
+    full = (H.gc_fields(o["gcs"])[..., 0] != 0).reshape(-1, 2, 2)     # K1 taps 0 for an empty part; the stale value (Q6) is looked up downstream (w3)
     for hop_only in (False, True):
         gpu_ctx.reset()
         pcm, tp = gpu_ctx.decode(t, lookahead=1152, taps=True, hop_only=hop_only)
-        assert np.array_equal(tp["is_huff"], o["is_huff"]) and np.array_equal(tp["count1"], o["count1"])
+        assert np.array_equal(tp["is_huff"], o["is_huff"]) and np.array_equal(tp["count1"][full], o["count1"][full]) and not tp["count1"][~full].any()
         assert np.array_equal(tp["scf_l"][ml], o["scf_l"][ml]) and np.array_equal(tp["scf_s"][ms], o["scf_s"][ms])
 
 
