@@ -184,6 +184,31 @@ int  p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_stage /*[8]:
 int  p3_batch_time_xr(p3_ctx *c, int iters, float *ms_total, float *ms_stage /*[2]: k_imdct, k_polyphase*/);   /* BASELINE configs[1] resident in HBM: the two transform kernels over the spectra a P3_MODE_EXACT run of the batch left on the device */
 int  p3_kernel_launch_count(p3_ctx *c);               /* kernels launched by the last p3_batch_run */
 
+/* ---- BASELINE configs[4]: one stream on rank 0, frame-sharded over the GPUs of the box, PCM gathered to rank 0 ------------
+ * One process per GPU, each with its own p3_ctx.  NCCL (loaded at run time with dlopen, called from C) carries exactly what
+ * north_star names: the scatter of the compressed byte ranges from rank 0 and the gather of the PCM to rank 0 -- chunked, so
+ * that blocks already decoded travel while later ones decode.  Shards are independent up to a warm-up (the frame in front of
+ * the shard for the filter state + earlier frames for reservoir bytes), so the decode itself has no
+ * exchange step and the result is bit-identical to the single-GPU decode of the same stream. */
+typedef struct p3_dist p3_dist;
+typedef struct {
+  int64_t  n_frames_total, n_frames_mine, warmup_mine, chunks;
+  int32_t  nch, stop, launches, pad_;
+  uint64_t consumed, bytes_in, bytes_out;    /* bytes_in: compressed bytes this rank received; bytes_out: PCM bytes it sent */
+  float    ms, ms_scatter;                   /* device time (CUDA events) of this rank's part of the call / until its scatter traffic was done */
+} p3_shard_result;
+int  p3_dist_unique_id(uint8_t *out256);     /* rank 0: two NCCL unique ids (scatter and gather communicators), 2 x 128 bytes, to be handed to every rank */
+int  p3_dist_init(p3_ctx *c, const uint8_t *ids256, int rank, int world, p3_dist **out);
+void p3_dist_destroy(p3_dist *d);
+int  p3_dist_nccl_version(void);
+/* collective over all ranks; rank 0 passes the stream (host memory, or device memory when raw_on_device: used in place, 64
+ * readable bytes must follow), the others NULL.  Afterwards rank 0 holds the PCM of the whole stream in the context's PCM
+ * buffer: p3_batch_pcm_device() / p3_batch_download(). */
+int  p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_bytes, int raw_on_device, const p3_parse_opts *opts,
+                       int64_t chunk_frames, p3_shard_result *res);
+/* the floor of the gather on this box: every rank > 0 sends bytes_per_rank to rank 0, nothing else running */
+int  p3_dist_measure_ingest(p3_dist *d, uint64_t bytes_per_rank, int iters, float *ms_per_iter);
+
 #ifdef __cplusplus
 }
 #endif

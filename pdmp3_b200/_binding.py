@@ -39,6 +39,12 @@ class P3Parsed(C.Structure):
                 ("hop_only", C.c_int32), ("pad_", C.c_int32)]
 
 
+class P3ShardResult(C.Structure):
+    _fields_ = [("n_frames_total", C.c_int64), ("n_frames_mine", C.c_int64), ("warmup_mine", C.c_int64), ("chunks", C.c_int64),
+                ("nch", C.c_int32), ("stop", C.c_int32), ("launches", C.c_int32), ("pad_", C.c_int32),
+                ("consumed", C.c_uint64), ("bytes_in", C.c_uint64), ("bytes_out", C.c_uint64), ("ms", C.c_float), ("ms_scatter", C.c_float)]
+
+
 class P3Taps(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("is_huff", "count1", "scf", "xr", "y")]
 
@@ -76,6 +82,11 @@ def lib():
                                 C.c_void_p, C.c_int64, C.POINTER(P3Taps)]
     L.p3_hop_rounds.argtypes = [C.c_void_p]
     L.p3_batch_channels.argtypes = [C.c_void_p]
+    L.p3_dist_unique_id.argtypes = [C.c_void_p]
+    L.p3_dist_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.p3_dist_destroy.argtypes = [C.c_void_p]
+    L.p3_sharded_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(P3ParseOpts), C.c_int64, C.POINTER(P3ShardResult)]
+    L.p3_dist_measure_ingest.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float)]
     L.p3_batch_run.argtypes = [C.c_void_p]
     L.p3_batch_sync.argtypes = [C.c_void_p]
     L.p3_batch_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(P3Taps)]
@@ -282,6 +293,54 @@ class Context:
 
     def launch_count(self):
         return lib().p3_kernel_launch_count(self.h)
+
+
+def dist_unique_id():
+    """rank 0: the 256 bytes (two NCCL unique ids) every rank needs for Dist()"""
+    buf = (C.c_uint8 * 256)()
+    _check(lib().p3_dist_unique_id(buf), "p3_dist_unique_id")
+    return bytes(buf)
+
+
+class Dist:
+    """BASELINE configs[4]: the frame-sharded decode of one stream held on rank 0, PCM gathered to rank 0 (p3_dist.cuh; NCCL from C)."""
+
+    def __init__(self, ctx, ids, rank, world):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.h = C.c_void_p()
+        b = (C.c_uint8 * 256).from_buffer_copy(ids)
+        _check(lib().p3_dist_init(ctx.h, b, rank, world, C.byref(self.h)), "p3_dist_init")
+
+    def sharded_decode(self, stream=None, device_ptr=None, nbytes=0, chunk_frames=0, iso=False):
+        """rank 0: `stream` (np.uint8, host) or (device_ptr, nbytes) of a device buffer with 64 bytes of slack; others: nothing.
+        -> P3ShardResult fields as a dict; rank 0 then reads the PCM with pcm()"""
+        o = P3ParseOpts(0, 0, 0, 0, 1, 1 if iso else 0)
+        res = P3ShardResult()
+        if device_ptr is not None:
+            rc = lib().p3_sharded_decode(self.h, device_ptr, nbytes, 1, C.byref(o), chunk_frames, C.byref(res))
+        elif stream is not None:
+            self._raw = np.ascontiguousarray(stream, dtype=np.uint8)
+            rc = lib().p3_sharded_decode(self.h, self._raw.ctypes.data, len(self._raw), 0, C.byref(o), chunk_frames, C.byref(res))
+        else:
+            rc = lib().p3_sharded_decode(self.h, None, 0, 0, C.byref(o), chunk_frames, C.byref(res))
+        _check(rc, "p3_sharded_decode")
+        return {k: getattr(res, k) for k, _ in P3ShardResult._fields_}
+
+    def pcm(self, res):
+        """rank 0: the PCM of the whole stream [n_frames_total, 1152, nch]"""
+        out = np.zeros((res["n_frames_total"], 1152, res["nch"]), np.int16)
+        _check(lib().p3_batch_download(self.ctx.h, out.ctypes.data, None), "p3_batch_download")
+        return out
+
+    def measure_ingest(self, bytes_per_rank, iters=3):
+        ms = C.c_float()
+        _check(lib().p3_dist_measure_ingest(self.h, bytes_per_rank, iters, C.byref(ms)), "p3_dist_measure_ingest")
+        return ms.value
+
+    def close(self):
+        if self.h:
+            lib().p3_dist_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class Decoder:

@@ -49,7 +49,7 @@ def build_product(force=False, verbose=False):
         if verbose:
             print(log)
         objs.append(o)
-    _run([nvcc] + NVCC_ARCH + ["-shared", "-o", out] + objs + ["-lpthread", "-lm"])
+    _run([nvcc] + NVCC_ARCH + ["-shared", "-o", out] + objs + ["-lpthread", "-lm", "-ldl"])
     return out
 
 

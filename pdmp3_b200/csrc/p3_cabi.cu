@@ -44,6 +44,7 @@ static int ensure(dbuf *b, size_t n)
  * let the upload of batch k+1 and the download of batch k-1 overlap the kernels of batch k. */
 struct p3_slot {
   dbuf raw, frames, gcs, pcm, ms;         /* ms: compact main-data stream (k_compact -> k_huffman) */
+  const uint8_t *raw_dev;                 /* the staged byte stream the kernels read: raw.p, or a caller-owned device buffer (p3_sharded_decode) */
   uint64_t ms_bytes;
   uint8_t *d_tail; uint8_t *h_tail;       /* 512 main-data bytes in front of the batch (pinned host copy) */
   int *d_any_empty; int hop_only;         /* device side-info parser: flag for the Q6 chain; pending for this slot */
@@ -283,6 +284,7 @@ static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_
   if ((rc = size_batch(c, sl, nf, b->n_pcm_frames, maxg, b->frames[nf - 1].main_pos + b->frames[nf - 1].main_size - b->frames[0].main_pos, st))) return rc;
   memcpy(sl->h_tail, c->h_tail, 512);
   CK(cudaMemcpyAsync(sl->raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, st));
+  sl->raw_dev = (const uint8_t *)sl->raw.p;
   CK(cudaMemcpyAsync(sl->frames.p, b->frames, (size_t)nf * sizeof(p3_frame), cudaMemcpyHostToDevice, st));
   sl->hop_only = b->hop_only;
   sl->iso = b->n_frames > 0 && (b->frames[0].flags & P3_FRAME_ISO) != 0;
@@ -334,7 +336,7 @@ static int run_chunk(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, cudaEvent_t
   p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
   CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));   /* fields a launch does not rewrite carry over */
   if (ev) CK(cudaEventRecord(ev[0], c->stream));
-  k_compact<<<(unsigned)((nf + 3) / 4), 128, 0, c->stream>>>((const uint8_t *)sl->raw.p, fr, sl->d_tail, f0, f1, (uint32_t *)sl->ms.p);
+  k_compact<<<(unsigned)((nf + 3) / 4), 128, 0, c->stream>>>(sl->raw_dev, fr, sl->d_tail, f0, f1, (uint32_t *)sl->ms.p);
   if (ev) CK(cudaEventRecord(ev[1], c->stream));
   size_t smem1 = (size_t)c->k1_smem_words * 4 + 4 * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
   k_huffman<<<(unsigned)((nf + K1_FPB - 1) / K1_FPB), K1_THREADS, smem1, c->stream>>>((const uint32_t *)sl->ms.p, fr, gc, c->d_tables, f0, f1,
@@ -363,16 +365,25 @@ static int run_chunk(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, cudaEvent_t
 }
 
 /* Read_Audio_L3 on the device (k_sideinfo + the Q6 chain): once per staged batch, in front of the first decode */
+static int run_sideinfo_range(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1)
+{
+  if (f1 <= f0) return P3_OK;
+  CK(cudaMemsetAsync(sl->d_any_empty, 0, sizeof(int), c->stream));
+  k_sideinfo<<<(unsigned)((f1 - f0 + 127) / 128), 128, 0, c->stream>>>(sl->raw_dev, (p3_frame *)sl->frames.p + f0, (p3_gc *)sl->gcs.p + 4 * f0, f1 - f0, sl->d_any_empty);
+  /* (a range that does not start at frame 0: an empty part whose slot was last written before f0 gets w3 = "not in this
+   *  batch", which the kernels resolve through the carried state -- what they do at a launch boundary anyway) */
+  k_q6_chain<<<1, 1024, 0, c->stream>>>((const p3_frame *)sl->frames.p + f0, (p3_gc *)sl->gcs.p + 4 * f0, f1 - f0, sl->d_any_empty);
+  CK(cudaGetLastError());
+  c->launches_parse = 2;
+  return P3_OK;
+}
+
 static int run_sideinfo(p3_ctx *c, p3_slot *sl)
 {
   if (!sl->hop_only || c->n_frames == 0) return P3_OK;
-  CK(cudaMemsetAsync(sl->d_any_empty, 0, sizeof(int), c->stream));
-  k_sideinfo<<<(unsigned)((c->n_frames + 127) / 128), 128, 0, c->stream>>>((const uint8_t *)sl->raw.p, (p3_frame *)sl->frames.p, (p3_gc *)sl->gcs.p, c->n_frames, sl->d_any_empty);
-  k_q6_chain<<<1, 1024, 0, c->stream>>>((const p3_frame *)sl->frames.p, (p3_gc *)sl->gcs.p, c->n_frames, sl->d_any_empty);
-  CK(cudaGetLastError());
+  int rc = run_sideinfo_range(c, sl, 0, c->n_frames);
   sl->hop_only = 0;                                        /* the descriptors are complete now; later runs of the same batch reuse them */
-  c->launches_parse = 2;
-  return P3_OK;
+  return rc;
 }
 
 static int run_all(p3_ctx *c, p3_slot *sl)
@@ -601,6 +612,22 @@ extern "C" int p3_batch_time_xr(p3_ctx *c, int iters, float *ms_total, float *ms
  * the bytes, hop on the device, size the buffers.  *st (may be NULL) is the parser state in and, when the batch is
  * committed by p3_decode_raw(), out; *info receives n_frames / n_pcm_frames / consumed / stop as p3_parse() would report
  * them (its frames / gcs pointers stay NULL: the descriptors exist on the device only). */
+/* the hop of a staged byte stream (sl->raw_dev, raw_bytes): frames -> sl->frames, the result block -> c->hop.h_res */
+static int hop_staged(p3_ctx *c, p3_slot *sl, uint64_t raw_bytes, const p3_parse_opts *o, const p3_parse_state *st_in, cudaStream_t st)
+{
+  int rc;
+  if (c->tail_on_device) CK(cudaMemcpyAsync(sl->d_tail, c->d_tail_cur, 512, cudaMemcpyDeviceToDevice, st));
+  else { memcpy(sl->h_tail, c->h_tail, 512); CK(cudaMemcpyAsync(sl->d_tail, sl->h_tail, 512, cudaMemcpyHostToDevice, st)); }
+  if ((rc = p3_hop_count(&c->hop, st, sl->raw_dev, raw_bytes, o, st_in, 0))) return fail(rc, "device frame hop failed");
+  const p3_hop_result *r = c->hop.h_res;
+  c->n_frames = r->n_frames; c->n_pcm_frames = r->n_pcm_frames; c->raw_bytes = raw_bytes; c->nch = (uint32_t)r->nch;
+  if ((rc = ensure(&sl->frames, (size_t)(r->n_frames ? r->n_frames : 1) * sizeof(p3_frame)))) return rc;
+  if ((rc = p3_hop_emit(&c->hop, st, sl->raw_dev, raw_bytes, o, st_in, (p3_frame *)sl->frames.p, sl->d_tail, c->d_tail_nxt))) return fail(rc, "device frame hop failed");
+  c->have_next_tail_dev = 1; c->have_next_tail = 0;
+  sl->hop_only = 1; sl->iso = o->iso != 0;
+  return P3_OK;
+}
+
 static int stage_raw(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_bytes, int raw_on_device, const p3_parse_opts *o, const p3_parse_state *st_in, p3_parsed *info, cudaStream_t st)
 {
   p3_parse_opts od; memset(&od, 0, sizeof od);
@@ -609,18 +636,12 @@ static int stage_raw(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_by
   if (!st_in) st_in = &sd;
   int rc;
   if ((rc = ensure(&sl->raw, raw_bytes + 64))) return rc;
+  sl->raw_dev = (const uint8_t *)sl->raw.p;
   if (raw_bytes) CK(cudaMemcpyAsync(sl->raw.p, raw, raw_bytes, raw_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync((uint8_t *)sl->raw.p + raw_bytes, 0, 64, st));
-  if (c->tail_on_device) CK(cudaMemcpyAsync(sl->d_tail, c->d_tail_cur, 512, cudaMemcpyDeviceToDevice, st));
-  else { memcpy(sl->h_tail, c->h_tail, 512); CK(cudaMemcpyAsync(sl->d_tail, sl->h_tail, 512, cudaMemcpyHostToDevice, st)); }
-  if ((rc = p3_hop_count(&c->hop, st, (const uint8_t *)sl->raw.p, raw_bytes, o, st_in, 0))) return fail(rc, "device frame hop failed");
+  if ((rc = hop_staged(c, sl, raw_bytes, o, st_in, st))) return rc;
   const p3_hop_result *r = c->hop.h_res;
-  c->n_frames = r->n_frames; c->n_pcm_frames = r->n_pcm_frames; c->raw_bytes = raw_bytes; c->nch = (uint32_t)r->nch;
-  if ((rc = ensure(&sl->frames, (size_t)(r->n_frames ? r->n_frames : 1) * sizeof(p3_frame)))) return rc;
-  if ((rc = p3_hop_emit(&c->hop, st, (const uint8_t *)sl->raw.p, raw_bytes, o, st_in, (p3_frame *)sl->frames.p, sl->d_tail, c->d_tail_nxt))) return fail(rc, "device frame hop failed");
-  c->have_next_tail_dev = 1; c->have_next_tail = 0;
   if ((rc = size_batch(c, sl, r->n_frames, r->n_pcm_frames, r->maxg, r->total_ms, st))) return rc;
-  sl->hop_only = 1; sl->iso = o->iso != 0;
   if (info) {
     memset(info, 0, sizeof *info);
     info->n_frames = r->n_frames; info->n_pcm_frames = r->n_pcm_frames; info->consumed = r->consumed; info->stop = r->stop; info->hop_only = 1; info->external = 1;
@@ -658,3 +679,5 @@ extern "C" int p3_decode_raw(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, 
   if (st && c->hop.h_res->n_frames > 0) *st = c->hop.h_res->st;
   return P3_OK;
 }
+
+#include "p3_dist.cuh"

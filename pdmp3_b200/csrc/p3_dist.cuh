@@ -1,0 +1,339 @@
+/* p3_dist.cuh -- BASELINE configs[4]: one stream held on rank 0, frame-sharded over the GPUs of the box, PCM gathered to rank 0
+ * (SURVEY 8e).  Included at the end of p3_cabi.cu.  NCCL is called from here (C side), loaded at run time with dlopen so
+ * that the library neither links against nor needs NCCL for single-GPU use.
+ *
+ *   rank 0                                               rank r > 0
+ *   hop of the whole stream on the device (p3_hop.cu)
+ *   k_shard_plan: frame range, warm-up, byte range        |
+ *   of every rank  ---- ncclBroadcast (plan) ---------->  plan
+ *   ncclSend bytes of rank 1, 2, ...  (comm S, in rank    ncclRecv its byte range (previous frame for the filter state + the
+ *   order: rank 1 can start while rank 7 still waits)     frames before it that hold reservoir bytes: the warm-up)
+ *   decodes its own shard in chunks, straight into the    device hop of the range, side info, then chunk by chunk:
+ *   output buffer                                         K0 -> K1 -> synthesis -> ncclSend of the chunk's PCM (comm G)
+ *   ncclRecv of every (rank, chunk) PCM block straight      while the next chunk decodes
+ *   into its place in the output buffer, posted in the
+ *   order in which the blocks become ready
+ *
+ * Two communicators so that the scatter (rank 0 egress) and the gather (rank 0 ingress) run side by side: NVLink is full
+ * duplex and rank 0's ingress -- 4608 bytes per frame from W-1 peers -- is the floor of this configuration.
+ * No collective touches the decode itself: shards are independent (warm-up rule of SURVEY 3.5, as pdmp3_b200/shard.py).
+ */
+#include <dlfcn.h>
+#include <nccl.h>
+
+struct nccl_api {
+  void *h;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)(void);
+  ncclResult_t (*GroupEnd)(void);
+  const char *(*GetErrorString)(ncclResult_t);
+  ncclResult_t (*GetVersion)(int *);
+};
+static nccl_api g_nccl;
+
+static int nccl_load(void)
+{
+  if (g_nccl.h) return P3_OK;
+  /* RTLD_NOLOAD first: a host process that already carries NCCL (e.g. PyTorch's bundled copy) must not get a second one */
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(P3_ENODEV, "libnccl.so.2 not found: the multi-GPU path needs NCCL (%s)", dlerror());
+#define NCCL_SYM(field, name) do { *(void **)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) return fail(P3_ENODEV, "NCCL symbol %s missing", name); } while (0)
+  NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); NCCL_SYM(CommInitRank, "ncclCommInitRank"); NCCL_SYM(CommDestroy, "ncclCommDestroy");
+  NCCL_SYM(Send, "ncclSend"); NCCL_SYM(Recv, "ncclRecv"); NCCL_SYM(Broadcast, "ncclBroadcast");
+  NCCL_SYM(GroupStart, "ncclGroupStart"); NCCL_SYM(GroupEnd, "ncclGroupEnd"); NCCL_SYM(GetErrorString, "ncclGetErrorString");
+  NCCL_SYM(GetVersion, "ncclGetVersion");
+#undef NCCL_SYM
+  g_nccl.h = h;
+  return P3_OK;
+}
+#define NK(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) return fail(P3_ECUDA, "%s: %s (%s:%d)", #x, g_nccl.GetErrorString(r_), __FILE__, __LINE__); } while (0)
+
+typedef struct {                          /* one per rank, computed on rank 0 (k_shard_plan), broadcast */
+  int64_t  first, last, warmup;           /* frames [first, last) of the stream are this rank's; `warmup` frames in front of them are decoded for state only */
+  uint64_t byte_lo, byte_hi;              /* byte range of the stream the rank needs */
+  uint64_t ms_bytes;                      /* main-data bytes of frames [first - warmup, last) */
+} p3_shard_plan;
+
+typedef struct {                          /* broadcast in front of the plans */
+  int64_t n_frames; int32_t nch, iso; uint32_t maxg, stop; uint64_t consumed;
+} p3_shard_head;
+
+#define P3_DIST_MAXW 16
+
+struct p3_dist {
+  p3_ctx *c; int rank, world;
+  ncclComm_t comm_s, comm_g;             /* scatter (+ plan broadcast) | gather */
+  cudaStream_t s_scatter, s_gather;
+  cudaEvent_t ev_a, ev_b, ev_t0, ev_t1, ev_s1;
+  cudaEvent_t *ev_chunk; int n_ev;
+  uint8_t *d_plan, *h_plan;              /* p3_shard_head + world x p3_shard_plan */
+};
+
+/* plan of every rank from the frame records of the whole stream (same rule as pdmp3_b200/shard.py::plan_shards): one thread per rank */
+extern "C" __global__ void k_shard_plan(const p3_frame *__restrict__ fr, int64_t n, int world, p3_shard_plan *__restrict__ plan)
+{
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  const int64_t a = n * r / world, b = n * (r + 1) / world;
+  int64_t w = a;
+  if (a > 0 && b > a) {
+    w = a - 1;                                              /* the frame that must decode correctly: it primes the IMDCT overlap and the polyphase history */
+    const int64_t need = (int64_t)fr[w].main_pos - fr[w].main_begin;
+    while (w > 0 && (int64_t)fr[w].main_pos > need) w--;    /* earlier frames: reservoir bytes only */
+  }
+  p3_shard_plan p;
+  p.first = a; p.last = b; p.warmup = a - w;
+  p.byte_lo = w == 0 ? 0 : fr[w - 1].main_off + fr[w - 1].main_size;
+  p.byte_hi = b <= a ? p.byte_lo : fr[b - 1].main_off + fr[b - 1].main_size;
+  p.ms_bytes = b <= a ? 0 : fr[b - 1].main_pos + fr[b - 1].main_size - fr[w].main_pos;
+  plan[r] = p;
+}
+
+extern "C" int p3_dist_unique_id(uint8_t *out /* 2 x 128 bytes */)
+{
+  int rc = nccl_load(); if (rc) return rc;
+  if (!out) return fail(P3_EINVAL, "null argument");
+  ncclUniqueId a, b;
+  NK(g_nccl.GetUniqueId(&a)); NK(g_nccl.GetUniqueId(&b));
+  memcpy(out, &a, 128); memcpy(out + 128, &b, 128);
+  return P3_OK;
+}
+
+extern "C" void p3_dist_destroy(p3_dist *d)
+{
+  if (!d) return;
+  cudaSetDevice(d->c->device);
+  if (d->comm_s) g_nccl.CommDestroy(d->comm_s);
+  if (d->comm_g) g_nccl.CommDestroy(d->comm_g);
+  if (d->s_scatter) cudaStreamDestroy(d->s_scatter);
+  if (d->s_gather) cudaStreamDestroy(d->s_gather);
+  cudaEvent_t evs[] = {d->ev_a, d->ev_b, d->ev_t0, d->ev_t1, d->ev_s1};
+  for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+  for (int i = 0; i < d->n_ev; i++) cudaEventDestroy(d->ev_chunk[i]);
+  free(d->ev_chunk);
+  cudaFree(d->d_plan); if (d->h_plan) cudaFreeHost(d->h_plan);
+  free(d);
+}
+
+/* every rank calls this with the 256 bytes rank 0 got from p3_dist_unique_id() (how they travel is the caller's business:
+ * MPI, a file, torch.distributed ...).  The context's device must be the rank's GPU. */
+extern "C" int p3_dist_init(p3_ctx *c, const uint8_t *ids, int rank, int world, p3_dist **out)
+{
+  if (!c || !ids || !out || rank < 0 || rank >= world || world > P3_DIST_MAXW) return fail(P3_EINVAL, "bad argument");
+  int rc = nccl_load(); if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  p3_dist *d = (p3_dist *)calloc(1, sizeof *d);
+  if (!d) return fail(P3_ENOMEM, "calloc");
+  d->c = c; d->rank = rank; d->world = world;
+  ncclUniqueId a, b; memcpy(&a, ids, 128); memcpy(&b, ids + 128, 128);
+#define DK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { p3_dist_destroy(d); return fail(P3_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+#define DN(x) do { ncclResult_t r_ = (x); if (r_ != ncclSuccess) { p3_dist_destroy(d); return fail(P3_ECUDA, "%s: %s", #x, g_nccl.GetErrorString(r_)); } } while (0)
+  DN(g_nccl.CommInitRank(&d->comm_s, world, a, rank));
+  DN(g_nccl.CommInitRank(&d->comm_g, world, b, rank));
+  DK(cudaStreamCreateWithFlags(&d->s_scatter, cudaStreamNonBlocking));
+  DK(cudaStreamCreateWithFlags(&d->s_gather, cudaStreamNonBlocking));
+  DK(cudaEventCreateWithFlags(&d->ev_a, cudaEventDisableTiming)); DK(cudaEventCreateWithFlags(&d->ev_b, cudaEventDisableTiming));
+  DK(cudaEventCreate(&d->ev_t0)); DK(cudaEventCreate(&d->ev_t1)); DK(cudaEventCreate(&d->ev_s1));
+  const size_t pb = sizeof(p3_shard_head) + (size_t)world * sizeof(p3_shard_plan);
+  DK(cudaMalloc(&d->d_plan, pb)); DK(cudaHostAlloc((void **)&d->h_plan, pb, cudaHostAllocPortable));
+#undef DK
+#undef DN
+  *out = d;
+  return P3_OK;
+}
+
+extern "C" int p3_dist_nccl_version(void) { int v = 0; if (nccl_load() == P3_OK) g_nccl.GetVersion(&v); return v; }
+
+static int dist_events(p3_dist *d, int n)
+{
+  if (n <= d->n_ev) return P3_OK;
+  cudaEvent_t *e = (cudaEvent_t *)realloc(d->ev_chunk, (size_t)n * sizeof *e);
+  if (!e) return fail(P3_ENOMEM, "realloc");
+  d->ev_chunk = e;
+  for (int i = d->n_ev; i < n; i++) CK(cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming));
+  d->n_ev = n;
+  return P3_OK;
+}
+
+/* PCM slots [lo, hi) (in frames of the rank's shard) that chunk j of a shard with `wu` warm-up frames and `cnt` own frames produces */
+static inline void chunk_slots(int64_t j, int64_t C, int64_t wu, int64_t cnt, int64_t *lo, int64_t *hi)
+{
+  int64_t f0 = j * C, f1 = (j + 1) * C; if (f1 > wu + cnt) f1 = wu + cnt;
+  *lo = (f0 > wu ? f0 : wu) - wu; *hi = f1 > wu ? f1 - wu : 0;
+  if (*hi < *lo) *hi = *lo;
+}
+
+/* The sharded decode.  Rank 0: `raw` is the whole stream (host memory, or device memory when raw_on_device -- then it is used
+ * in place and must be followed by 64 readable bytes); other ranks pass NULL / 0.  chunk_frames: frames per launch sequence and
+ * per PCM block on the wire (<= 0: 65536; rounded to a multiple of 32).  On return rank 0's PCM of the WHOLE stream is in the
+ * context's PCM buffer (p3_batch_pcm_device(), p3_batch_download()), [n_frames][1152][nch] int16.  res (optional):
+ * frames decoded by this rank, frames of the stream, device time of this rank's part in ms (CUDA events, from the first
+ * byte staged to the last PCM block sent / received), and of the scatter alone. */
+extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_bytes, int raw_on_device, const p3_parse_opts *o_in,
+                                 int64_t chunk_frames, p3_shard_result *res)
+{
+  if (!d) return fail(P3_EINVAL, "null argument");
+  p3_ctx *c = d->c; const int W = d->world, R = d->rank;
+  if (R == 0 && !raw) return fail(P3_EINVAL, "rank 0 holds the stream");
+  CK(cudaSetDevice(c->device));
+  int rc;
+  if ((rc = p3_batch_sync(c))) return rc;
+  if ((rc = p3_ctx_reset(c))) return rc;                   /* every shard starts from zero state + its warm-up (rank 0: like pdmp3_open_feed) */
+  p3_parse_opts o; if (o_in) o = *o_in; else memset(&o, 0, sizeof o);
+  o.max_frames = 0; o.warmup_frames = 0; o.hop_only = 1;
+  int64_t C = chunk_frames > 0 ? chunk_frames : 65536;
+  C -= C % K1_FPB; if (C < K1_FPB) C = K1_FPB;
+  c->chunk_frames = C; c->taps = 0;
+  p3_slot *sl = &c->slot[c->cur_slot];
+  slot_release(sl);
+  p3_shard_head *hd = (p3_shard_head *)d->h_plan; p3_shard_plan *pl = (p3_shard_plan *)(d->h_plan + sizeof(p3_shard_head));
+  const size_t pb = sizeof(p3_shard_head) + (size_t)W * sizeof(p3_shard_plan);
+  const p3_parse_state st0 = {0, 0, 0, -1, -1};
+  CK(cudaEventRecord(d->ev_t0, c->stream));
+
+  /* ---- rank 0: stage, hop, plan ---- */
+  if (R == 0) {
+    if (raw_on_device) sl->raw_dev = raw;
+    else {
+      if ((rc = ensure(&sl->raw, raw_bytes + 64))) return rc;
+      sl->raw_dev = (const uint8_t *)sl->raw.p;
+      CK(cudaMemcpyAsync(sl->raw.p, raw, raw_bytes, cudaMemcpyHostToDevice, c->stream));
+      CK(cudaMemsetAsync((uint8_t *)sl->raw.p + raw_bytes, 0, 64, c->stream));
+    }
+    if ((rc = hop_staged(c, sl, raw_bytes, &o, &st0, c->stream))) return rc;
+    const p3_hop_result *r = c->hop.h_res;
+    memset(hd, 0, sizeof *hd);
+    hd->n_frames = r->n_frames; hd->nch = r->nch; hd->iso = (int32_t)o.iso; hd->maxg = r->maxg; hd->stop = (uint32_t)r->stop; hd->consumed = r->consumed;
+    CK(cudaMemcpyAsync(d->d_plan, hd, sizeof *hd, cudaMemcpyHostToDevice, c->stream));
+    k_shard_plan<<<1, 32, 0, c->stream>>>((const p3_frame *)sl->frames.p, r->n_frames, W, (p3_shard_plan *)(d->d_plan + sizeof(p3_shard_head)));
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(d->ev_a, c->stream));
+    CK(cudaStreamWaitEvent(d->s_scatter, d->ev_a, 0));
+  }
+  NK(g_nccl.Broadcast(d->d_plan, d->d_plan, pb, ncclUint8, 0, d->comm_s, d->s_scatter));
+  CK(cudaMemcpyAsync(d->h_plan, d->d_plan, pb, cudaMemcpyDeviceToHost, d->s_scatter));
+  CK(cudaStreamSynchronize(d->s_scatter));
+  const p3_shard_plan me = pl[R];
+  const int64_t n_total = hd->n_frames; const int nch = hd->nch;
+  o.iso = (uint32_t)hd->iso;
+  const size_t fbytes = (size_t)1152 * sizeof(int16_t) * (size_t)nch;
+
+  /* ---- scatter: rank 0 sends the byte ranges in rank order, every other rank receives its own ---- */
+  if (R == 0) {
+    for (int r = 1; r < W; r++)
+      if (pl[r].byte_hi > pl[r].byte_lo) NK(g_nccl.Send(sl->raw_dev + pl[r].byte_lo, pl[r].byte_hi - pl[r].byte_lo, ncclUint8, r, d->comm_s, d->s_scatter));
+    CK(cudaEventRecord(d->ev_s1, d->s_scatter));
+    c->n_frames = n_total; c->n_pcm_frames = n_total; c->nch = (uint32_t)nch;
+    if ((rc = size_batch(c, sl, n_total, n_total, hd->maxg, me.ms_bytes, c->stream))) return rc;
+  } else {
+    const uint64_t len = me.byte_hi - me.byte_lo;
+    if ((rc = ensure(&sl->raw, len + 64))) return rc;
+    sl->raw_dev = (const uint8_t *)sl->raw.p;
+    if (len) NK(g_nccl.Recv(sl->raw.p, len, ncclUint8, 0, d->comm_s, d->s_scatter));
+    CK(cudaMemsetAsync((uint8_t *)sl->raw.p + len, 0, 64, d->s_scatter));
+    CK(cudaEventRecord(d->ev_s1, d->s_scatter));
+    CK(cudaStreamWaitEvent(c->stream, d->ev_s1, 0));
+    p3_parse_opts oo = o; oo.warmup_frames = (uint32_t)me.warmup; oo.max_frames = me.warmup + (me.last - me.first);
+    if (me.last > me.first) {
+      if ((rc = hop_staged(c, sl, len, &oo, &st0, c->stream))) return rc;
+      const p3_hop_result *r = c->hop.h_res;
+      if (r->n_frames != me.warmup + (me.last - me.first)) return fail(P3_EINVAL, "shard of rank %d holds %lld frames, the plan says %lld", R, (long long)r->n_frames, (long long)(me.warmup + me.last - me.first));
+      if ((rc = size_batch(c, sl, r->n_frames, r->n_pcm_frames, r->maxg, r->total_ms, c->stream))) return rc;
+    } else { c->n_frames = 0; c->n_pcm_frames = 0; c->nch = (uint32_t)nch; }
+  }
+
+  /* ---- decode the rank's frames chunk by chunk; every finished chunk's PCM goes on the wire while the next one decodes ---- */
+  const int64_t my_f0 = R == 0 ? me.first : 0, my_f1 = R == 0 ? me.last : c->n_frames;     /* frames of the staged batch this rank decodes */
+  const int64_t nchunk = (my_f1 - my_f0 + C - 1) / C;
+  if ((rc = dist_events(d, (int)(nchunk > 0 ? nchunk : 1)))) return rc;
+  c->launches = 0;
+  if (my_f1 > my_f0) {
+    if ((rc = run_sideinfo_range(c, sl, my_f0, my_f1))) return rc;
+    sl->hop_only = 0;
+  }
+  for (int64_t j = 0; j < nchunk; j++) {
+    const int64_t f0 = my_f0 + j * C, f1 = f0 + C < my_f1 ? f0 + C : my_f1;
+    if ((rc = run_chunk(c, sl, f0, f1, NULL))) return rc;
+    if (R != 0) {
+      int64_t lo, hi; chunk_slots(j, C, me.warmup, me.last - me.first, &lo, &hi);
+      CK(cudaEventRecord(d->ev_chunk[j], c->stream));
+      CK(cudaStreamWaitEvent(d->s_gather, d->ev_chunk[j], 0));
+      if (hi > lo) NK(g_nccl.Send((const uint8_t *)sl->pcm.p + (size_t)lo * fbytes, (size_t)(hi - lo) * fbytes, ncclUint8, 0, d->comm_g, d->s_gather));
+    }
+  }
+  /* ---- gather on rank 0: every (rank, chunk) block straight into its place, posted in the order the blocks become ready:
+   *      rank r's bytes leave rank 0 after those of ranks 1..r-1, then its chunks follow at the decode rate ---- */
+  if (R == 0 && W > 1) {
+    struct blk { double t; int r; int64_t lo, hi; } *bl; int nb = 0;
+    int64_t maxblk = 0; for (int r = 1; r < W; r++) maxblk += (pl[r].warmup + pl[r].last - pl[r].first + C - 1) / C + 1;
+    bl = (blk *)malloc((size_t)(maxblk > 0 ? maxblk : 1) * sizeof *bl);
+    if (!bl) return fail(P3_ENOMEM, "malloc");
+    double t_sc = 0;
+    for (int r = 1; r < W; r++) {
+      t_sc += (double)(pl[r].byte_hi - pl[r].byte_lo) / 650e3;                      /* ~650 GB/s on the wire, in microseconds */
+      const int64_t wu = pl[r].warmup, cnt = pl[r].last - pl[r].first, nc = (wu + cnt + C - 1) / C;
+      for (int64_t j = 0; j < nc; j++) {
+        int64_t lo, hi; chunk_slots(j, C, wu, cnt, &lo, &hi);
+        if (hi > lo) { bl[nb].t = t_sc + (double)(j + 1) * (double)C * 0.0105; bl[nb].r = r; bl[nb].lo = lo; bl[nb].hi = hi; nb++; }   /* ~10.5 ns of kernels per frame */
+      }
+    }
+    for (int i = 1; i < nb; i++) { blk x = bl[i]; int k = i - 1; while (k >= 0 && bl[k].t > x.t) { bl[k + 1] = bl[k]; k--; } bl[k + 1] = x; }   /* stable insertion sort: the order per rank is kept */
+    int G = 4; { const char *e = getenv("P3_GATHER_GROUP"); if (e && atoi(e) >= 1) G = atoi(e); }
+    for (int i = 0; i < nb; i += G) {
+      NK(g_nccl.GroupStart());
+      for (int k = i; k < i + G && k < nb; k++)
+        NK(g_nccl.Recv((uint8_t *)sl->pcm.p + (size_t)(pl[bl[k].r].first + bl[k].lo) * fbytes, (size_t)(bl[k].hi - bl[k].lo) * fbytes, ncclUint8, bl[k].r, d->comm_g, d->s_gather));
+      NK(g_nccl.GroupEnd());
+    }
+    free(bl);
+  }
+  /* ---- join ---- */
+  CK(cudaEventRecord(d->ev_b, d->s_gather));
+  CK(cudaStreamWaitEvent(c->stream, d->ev_b, 0));
+  if (R == 0) CK(cudaStreamWaitEvent(c->stream, d->ev_s1, 0));
+  CK(cudaEventRecord(d->ev_t1, c->stream));
+  CK(cudaStreamSynchronize(c->stream)); CK(cudaStreamSynchronize(d->s_scatter)); CK(cudaStreamSynchronize(d->s_gather));
+  c->have_next_tail_dev = 0; c->have_next_tail = 0;        /* a sharded decode is one whole stream: nothing is carried into a next call */
+  if (R == 0) { c->n_frames = n_total; c->n_pcm_frames = n_total; }
+  if (res) {
+    memset(res, 0, sizeof *res);
+    res->n_frames_total = n_total; res->n_frames_mine = me.last - me.first; res->warmup_mine = me.warmup; res->nch = nch;
+    res->stop = (int32_t)hd->stop; res->consumed = hd->consumed; res->chunks = nchunk; res->launches = c->launches;
+    res->bytes_in = R == 0 ? 0 : me.byte_hi - me.byte_lo; res->bytes_out = R == 0 ? 0 : (uint64_t)(me.last - me.first) * fbytes;
+    CK(cudaEventElapsedTime(&res->ms, d->ev_t0, d->ev_t1));
+    CK(cudaEventElapsedTime(&res->ms_scatter, d->ev_t0, d->ev_s1));
+  }
+  return P3_OK;
+}
+
+/* Floor of the gather: every rank r > 0 sends bytes_per_rank to rank 0 with nothing else going on (grouped receives from all
+ * peers at once), `iters` times; *gbs = bytes that entered rank 0 per second (max over iterations is NOT taken: the mean). */
+extern "C" int p3_dist_measure_ingest(p3_dist *d, uint64_t bytes_per_rank, int iters, float *ms_per_iter)
+{
+  if (!d || iters <= 0) return fail(P3_EINVAL, "bad argument");
+  p3_ctx *c = d->c; const int W = d->world, R = d->rank;
+  CK(cudaSetDevice(c->device));
+  dbuf *scratch = &c->slot[c->cur_slot ^ 1].pcm;
+  int rc = ensure(scratch, R == 0 ? bytes_per_rank * (uint64_t)(W > 1 ? W - 1 : 1) : bytes_per_rank);
+  if (rc) return rc;
+  for (int it = -1; it < iters; it++) {                      /* one untimed round first */
+    if (it == 0) CK(cudaEventRecord(d->ev_t0, d->s_gather));
+    if (R == 0) {
+      NK(g_nccl.GroupStart());
+      for (int r = 1; r < W; r++) NK(g_nccl.Recv((uint8_t *)scratch->p + (size_t)(r - 1) * bytes_per_rank, bytes_per_rank, ncclUint8, r, d->comm_g, d->s_gather));
+      NK(g_nccl.GroupEnd());
+    } else NK(g_nccl.Send(scratch->p, bytes_per_rank, ncclUint8, 0, d->comm_g, d->s_gather));
+  }
+  CK(cudaEventRecord(d->ev_t1, d->s_gather));
+  CK(cudaStreamSynchronize(d->s_gather));
+  float ms; CK(cudaEventElapsedTime(&ms, d->ev_t0, d->ev_t1));
+  if (ms_per_iter) *ms_per_iter = ms / iters;
+  return P3_OK;
+}
