@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["exact", "fast"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--chunk", type=int, default=65536, help="N > 1: frames per launch sequence and per PCM block on the wire")
     ap.add_argument("--workload", default="cbr320", choices=["cbr320", "vbr", "xr"], help="cbr320 = BASELINE configs[2] (headline); vbr = configs[3]; xr = configs[1] (transform kernels only)")
     a = ap.parse_args()
     global CFG, WORKLOAD
@@ -257,21 +258,57 @@ def main():
     ms = float(t.item())
     value = world * n_frames * 1152 / (ms * 1e-3)
 
-    # ---- gather of PCM to rank 0 (config 5), timed separately ----
-    gather = None
+    # ---- N > 1: BASELINE configs[4] as ONE path -- the whole stream (world x frames) resident in rank 0's HBM, device hop + shard plan
+    #      on rank 0, NCCL scatter of the byte ranges, every rank decodes its shard chunk by chunk, PCM blocks gathered into rank 0's HBM
+    #      while later chunks decode (p3_sharded_decode, NCCL called from the C side).  This is `value` for N > 1; the number above
+    #      (N independent replicas, no communication) stays as an extra key. ----
+    sharded = None
     if world > 1:
-        nbytes = n_frames * 4608
-        ptr = pdmp3_b200.lib().p3_batch_pcm_device(ctx.h, None)
-        class _W: pass
-        w = _W(); w.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-        mine = torch.as_tensor(w, device="cuda")
-        dst = [torch.empty(nbytes, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
-        barrier(); dist.gather(mine, dst, dst=0); barrier()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); dist.gather(mine, dst, dst=0); e1.record(); barrier()
-        tg = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda"); dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(tg.item()), "bytes_to_rank0": nbytes * (world - 1),
-                  "value_with_gather": world * n_frames * 1152 / ((ms + float(tg.item())) * 1e-3)}
+        replicas = {"value": value, "ms_per_step": ms, "note": "N independent replicas of the single-GPU kernel sequence, no scatter / gather"}
+        ids = [pdmp3_b200.dist_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sctx = pdmp3_b200.Context(local, pdmp3_b200.MODE_FAST if a.mode == "fast" else pdmp3_b200.MODE_EXACT)
+        dd = pdmp3_b200.Dist(sctx, ids[0], rank, world)
+        total = world * nf
+        dev = None
+        if rank == 0:
+            big = make_stream(total)
+            dev = torch.zeros(len(big) + 64, dtype=torch.uint8, device="cuda"); dev[:len(big)] = torch.from_numpy(big).cuda()
+            big_bytes = len(big); del big
+            torch.cuda.synchronize()
+        ms_steps, res = [], None
+        for it in range(max(a.warmup, 3) + a.steps):
+            barrier()
+            res = dd.sharded_decode(device_ptr=dev.data_ptr(), nbytes=big_bytes, chunk_frames=a.chunk) if rank == 0 else dd.sharded_decode(chunk_frames=a.chunk)
+            if it >= max(a.warmup, 3): ms_steps.append(res["ms"])
+        barrier()
+        tsh = torch.tensor([float(np.mean(ms_steps))], dtype=torch.float64, device="cuda"); dist.all_reduce(tsh, op=dist.ReduceOp.MAX)
+        ms_sh = float(tsh.item())
+        tsc = torch.tensor([res["ms_scatter"]], dtype=torch.float64, device="cuda"); dist.all_reduce(tsc, op=dist.ReduceOp.MAX)
+        # what landed on rank 0: the stream is a 15 625-frame block tiled, so from the second tile on every tile's PCM is the same bytes whichever rank decoded it
+        tiles_ok = None
+        if rank == 0:
+            nb = 0; ptr = pdmp3_b200.lib().p3_batch_pcm_device(sctx.h, None)
+            class _W: pass
+            w = _W(); w.__cuda_array_interface__ = {"shape": (total * 4608,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+            pcm_all = torch.as_tensor(w, device="cuda")
+            tb = BLOCK * 4608; ntile = total // BLOCK
+            ref_tile = pcm_all[tb:2 * tb]
+            tiles_ok = bool(all(torch.equal(pcm_all[k * tb:(k + 1) * tb], ref_tile) for k in range(2, ntile))) if ntile > 2 else None
+            assert res["n_frames_total"] == total and tiles_ok is not False, "gathered PCM is wrong"
+        # the floor: the same PCM bytes entering rank 0 with nothing else going on
+        barrier()
+        floor_ms = dd.measure_ingest(nf * 4608, 3)
+        tfl = torch.tensor([floor_ms], dtype=torch.float64, device="cuda"); dist.all_reduce(tfl, op=dist.ReduceOp.MAX)
+        floor_ms = float(tfl.item())
+        sharded = {"ms_per_step": ms_sh, "frames_total": total, "chunk_frames": a.chunk, "scatter_ms": float(tsc.item()),
+                   "bytes_to_rank0": nf * 4608 * (world - 1), "bytes_from_rank0": (big_bytes * (world - 1)) // world if rank == 0 else None,
+                   "ingest_floor_ms": floor_ms, "ingest_floor_GBps": nf * 4608 * (world - 1) / floor_ms / 1e6, "time_over_floor": ms_sh / floor_ms,
+                   "tiles_identical_on_rank0": tiles_ok, "launches_per_step_rank0": res["launches"],
+                   "floor": "a bare grouped ncclRecv of the same PCM bytes from all peers into rank 0 (p3_dist_measure_ingest); B200_PROFILING.md quotes 770 GB/s for a peer copy"}
+        value = total * 1152 / (ms_sh * 1e-3); ms = ms_sh; launches = res["launches"]
+        dd.close(); sctx.close(); del dev
+        sharded["replicas_no_collective"] = replicas
 
     # ---- end to end through the drop-in C API, host buffers ----
     e2e = None
@@ -318,10 +355,11 @@ def main():
     if os.path.exists(tj):
         tr = json.load(open(tj)).get(names[dom])
         if tr: traffic = tr["dram_bytes_per_frame"] * n_frames
-    roof = {"bound": "hbm", "kernel": names[dom], "achieved": alg_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+    roof = {"bound": "hbm (SURVEY 8d's label for the path; ncu shows the kernels bound by instruction issue and the FMA pipe, DRAM 17-19 % busy)", "kernel": names[dom], "achieved": alg_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": alg_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
             "algorithmic_bytes_per_frame": frame_bytes + 4608.0,
-            "whole_path": {"achieved": alg_bytes / (ms * 1e-3) / 1e9, "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak},
+            "whole_path": {"achieved": world * alg_bytes / (ms * 1e-3) / 1e9, "frac": world * alg_bytes / (ms * 1e-3) / 1e9 / (world * peak),
+                           "note": None if world == 1 else "N > 1: bound by rank 0's NVLink ingress (4608 B per frame from N-1 peers), see sharded.time_over_floor"},
             "stage_ms": {k: v for k, v in zip(names, ms_stage) if k != "-"}}
     cpu = None
     if not a.no_cpu and world == 1:
@@ -336,9 +374,10 @@ def main():
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": WORKLOAD, "frames_per_gpu": int(n_frames), "mode": a.mode,
                                  "l2": "inputs+outputs (5.6 GB per step) exceed the 126 MB L2; no flush needed",
-                                 "parallelism": "frame-sharded x%d, no data-path collective" % world, "host_parse_s": t_parse},
+                                 "parallelism": ("1 GPU" if world == 1 else "frame-sharded x%d: NCCL ncclSend/ncclRecv scatter of compressed byte ranges from rank 0, chunked ncclSend/ncclRecv gather of PCM to rank 0 (overlapped with the decode of later chunks), no collective inside the decode" % world),
+                                 "frames_total": int(world * n_frames), "host_parse_s": t_parse},
                       "clocks": clocks, "e2e": e2e, "gpu_launches": launches * a.steps, "roofline": roof, "cpu_baseline": cpu,
-                      "gather_to_rank0": gather}))
+                      "sharded": sharded}))
     sys.stdout.flush()
     if world > 1: dist.destroy_process_group()
     return 0

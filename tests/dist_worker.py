@@ -12,13 +12,13 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("gloo")                          # control plane only: the two NCCL ids travel over it
-    ids = [pdmp3_b200.dist_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
     cases = [("cfg4", dict(H.CONFIGS["cfg4_vbr_mixed"]), 700, 64), ("cfg3", dict(H.CONFIGS["cfg3_320k_js_ms"]), 3000, 256),
              ("garbage", dict(garbage_pm=200, blocks=1), 500, 96), ("mono", dict(mode=3, blocks=1, bitrate_index=7), 400, 64),
              ("tiny", dict(H.CONFIGS["cfg3_320k_js_ms"]), 3, 64)]
     for mode in (pdmp3_b200.MODE_FAST, pdmp3_b200.MODE_EXACT):
         ctx = pdmp3_b200.Context(local, mode)
+        ids = [pdmp3_b200.dist_unique_id() if rank == 0 else None]       # (a pair of NCCL ids serves one pair of communicators)
+        dist.broadcast_object_list(ids, src=0)
         d = pdmp3_b200.Dist(ctx, ids[0], rank, world)
         for name, kw, n, chunk in cases:
             for on_device in (False, True):

@@ -1,0 +1,13 @@
+# multi-GPU call: tools/gpu_dist.sh <tag> <nproc> [bench]   -> gpurun_out/<tag>_dist_worker.log (+ bench lines)
+T=${1:-r2d}; N=${2:-2}; shift; shift
+mkdir -p gpurun_out
+nvidia-smi topo -m > gpurun_out/${T}_topo.txt 2>&1
+ip addr > gpurun_out/${T}_ipaddr.txt 2>&1 || true
+NCCL_DEBUG=${NCCL_DEBUG:-WARN} timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 tests/dist_worker.py > gpurun_out/${T}_dist_worker.log 2>&1
+echo "worker rc=$?"; grep -n "DIST_OK\|Error\|error\|WARN" gpurun_out/${T}_dist_worker.log | head -30
+for a in "$@"; do
+  if [ "$a" = bench ]; then
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/${T}_bench_${N}gpu.json 2> gpurun_out/${T}_bench_${N}gpu.err
+    echo "bench rc=$?"; cut -c1-1500 gpurun_out/${T}_bench_${N}gpu.json; tail -5 gpurun_out/${T}_bench_${N}gpu.err
+  fi
+done

@@ -3,7 +3,7 @@ T=${1:-r2x}; shift
 STEPS=${*:-tests smoke bench san ncu}
 mkdir -p gpurun_out
 has() { case " $STEPS " in *" $1 "*) return 0;; esac; return 1; }
-if has tests; then ( timeout 1500 python -m pytest ${PYTEST_ARGS:-tests} -x -q -m gpu 2>&1 | tail -15 ) > gpurun_out/${T}_tests.log 2>&1; cat gpurun_out/${T}_tests.log; fi
+if has tests; then timeout 1500 python -m pytest ${PYTEST_ARGS:-tests} -x -q -m gpu > gpurun_out/${T}_tests.log 2>&1; tail -15 gpurun_out/${T}_tests.log; fi
 if has smoke; then ( timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 ) > gpurun_out/${T}_smoke.log 2>&1; cat gpurun_out/${T}_smoke.log; fi
 if has bench; then
   timeout 600 python bench.py > gpurun_out/${T}_bench_fast.json 2> gpurun_out/${T}_bench.err
