@@ -188,7 +188,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["exact", "fast"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--chunk", type=int, default=65536, help="N > 1: frames per launch sequence and per PCM block on the wire")
+    ap.add_argument("--chunk", type=int, default=262144, help="N > 1: frames per launch sequence and per PCM block on the wire")
     ap.add_argument("--workload", default="cbr320", choices=["cbr320", "vbr", "xr"], help="cbr320 = BASELINE configs[2] (headline); vbr = configs[3]; xr = configs[1] (transform kernels only)")
     a = ap.parse_args()
     global CFG, WORKLOAD
@@ -301,7 +301,9 @@ def main():
         floor_ms = dd.measure_ingest(nf * 4608, 3)
         tfl = torch.tensor([floor_ms], dtype=torch.float64, device="cuda"); dist.all_reduce(tfl, op=dist.ReduceOp.MAX)
         floor_ms = float(tfl.item())
-        sharded = {"ms_per_step": ms_sh, "frames_total": total, "chunk_frames": a.chunk, "scatter_ms": float(tsc.item()),
+        tm = torch.tensor([res["ms_staged"], res["ms_decoded"], res["ms"]], dtype=torch.float64, device="cuda")
+        tms = [torch.zeros_like(tm) for _ in range(world)]; dist.all_gather(tms, tm)
+        sharded = {"ms_per_step": ms_sh, "per_rank_ms_staged_decoded_total": [[round(float(x), 3) for x in t.tolist()] for t in tms], "frames_total": total, "chunk_frames": a.chunk, "scatter_ms": float(tsc.item()),
                    "bytes_to_rank0": nf * 4608 * (world - 1), "bytes_from_rank0": (big_bytes * (world - 1)) // world if rank == 0 else None,
                    "ingest_floor_ms": floor_ms, "ingest_floor_GBps": nf * 4608 * (world - 1) / floor_ms / 1e6, "time_over_floor": ms_sh / floor_ms,
                    "tiles_identical_on_rank0": tiles_ok, "launches_per_step_rank0": res["launches"],

@@ -196,6 +196,7 @@ typedef struct {
   int32_t  nch, stop, launches, pad_;
   uint64_t consumed, bytes_in, bytes_out;    /* bytes_in: compressed bytes this rank received; bytes_out: PCM bytes it sent */
   float    ms, ms_scatter;                   /* device time (CUDA events) of this rank's part of the call / until its scatter traffic was done */
+  float    ms_staged, ms_decoded;            /* ... until its bytes were staged and hopped / until its own frames were decoded */
 } p3_shard_result;
 int  p3_dist_unique_id(uint8_t *out256);     /* rank 0: two NCCL unique ids (scatter and gather communicators), 2 x 128 bytes, to be handed to every rank */
 int  p3_dist_init(p3_ctx *c, const uint8_t *ids256, int rank, int world, p3_dist **out);

@@ -42,7 +42,8 @@ class P3Parsed(C.Structure):
 class P3ShardResult(C.Structure):
     _fields_ = [("n_frames_total", C.c_int64), ("n_frames_mine", C.c_int64), ("warmup_mine", C.c_int64), ("chunks", C.c_int64),
                 ("nch", C.c_int32), ("stop", C.c_int32), ("launches", C.c_int32), ("pad_", C.c_int32),
-                ("consumed", C.c_uint64), ("bytes_in", C.c_uint64), ("bytes_out", C.c_uint64), ("ms", C.c_float), ("ms_scatter", C.c_float)]
+                ("consumed", C.c_uint64), ("bytes_in", C.c_uint64), ("bytes_out", C.c_uint64), ("ms", C.c_float), ("ms_scatter", C.c_float),
+                ("ms_staged", C.c_float), ("ms_decoded", C.c_float)]
 
 
 class P3Taps(C.Structure):

@@ -71,7 +71,7 @@ struct p3_dist {
   p3_ctx *c; int rank, world;
   ncclComm_t comm_s, comm_g;             /* scatter (+ plan broadcast) | gather */
   cudaStream_t s_scatter, s_gather;
-  cudaEvent_t ev_a, ev_b, ev_t0, ev_t1, ev_s1;
+  cudaEvent_t ev_a, ev_b, ev_t0, ev_t1, ev_s1, ev_h, ev_d;
   cudaEvent_t *ev_chunk; int n_ev;
   uint8_t *d_plan, *h_plan;              /* p3_shard_head + world x p3_shard_plan */
 };
@@ -114,7 +114,7 @@ extern "C" void p3_dist_destroy(p3_dist *d)
   if (d->comm_g) g_nccl.CommDestroy(d->comm_g);
   if (d->s_scatter) cudaStreamDestroy(d->s_scatter);
   if (d->s_gather) cudaStreamDestroy(d->s_gather);
-  cudaEvent_t evs[] = {d->ev_a, d->ev_b, d->ev_t0, d->ev_t1, d->ev_s1};
+  cudaEvent_t evs[] = {d->ev_a, d->ev_b, d->ev_t0, d->ev_t1, d->ev_s1, d->ev_h, d->ev_d};
   for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
   for (int i = 0; i < d->n_ev; i++) cudaEventDestroy(d->ev_chunk[i]);
   free(d->ev_chunk);
@@ -140,7 +140,7 @@ extern "C" int p3_dist_init(p3_ctx *c, const uint8_t *ids, int rank, int world, 
   DK(cudaStreamCreateWithFlags(&d->s_scatter, cudaStreamNonBlocking));
   DK(cudaStreamCreateWithFlags(&d->s_gather, cudaStreamNonBlocking));
   DK(cudaEventCreateWithFlags(&d->ev_a, cudaEventDisableTiming)); DK(cudaEventCreateWithFlags(&d->ev_b, cudaEventDisableTiming));
-  DK(cudaEventCreate(&d->ev_t0)); DK(cudaEventCreate(&d->ev_t1)); DK(cudaEventCreate(&d->ev_s1));
+  DK(cudaEventCreate(&d->ev_t0)); DK(cudaEventCreate(&d->ev_t1)); DK(cudaEventCreate(&d->ev_s1)); DK(cudaEventCreate(&d->ev_h)); DK(cudaEventCreate(&d->ev_d));
   const size_t pb = sizeof(p3_shard_head) + (size_t)world * sizeof(p3_shard_plan);
   DK(cudaMalloc(&d->d_plan, pb)); DK(cudaHostAlloc((void **)&d->h_plan, pb, cudaHostAllocPortable));
 #undef DK
@@ -162,10 +162,21 @@ static int dist_events(p3_dist *d, int n)
   return P3_OK;
 }
 
+/* Chunk schedule of a shard of nf frames (warm-up included): the first chunks are small so that PCM is on the wire early
+ * (C/4, C/4, C/2), the rest are C frames -- few enough waves of CTAs per launch that the tail of each launch stays small.
+ * Every rank derives the same schedule from the plan.  Returns the first frame of chunk j (== nf once past the end). */
+static inline int64_t chunk_start(int64_t j, int64_t C, int64_t nf)
+{
+  const int64_t q = C >= 4 * K1_FPB ? (C / 4) - (C / 4) % K1_FPB : C;
+  int64_t f = j <= 0 ? 0 : j == 1 ? q : j == 2 ? 2 * q : (q == C ? j * C : C + (j - 3) * C);
+  if (q == C) f = j * C;
+  return f < nf ? f : nf;
+}
+static inline int64_t chunk_count(int64_t C, int64_t nf) { int64_t j = 0; while (chunk_start(j, C, nf) < nf) j++; return j; }
 /* PCM slots [lo, hi) (in frames of the rank's shard) that chunk j of a shard with `wu` warm-up frames and `cnt` own frames produces */
 static inline void chunk_slots(int64_t j, int64_t C, int64_t wu, int64_t cnt, int64_t *lo, int64_t *hi)
 {
-  int64_t f0 = j * C, f1 = (j + 1) * C; if (f1 > wu + cnt) f1 = wu + cnt;
+  const int64_t f0 = chunk_start(j, C, wu + cnt), f1 = chunk_start(j + 1, C, wu + cnt);
   *lo = (f0 > wu ? f0 : wu) - wu; *hi = f1 > wu ? f1 - wu : 0;
   if (*hi < *lo) *hi = *lo;
 }
@@ -188,7 +199,7 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
   if ((rc = p3_ctx_reset(c))) return rc;                   /* every shard starts from zero state + its warm-up (rank 0: like pdmp3_open_feed) */
   p3_parse_opts o; if (o_in) o = *o_in; else memset(&o, 0, sizeof o);
   o.max_frames = 0; o.warmup_frames = 0; o.hop_only = 1;
-  int64_t C = chunk_frames > 0 ? chunk_frames : 65536;
+  int64_t C = chunk_frames > 0 ? chunk_frames : 262144;
   C -= C % K1_FPB; if (C < K1_FPB) C = K1_FPB;
   c->chunk_frames = C; c->taps = 0;
   p3_slot *sl = &c->slot[c->cur_slot];
@@ -251,15 +262,16 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
 
   /* ---- decode the rank's frames chunk by chunk; every finished chunk's PCM goes on the wire while the next one decodes ---- */
   const int64_t my_f0 = R == 0 ? me.first : 0, my_f1 = R == 0 ? me.last : c->n_frames;     /* frames of the staged batch this rank decodes */
-  const int64_t nchunk = (my_f1 - my_f0 + C - 1) / C;
+  const int64_t nchunk = chunk_count(C, my_f1 - my_f0);
   if ((rc = dist_events(d, (int)(nchunk > 0 ? nchunk : 1)))) return rc;
   c->launches = 0;
+  CK(cudaEventRecord(d->ev_h, c->stream));                 /* staged, hopped, planned (rank 0) / bytes received and hopped (others) */
   if (my_f1 > my_f0) {
     if ((rc = run_sideinfo_range(c, sl, my_f0, my_f1))) return rc;
     sl->hop_only = 0;
   }
   for (int64_t j = 0; j < nchunk; j++) {
-    const int64_t f0 = my_f0 + j * C, f1 = f0 + C < my_f1 ? f0 + C : my_f1;
+    const int64_t f0 = my_f0 + chunk_start(j, C, my_f1 - my_f0), f1 = my_f0 + chunk_start(j + 1, C, my_f1 - my_f0);
     if ((rc = run_chunk(c, sl, f0, f1, NULL))) return rc;
     if (R != 0) {
       int64_t lo, hi; chunk_slots(j, C, me.warmup, me.last - me.first, &lo, &hi);
@@ -268,20 +280,21 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
       if (hi > lo) NK(g_nccl.Send((const uint8_t *)sl->pcm.p + (size_t)lo * fbytes, (size_t)(hi - lo) * fbytes, ncclUint8, 0, d->comm_g, d->s_gather));
     }
   }
+  CK(cudaEventRecord(d->ev_d, c->stream));                 /* this rank's own frames are decoded */
   /* ---- gather on rank 0: every (rank, chunk) block straight into its place, posted in the order the blocks become ready:
    *      rank r's bytes leave rank 0 after those of ranks 1..r-1, then its chunks follow at the decode rate ---- */
   if (R == 0 && W > 1) {
     struct blk { double t; int r; int64_t lo, hi; } *bl; int nb = 0;
-    int64_t maxblk = 0; for (int r = 1; r < W; r++) maxblk += (pl[r].warmup + pl[r].last - pl[r].first + C - 1) / C + 1;
+    int64_t maxblk = 0; for (int r = 1; r < W; r++) maxblk += chunk_count(C, pl[r].warmup + pl[r].last - pl[r].first) + 1;
     bl = (blk *)malloc((size_t)(maxblk > 0 ? maxblk : 1) * sizeof *bl);
     if (!bl) return fail(P3_ENOMEM, "malloc");
     double t_sc = 0;
     for (int r = 1; r < W; r++) {
       t_sc += (double)(pl[r].byte_hi - pl[r].byte_lo) / 650e3;                      /* ~650 GB/s on the wire, in microseconds */
-      const int64_t wu = pl[r].warmup, cnt = pl[r].last - pl[r].first, nc = (wu + cnt + C - 1) / C;
+      const int64_t wu = pl[r].warmup, cnt = pl[r].last - pl[r].first, nc = chunk_count(C, wu + cnt);
       for (int64_t j = 0; j < nc; j++) {
         int64_t lo, hi; chunk_slots(j, C, wu, cnt, &lo, &hi);
-        if (hi > lo) { bl[nb].t = t_sc + (double)(j + 1) * (double)C * 0.0105; bl[nb].r = r; bl[nb].lo = lo; bl[nb].hi = hi; nb++; }   /* ~10.5 ns of kernels per frame */
+        if (hi > lo) { bl[nb].t = t_sc + (double)chunk_start(j + 1, C, wu + cnt) * 0.0105; bl[nb].r = r; bl[nb].lo = lo; bl[nb].hi = hi; nb++; }   /* ~10.5 ns of kernels per frame */
       }
     }
     for (int i = 1; i < nb; i++) { blk x = bl[i]; int k = i - 1; while (k >= 0 && bl[k].t > x.t) { bl[k + 1] = bl[k]; k--; } bl[k + 1] = x; }   /* stable insertion sort: the order per rank is kept */
@@ -309,6 +322,8 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
     res->bytes_in = R == 0 ? 0 : me.byte_hi - me.byte_lo; res->bytes_out = R == 0 ? 0 : (uint64_t)(me.last - me.first) * fbytes;
     CK(cudaEventElapsedTime(&res->ms, d->ev_t0, d->ev_t1));
     CK(cudaEventElapsedTime(&res->ms_scatter, d->ev_t0, d->ev_s1));
+    CK(cudaEventElapsedTime(&res->ms_staged, d->ev_t0, d->ev_h));
+    CK(cudaEventElapsedTime(&res->ms_decoded, d->ev_t0, d->ev_d));
   }
   return P3_OK;
 }

@@ -6,6 +6,12 @@ ip addr > gpurun_out/${T}_ipaddr.txt 2>&1 || true
 NCCL_DEBUG=${NCCL_DEBUG:-WARN} timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 tests/dist_worker.py > gpurun_out/${T}_dist_worker.log 2>&1
 echo "worker rc=$?"; grep -n "DIST_OK\|Error\|error\|WARN" gpurun_out/${T}_dist_worker.log | head -30
 for a in "$@"; do
+  if [ "$a" = chunks ]; then
+    for ch in ${CHUNKS:-131072 262144 524288}; do
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29543 bench.py --gpus $N --steps 5 --warmup 3 --no-e2e --no-cpu --chunk $ch > gpurun_out/${T}_bench_${N}gpu_c$ch.json 2>> gpurun_out/${T}_bench_${N}gpu.err
+      python -c "import json,sys; d=json.load(open('gpurun_out/${T}_bench_${N}gpu_c$ch.json')); s=d['sharded']; print('chunk', $ch, 'ms', s['ms_per_step'], 'floor', s['ingest_floor_ms'], 'x', s['time_over_floor'], s['per_rank_ms_staged_decoded_total'])"
+    done
+  fi
   if [ "$a" = bench ]; then
     timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/${T}_bench_${N}gpu.json 2> gpurun_out/${T}_bench_${N}gpu.err
     echo "bench rc=$?"; cut -c1-1500 gpurun_out/${T}_bench_${N}gpu.json; tail -5 gpurun_out/${T}_bench_${N}gpu.err
