@@ -202,6 +202,8 @@ int  p3_dist_unique_id(uint8_t *out256);     /* rank 0: two NCCL unique ids (sca
 int  p3_dist_init(p3_ctx *c, const uint8_t *ids256, int rank, int world, p3_dist **out);
 void p3_dist_destroy(p3_dist *d);
 int  p3_dist_nccl_version(void);
+int  p3_dist_gather_transport(p3_dist *d);   /* 1: PCM blocks go to rank 0 as copy-engine peer copies through a CUDA IPC mapping of its output buffer
+                                                (no SM on either end); 0: ncclSend / ncclRecv (P3_GATHER=nccl, or the mapping is not possible) */
 /* collective over all ranks; rank 0 passes the stream (host memory, or device memory when raw_on_device: used in place, 64
  * readable bytes must follow), the others NULL.  Afterwards rank 0 holds the PCM of the whole stream in the context's PCM
  * buffer: p3_batch_pcm_device() / p3_batch_download(). */

@@ -86,6 +86,7 @@ def lib():
     L.p3_dist_unique_id.argtypes = [C.c_void_p]
     L.p3_dist_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     L.p3_dist_destroy.argtypes = [C.c_void_p]
+    L.p3_dist_gather_transport.argtypes = [C.c_void_p]
     L.p3_sharded_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(P3ParseOpts), C.c_int64, C.POINTER(P3ShardResult)]
     L.p3_dist_measure_ingest.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_float)]
     L.p3_batch_run.argtypes = [C.c_void_p]
@@ -332,6 +333,9 @@ class Dist:
         out = np.zeros((res["n_frames_total"], 1152, res["nch"]), np.int16)
         _check(lib().p3_batch_download(self.ctx.h, out.ctypes.data, None), "p3_batch_download")
         return out
+
+    def gather_transport(self):
+        return "cuda-ipc copy engine" if lib().p3_dist_gather_transport(self.h) == 1 else "nccl send/recv"
 
     def measure_ingest(self, bytes_per_rank, iters=3):
         ms = C.c_float()

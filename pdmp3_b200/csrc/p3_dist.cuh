@@ -16,6 +16,13 @@
  *
  * Two communicators so that the scatter (rank 0 egress) and the gather (rank 0 ingress) run side by side: NVLink is full
  * duplex and rank 0's ingress -- 4608 bytes per frame from W-1 peers -- is the floor of this configuration.
+ *
+ * Gather transport.  NCCL's point-to-point kernels occupy SMs on both ends while the decode kernels want all of them (measured
+ * at 2 GPUs: the decode of 10^6 frames takes 11.7-13.5 ms instead of 9.6 ms next to them).  Where CUDA IPC works between the
+ * ranks (one box, one container: it does) rank 0 therefore exports its output buffer, every rank maps it, and a finished
+ * chunk's PCM goes straight to its place in rank 0's HBM with a copy-engine peer copy over NVLink (no SM involved, no
+ * matching receive to schedule); NCCL then only carries the plan, the byte ranges and a completion token per rank.
+ * P3_GATHER=nccl forces the ncclSend/ncclRecv gather (the fallback when a mapping fails).
  * No collective touches the decode itself: shards are independent (warm-up rule of SURVEY 3.5, as pdmp3_b200/shard.py).
  */
 #include <dlfcn.h>
@@ -33,6 +40,7 @@ struct nccl_api {
   ncclResult_t (*GroupEnd)(void);
   const char *(*GetErrorString)(ncclResult_t);
   ncclResult_t (*GetVersion)(int *);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
 };
 static nccl_api g_nccl;
 
@@ -48,7 +56,7 @@ static int nccl_load(void)
   NCCL_SYM(GetUniqueId, "ncclGetUniqueId"); NCCL_SYM(CommInitRank, "ncclCommInitRank"); NCCL_SYM(CommDestroy, "ncclCommDestroy");
   NCCL_SYM(Send, "ncclSend"); NCCL_SYM(Recv, "ncclRecv"); NCCL_SYM(Broadcast, "ncclBroadcast");
   NCCL_SYM(GroupStart, "ncclGroupStart"); NCCL_SYM(GroupEnd, "ncclGroupEnd"); NCCL_SYM(GetErrorString, "ncclGetErrorString");
-  NCCL_SYM(GetVersion, "ncclGetVersion");
+  NCCL_SYM(GetVersion, "ncclGetVersion"); NCCL_SYM(AllReduce, "ncclAllReduce");
 #undef NCCL_SYM
   g_nccl.h = h;
   return P3_OK;
@@ -65,6 +73,8 @@ typedef struct {                          /* broadcast in front of the plans */
   int64_t n_frames; int32_t nch, iso; uint32_t maxg, stop; uint64_t consumed;
 } p3_shard_head;
 
+typedef struct { cudaIpcMemHandle_t h; uint64_t bytes; uint64_t serial; } p3_ipc_msg;   /* rank 0's output buffer, for the peers to map */
+
 #define P3_DIST_MAXW 16
 
 struct p3_dist {
@@ -74,6 +84,12 @@ struct p3_dist {
   cudaEvent_t ev_a, ev_b, ev_t0, ev_t1, ev_s1, ev_h, ev_d;
   cudaEvent_t *ev_chunk; int n_ev;
   uint8_t *d_plan, *h_plan;              /* p3_shard_head + world x p3_shard_plan */
+  /* copy-engine gather through a CUDA IPC mapping of rank 0's output buffer */
+  int use_ipc;                           /* 1: agreed by all ranks at init */
+  p3_ipc_msg *d_ipc, *h_ipc;             /* message buffer (device for the broadcast, page-locked host copy) */
+  void *exp_ptr; uint64_t exp_serial; cudaIpcMemHandle_t exp_handle;   /* rank 0: the buffer the current handle stands for */
+  void *map_ptr; uint64_t map_serial;    /* peers: the mapping currently open */
+  int *d_tok;                            /* completion tokens */
 };
 
 /* plan of every rank from the frame records of the whole stream (same rule as pdmp3_b200/shard.py::plan_shards): one thread per rank */
@@ -119,6 +135,8 @@ extern "C" void p3_dist_destroy(p3_dist *d)
   for (int i = 0; i < d->n_ev; i++) cudaEventDestroy(d->ev_chunk[i]);
   free(d->ev_chunk);
   cudaFree(d->d_plan); if (d->h_plan) cudaFreeHost(d->h_plan);
+  if (d->map_ptr) cudaIpcCloseMemHandle(d->map_ptr);
+  cudaFree(d->d_ipc); if (d->h_ipc) cudaFreeHost(d->h_ipc); cudaFree(d->d_tok);
   free(d);
 }
 
@@ -141,13 +159,38 @@ extern "C" int p3_dist_init(p3_ctx *c, const uint8_t *ids, int rank, int world, 
   DK(cudaStreamCreateWithFlags(&d->s_gather, cudaStreamNonBlocking));
   DK(cudaEventCreateWithFlags(&d->ev_a, cudaEventDisableTiming)); DK(cudaEventCreateWithFlags(&d->ev_b, cudaEventDisableTiming));
   DK(cudaEventCreate(&d->ev_t0)); DK(cudaEventCreate(&d->ev_t1)); DK(cudaEventCreate(&d->ev_s1)); DK(cudaEventCreate(&d->ev_h)); DK(cudaEventCreate(&d->ev_d));
-  const size_t pb = sizeof(p3_shard_head) + (size_t)world * sizeof(p3_shard_plan);
+  const size_t pb = sizeof(p3_shard_head) + (size_t)world * sizeof(p3_shard_plan) + sizeof(p3_ipc_msg);
   DK(cudaMalloc(&d->d_plan, pb)); DK(cudaHostAlloc((void **)&d->h_plan, pb, cudaHostAllocPortable));
+  DK(cudaMalloc(&d->d_ipc, sizeof(p3_ipc_msg))); DK(cudaHostAlloc((void **)&d->h_ipc, sizeof(p3_ipc_msg), cudaHostAllocPortable));
+  DK(cudaMalloc(&d->d_tok, (size_t)(world + 1) * sizeof(int))); DK(cudaMemset(d->d_tok, 0, (size_t)(world + 1) * sizeof(int)));
 #undef DK
 #undef DN
+  /* can every rank map rank 0's memory?  (one trial allocation; the answer is agreed with an all-reduce) */
+  {
+    const char *e = getenv("P3_GATHER");
+    int want = !(e && !strcmp(e, "nccl")), ok = want;
+    void *probe = NULL, *mapped = NULL;
+    if (rank == 0) { if (cudaMalloc(&probe, 1 << 20) != cudaSuccess || cudaIpcGetMemHandle(&d->h_ipc->h, probe) != cudaSuccess) ok = 0; }
+    if (rank == 0) cudaMemcpy(d->d_ipc, d->h_ipc, sizeof(p3_ipc_msg), cudaMemcpyHostToDevice);
+    if (g_nccl.Broadcast(d->d_ipc, d->d_ipc, sizeof(p3_ipc_msg), ncclUint8, 0, d->comm_s, d->s_scatter) != ncclSuccess) ok = 0;
+    cudaMemcpyAsync(d->h_ipc, d->d_ipc, sizeof(p3_ipc_msg), cudaMemcpyDeviceToHost, d->s_scatter); cudaStreamSynchronize(d->s_scatter);
+    if (rank != 0 && ok) { if (cudaIpcOpenMemHandle(&mapped, d->h_ipc->h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); } }
+    int *flag = d->d_tok + world;
+    cudaMemcpy(flag, &ok, sizeof(int), cudaMemcpyHostToDevice);
+    if (g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMin, d->comm_s, d->s_scatter) != ncclSuccess) ok = 0;
+    int agreed = 0; cudaMemcpyAsync(&agreed, flag, sizeof(int), cudaMemcpyDeviceToHost, d->s_scatter); cudaStreamSynchronize(d->s_scatter);
+    if (mapped) cudaIpcCloseMemHandle(mapped);
+    /* (rank 0 frees the probe only after every peer has closed it: one more collective as the barrier) */
+    g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMin, d->comm_s, d->s_scatter); cudaStreamSynchronize(d->s_scatter);
+    if (probe) cudaFree(probe);
+    d->use_ipc = ok && agreed;
+    cudaGetLastError();
+  }
   *out = d;
   return P3_OK;
 }
+
+extern "C" int p3_dist_gather_transport(p3_dist *d) { return d ? d->use_ipc : -1; }     /* 1: copy-engine peer copies through CUDA IPC, 0: ncclSend / ncclRecv */
 
 extern "C" int p3_dist_nccl_version(void) { int v = 0; if (nccl_load() == P3_OK) g_nccl.GetVersion(&v); return v; }
 
@@ -205,7 +248,8 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
   p3_slot *sl = &c->slot[c->cur_slot];
   slot_release(sl);
   p3_shard_head *hd = (p3_shard_head *)d->h_plan; p3_shard_plan *pl = (p3_shard_plan *)(d->h_plan + sizeof(p3_shard_head));
-  const size_t pb = sizeof(p3_shard_head) + (size_t)W * sizeof(p3_shard_plan);
+  const size_t pb = sizeof(p3_shard_head) + (size_t)W * sizeof(p3_shard_plan) + sizeof(p3_ipc_msg);
+  p3_ipc_msg *ipc = (p3_ipc_msg *)(d->h_plan + sizeof(p3_shard_head) + (size_t)W * sizeof(p3_shard_plan));
   const p3_parse_state st0 = {0, 0, 0, -1, -1};
   CK(cudaEventRecord(d->ev_t0, c->stream));
 
@@ -225,12 +269,30 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
     CK(cudaMemcpyAsync(d->d_plan, hd, sizeof *hd, cudaMemcpyHostToDevice, c->stream));
     k_shard_plan<<<1, 32, 0, c->stream>>>((const p3_frame *)sl->frames.p, r->n_frames, W, (p3_shard_plan *)(d->d_plan + sizeof(p3_shard_head)));
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(pl, d->d_plan + sizeof(p3_shard_head), (size_t)W * sizeof(p3_shard_plan), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    /* the output buffer (PCM of the whole stream) and, for the copy-engine gather, its IPC handle: it travels with the plan */
+    c->n_frames = r->n_frames; c->n_pcm_frames = r->n_frames; c->nch = (uint32_t)r->nch;
+    if ((rc = size_batch(c, sl, r->n_frames, r->n_frames, r->maxg, pl[0].ms_bytes, c->stream))) return rc;
+    memset(ipc, 0, sizeof *ipc);
+    if (d->use_ipc && W > 1) {
+      if (d->exp_ptr != sl->pcm.p) { CK(cudaIpcGetMemHandle(&d->exp_handle, sl->pcm.p)); d->exp_ptr = sl->pcm.p; d->exp_serial++; }
+      ipc->h = d->exp_handle; ipc->bytes = sl->pcm.cap; ipc->serial = d->exp_serial;
+    }
+    CK(cudaMemcpyAsync(d->d_plan + pb - sizeof(p3_ipc_msg), ipc, sizeof *ipc, cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(d->ev_a, c->stream));
     CK(cudaStreamWaitEvent(d->s_scatter, d->ev_a, 0));
   }
   NK(g_nccl.Broadcast(d->d_plan, d->d_plan, pb, ncclUint8, 0, d->comm_s, d->s_scatter));
-  CK(cudaMemcpyAsync(d->h_plan, d->d_plan, pb, cudaMemcpyDeviceToHost, d->s_scatter));
-  CK(cudaStreamSynchronize(d->s_scatter));
+  if (R != 0) {
+    CK(cudaMemcpyAsync(d->h_plan, d->d_plan, pb, cudaMemcpyDeviceToHost, d->s_scatter));
+    CK(cudaStreamSynchronize(d->s_scatter));
+    if (d->use_ipc && (!d->map_ptr || d->map_serial != ipc->serial)) {      /* map rank 0's output buffer (kept until it moves) */
+      if (d->map_ptr) { cudaIpcCloseMemHandle(d->map_ptr); d->map_ptr = NULL; }
+      CK(cudaIpcOpenMemHandle(&d->map_ptr, ipc->h, cudaIpcMemLazyEnablePeerAccess));
+      d->map_serial = ipc->serial;
+    }
+  }
   const p3_shard_plan me = pl[R];
   const int64_t n_total = hd->n_frames; const int nch = hd->nch;
   o.iso = (uint32_t)hd->iso;
@@ -241,8 +303,6 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
     for (int r = 1; r < W; r++)
       if (pl[r].byte_hi > pl[r].byte_lo) NK(g_nccl.Send(sl->raw_dev + pl[r].byte_lo, pl[r].byte_hi - pl[r].byte_lo, ncclUint8, r, d->comm_s, d->s_scatter));
     CK(cudaEventRecord(d->ev_s1, d->s_scatter));
-    c->n_frames = n_total; c->n_pcm_frames = n_total; c->nch = (uint32_t)nch;
-    if ((rc = size_batch(c, sl, n_total, n_total, hd->maxg, me.ms_bytes, c->stream))) return rc;
   } else {
     const uint64_t len = me.byte_hi - me.byte_lo;
     if ((rc = ensure(&sl->raw, len + 64))) return rc;
@@ -277,13 +337,25 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
       int64_t lo, hi; chunk_slots(j, C, me.warmup, me.last - me.first, &lo, &hi);
       CK(cudaEventRecord(d->ev_chunk[j], c->stream));
       CK(cudaStreamWaitEvent(d->s_gather, d->ev_chunk[j], 0));
-      if (hi > lo) NK(g_nccl.Send((const uint8_t *)sl->pcm.p + (size_t)lo * fbytes, (size_t)(hi - lo) * fbytes, ncclUint8, 0, d->comm_g, d->s_gather));
+      if (hi > lo) {
+        if (d->use_ipc)                                      /* copy engine, straight into rank 0's output buffer over NVLink */
+          CK(cudaMemcpyAsync((uint8_t *)d->map_ptr + (size_t)(me.first + lo) * fbytes, (const uint8_t *)sl->pcm.p + (size_t)lo * fbytes, (size_t)(hi - lo) * fbytes, cudaMemcpyDeviceToDevice, d->s_gather));
+        else NK(g_nccl.Send((const uint8_t *)sl->pcm.p + (size_t)lo * fbytes, (size_t)(hi - lo) * fbytes, ncclUint8, 0, d->comm_g, d->s_gather));
+      }
+    }
+  }
+  if (d->use_ipc && W > 1) {                                 /* completion: a token per rank once its copies have landed */
+    if (R != 0) NK(g_nccl.Send(d->d_tok + R, sizeof(int), ncclUint8, 0, d->comm_g, d->s_gather));
+    else {
+      NK(g_nccl.GroupStart());
+      for (int r = 1; r < W; r++) NK(g_nccl.Recv(d->d_tok + r, sizeof(int), ncclUint8, r, d->comm_g, d->s_gather));
+      NK(g_nccl.GroupEnd());
     }
   }
   CK(cudaEventRecord(d->ev_d, c->stream));                 /* this rank's own frames are decoded */
   /* ---- gather on rank 0: every (rank, chunk) block straight into its place, posted in the order the blocks become ready:
    *      rank r's bytes leave rank 0 after those of ranks 1..r-1, then its chunks follow at the decode rate ---- */
-  if (R == 0 && W > 1) {
+  if (R == 0 && W > 1 && !d->use_ipc) {
     struct blk { double t; int r; int64_t lo, hi; } *bl; int nb = 0;
     int64_t maxblk = 0; for (int r = 1; r < W; r++) maxblk += chunk_count(C, pl[r].warmup + pl[r].last - pl[r].first) + 1;
     bl = (blk *)malloc((size_t)(maxblk > 0 ? maxblk : 1) * sizeof *bl);
