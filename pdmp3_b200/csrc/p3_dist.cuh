@@ -73,7 +73,22 @@ typedef struct {                          /* broadcast in front of the plans */
   int64_t n_frames; int32_t nch, iso; uint32_t maxg, stop; uint64_t consumed;
 } p3_shard_head;
 
-typedef struct { cudaIpcMemHandle_t h; uint64_t bytes; uint64_t serial; } p3_ipc_msg;   /* rank 0's output buffer, for the peers to map */
+typedef struct {                          /* rank 0's buffers, for the peers to map (travels with the plan) */
+  cudaIpcMemHandle_t h; uint64_t bytes; uint64_t serial;          /* the output buffer (PCM of the whole stream) */
+  cudaIpcMemHandle_t h_raw; uint64_t raw_off; uint64_t raw_serial; /* the allocation holding the byte stream, and where the stream starts in it; serial 0: not mappable, the bytes come by ncclSend */
+} p3_ipc_msg;
+
+/* base of the allocation a device pointer lies in (driver API, taken from the libcuda the runtime has already loaded) */
+static int alloc_base(const void *p, void **base, size_t *size)
+{
+  typedef int (*fn_t)(unsigned long long *, size_t *, unsigned long long);
+  static fn_t fn; static int tried;
+  if (!tried) { tried = 1; void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_NOLOAD); if (!h) h = dlopen("libcuda.so.1", RTLD_NOW); if (h) fn = (fn_t)dlsym(h, "cuMemGetAddressRange_v2"); }
+  unsigned long long b = 0; size_t n = 0;
+  if (!fn || fn(&b, &n, (unsigned long long)(uintptr_t)p) != 0) return -1;
+  *base = (void *)(uintptr_t)b; *size = n;
+  return 0;
+}
 
 #define P3_DIST_MAXW 16
 
@@ -89,6 +104,8 @@ struct p3_dist {
   p3_ipc_msg *d_ipc, *h_ipc;             /* message buffer (device for the broadcast, page-locked host copy) */
   void *exp_ptr; uint64_t exp_serial; cudaIpcMemHandle_t exp_handle;   /* rank 0: the buffer the current handle stands for */
   void *map_ptr; uint64_t map_serial;    /* peers: the mapping currently open */
+  void *exp_raw; uint64_t exp_raw_serial; cudaIpcMemHandle_t exp_raw_handle;   /* same for the allocation that holds the byte stream */
+  void *map_raw; uint64_t map_raw_serial;
   int *d_tok;                            /* completion tokens */
 };
 
@@ -136,6 +153,7 @@ extern "C" void p3_dist_destroy(p3_dist *d)
   free(d->ev_chunk);
   cudaFree(d->d_plan); if (d->h_plan) cudaFreeHost(d->h_plan);
   if (d->map_ptr) cudaIpcCloseMemHandle(d->map_ptr);
+  if (d->map_raw) cudaIpcCloseMemHandle(d->map_raw);
   cudaFree(d->d_ipc); if (d->h_ipc) cudaFreeHost(d->h_ipc); cudaFree(d->d_tok);
   free(d);
 }
@@ -205,14 +223,21 @@ static int dist_events(p3_dist *d, int n)
   return P3_OK;
 }
 
-/* Chunk schedule of a shard of nf frames (warm-up included): the first chunks are small so that PCM is on the wire early
- * (C/4, C/4, C/2), the rest are C frames -- few enough waves of CTAs per launch that the tail of each launch stays small.
- * Every rank derives the same schedule from the plan.  Returns the first frame of chunk j (== nf once past the end). */
+/* Chunk schedule of a shard of nf frames (warm-up included): small chunks first so that PCM is on the wire early (C/4, C/4,
+ * C/2), C frames in the middle -- few enough waves of CTAs per launch that the tail of each launch stays small --, small
+ * chunks again at the end (C/2, C/4, C/4) so that little is left to send once the last kernel has finished.  Every rank
+ * derives the same schedule from the plan.  Returns the first frame of chunk j (== nf once past the end). */
 static inline int64_t chunk_start(int64_t j, int64_t C, int64_t nf)
 {
-  const int64_t q = C >= 4 * K1_FPB ? (C / 4) - (C / 4) % K1_FPB : C;
-  int64_t f = j <= 0 ? 0 : j == 1 ? q : j == 2 ? 2 * q : (q == C ? j * C : C + (j - 3) * C);
-  if (q == C) f = j * C;
+  const int64_t q = (C / 4) - (C / 4) % K1_FPB;
+  if (q < K1_FPB || nf < 3 * C) { const int64_t f = j * (q >= K1_FPB && nf < 3 * C && nf >= 8 * q ? q : C); return f < nf ? f : nf; }   /* short shards: uniform chunks */
+  const int64_t body0 = 4 * q, body1 = nf - 4 * q - (nf - 4 * q) % K1_FPB;                 /* head [0, 4q) | body | tail [body1, nf) */
+  const int64_t nbody = (body1 - body0 + C - 1) / C;
+  int64_t f;
+  if (j <= 0) f = 0; else if (j == 1) f = q; else if (j == 2) f = 2 * q;
+  else if (j < 3 + nbody) f = body0 + (j - 3) * C;
+  else if (j == 3 + nbody) f = body1; else if (j == 4 + nbody) f = body1 + 2 * q; else if (j == 5 + nbody) f = body1 + 3 * q;
+  else f = nf;
   return f < nf ? f : nf;
 }
 static inline int64_t chunk_count(int64_t C, int64_t nf) { int64_t j = 0; while (chunk_start(j, C, nf) < nf) j++; return j; }
@@ -278,6 +303,15 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
     if (d->use_ipc && W > 1) {
       if (d->exp_ptr != sl->pcm.p) { CK(cudaIpcGetMemHandle(&d->exp_handle, sl->pcm.p)); d->exp_ptr = sl->pcm.p; d->exp_serial++; }
       ipc->h = d->exp_handle; ipc->bytes = sl->pcm.cap; ipc->serial = d->exp_serial;
+      /* the byte stream: the peers pull their ranges with the copy engine if the allocation can be exported */
+      void *base = NULL; size_t asz = 0;
+      if (alloc_base(sl->raw_dev, &base, &asz) == 0) {
+        if (d->exp_raw != base) {
+          if (cudaIpcGetMemHandle(&d->exp_raw_handle, base) == cudaSuccess) { d->exp_raw = base; d->exp_raw_serial = ++d->exp_serial; }
+          else { cudaGetLastError(); d->exp_raw = NULL; }
+        }
+        if (d->exp_raw == base) { ipc->h_raw = d->exp_raw_handle; ipc->raw_off = (uint64_t)(sl->raw_dev - (const uint8_t *)base); ipc->raw_serial = d->exp_raw_serial; }
+      }
     }
     CK(cudaMemcpyAsync(d->d_plan + pb - sizeof(p3_ipc_msg), ipc, sizeof *ipc, cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(d->ev_a, c->stream));
@@ -292,22 +326,35 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
       CK(cudaIpcOpenMemHandle(&d->map_ptr, ipc->h, cudaIpcMemLazyEnablePeerAccess));
       d->map_serial = ipc->serial;
     }
+    if (d->use_ipc && ipc->raw_serial && (!d->map_raw || d->map_raw_serial != ipc->raw_serial)) {
+      if (d->map_raw) { cudaIpcCloseMemHandle(d->map_raw); d->map_raw = NULL; }
+      CK(cudaIpcOpenMemHandle(&d->map_raw, ipc->h_raw, cudaIpcMemLazyEnablePeerAccess));
+      d->map_raw_serial = ipc->raw_serial;
+    }
   }
+  const int pull = d->use_ipc && ipc->raw_serial != 0;      /* scatter by copy-engine pulls (every rank knows: the flag travelled with the plan) */
   const p3_shard_plan me = pl[R];
   const int64_t n_total = hd->n_frames; const int nch = hd->nch;
   o.iso = (uint32_t)hd->iso;
   const size_t fbytes = (size_t)1152 * sizeof(int16_t) * (size_t)nch;
 
-  /* ---- scatter: rank 0 sends the byte ranges in rank order, every other rank receives its own ---- */
+  /* ---- scatter: the byte ranges leave rank 0 in rank order (rank 1 can start decoding while rank 7 still waits).
+   *      Copy-engine variant: rank r pulls its range out of rank 0's buffer, and passes a token to rank r+1 when it has it;
+   *      NCCL variant: rank 0 sends the ranges one after the other. ---- */
   if (R == 0) {
-    for (int r = 1; r < W; r++)
-      if (pl[r].byte_hi > pl[r].byte_lo) NK(g_nccl.Send(sl->raw_dev + pl[r].byte_lo, pl[r].byte_hi - pl[r].byte_lo, ncclUint8, r, d->comm_s, d->s_scatter));
+    if (!pull)
+      for (int r = 1; r < W; r++)
+        if (pl[r].byte_hi > pl[r].byte_lo) NK(g_nccl.Send(sl->raw_dev + pl[r].byte_lo, pl[r].byte_hi - pl[r].byte_lo, ncclUint8, r, d->comm_s, d->s_scatter));
     CK(cudaEventRecord(d->ev_s1, d->s_scatter));
   } else {
     const uint64_t len = me.byte_hi - me.byte_lo;
     if ((rc = ensure(&sl->raw, len + 64))) return rc;
     sl->raw_dev = (const uint8_t *)sl->raw.p;
-    if (len) NK(g_nccl.Recv(sl->raw.p, len, ncclUint8, 0, d->comm_s, d->s_scatter));
+    if (pull) {
+      if (R > 1) NK(g_nccl.Recv(d->d_tok, sizeof(int), ncclUint8, R - 1, d->comm_s, d->s_scatter));
+      if (len) CK(cudaMemcpyAsync(sl->raw.p, (const uint8_t *)d->map_raw + ipc->raw_off + me.byte_lo, len, cudaMemcpyDeviceToDevice, d->s_scatter));
+      if (R + 1 < W) NK(g_nccl.Send(d->d_tok, sizeof(int), ncclUint8, R + 1, d->comm_s, d->s_scatter));
+    } else if (len) NK(g_nccl.Recv(sl->raw.p, len, ncclUint8, 0, d->comm_s, d->s_scatter));
     CK(cudaMemsetAsync((uint8_t *)sl->raw.p + len, 0, 64, d->s_scatter));
     CK(cudaEventRecord(d->ev_s1, d->s_scatter));
     CK(cudaStreamWaitEvent(c->stream, d->ev_s1, 0));
