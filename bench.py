@@ -188,7 +188,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["exact", "fast"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--chunk", type=int, default=262144, help="N > 1: frames per launch sequence and per PCM block on the wire")
+    ap.add_argument("--chunk", type=int, default=0, help="N > 1: frames per launch sequence and per PCM block on the wire (0: the library default, four waves of the synthesis kernel)")
     ap.add_argument("--workload", default="cbr320", choices=["cbr320", "vbr", "xr"], help="cbr320 = BASELINE configs[2] (headline); vbr = configs[3]; xr = configs[1] (transform kernels only)")
     a = ap.parse_args()
     global CFG, WORKLOAD

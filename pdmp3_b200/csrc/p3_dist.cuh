@@ -251,7 +251,7 @@ static inline void chunk_slots(int64_t j, int64_t C, int64_t wu, int64_t cnt, in
 
 /* The sharded decode.  Rank 0: `raw` is the whole stream (host memory, or device memory when raw_on_device -- then it is used
  * in place and must be followed by 64 readable bytes); other ranks pass NULL / 0.  chunk_frames: frames per launch sequence and
- * per PCM block on the wire (<= 0: 65536; rounded to a multiple of 32).  On return rank 0's PCM of the WHOLE stream is in the
+ * per PCM block on the wire (<= 0: four waves of the synthesis kernel, 227 328 frames on a B200; rounded to a multiple of 32).  On return rank 0's PCM of the WHOLE stream is in the
  * context's PCM buffer (p3_batch_pcm_device(), p3_batch_download()), [n_frames][1152][nch] int16.  res (optional):
  * frames decoded by this rank, frames of the stream, device time of this rank's part in ms (CUDA events, from the first
  * byte staged to the last PCM block sent / received), and of the scatter alone. */
@@ -267,7 +267,9 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
   if ((rc = p3_ctx_reset(c))) return rc;                   /* every shard starts from zero state + its warm-up (rank 0: like pdmp3_open_feed) */
   p3_parse_opts o; if (o_in) o = *o_in; else memset(&o, 0, sizeof o);
   o.max_frames = 0; o.warmup_frames = 0; o.hop_only = 1;
-  int64_t C = chunk_frames > 0 ? chunk_frames : 262144;
+  /* default chunk: four waves of the synthesis kernel (n_sm x 3 CTAs x 4 warps x 32 frames = 56 832 frames on a B200), so that the
+   * quarter chunks at both ends of the schedule are exactly one wave and no launch ends in a mostly empty wave */
+  int64_t C = chunk_frames > 0 ? chunk_frames : 4 * (int64_t)c->n_sm * 3 * p3_synthw_warps_per_cta() * c->fpc;
   C -= C % K1_FPB; if (C < K1_FPB) C = K1_FPB;
   c->chunk_frames = C; c->taps = 0;
   p3_slot *sl = &c->slot[c->cur_slot];
