@@ -169,11 +169,15 @@ int p3_batch_upload(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_
 int p3_batch_upload_raw(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, int raw_on_device, const p3_parse_opts *opts,
                         const p3_parse_state *state, p3_parsed *info);
 int p3_batch_channels(p3_ctx *c);                     /* channels of the staged batch (1 or 2) */
+float p3_hop_ms(p3_ctx *c);                           /* device time of the last device hop (CUDA events: kernels + result read-backs) */
 int p3_hop_rounds(p3_ctx *c);                         /* resolution rounds the last device hop needed (1 = every speculative chain met the true one) */
 /* device hop + decode + download in one call: the counterpart of p3_parse() + p3_decode_batch(); *state is advanced,
  * info->consumed says where the next call continues; at most pcm_cap_frames frames are decoded (<= 0: no limit) */
 int p3_decode_raw(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parse_opts *opts, p3_parse_state *state, p3_parsed *info,
                   int16_t *pcm, int64_t pcm_cap_frames, const p3_taps *host_taps);
+/* asynchronous, double-buffered variant behind pdmp3_read(): returns as soon as the hop result is known; raw / pcm stay in
+ * use until p3_batch_sync() */
+int p3_decode_raw_async(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parse_opts *opts, p3_parse_state *state, p3_parsed *info, int16_t *pcm);
 int p3_batch_run(p3_ctx *c);                          /* launches the kernel sequence on the ctx stream */
 int p3_batch_sync(p3_ctx *c);
 int p3_batch_download(p3_ctx *c, int16_t *pcm, const p3_taps *host_taps);

@@ -82,6 +82,8 @@ def lib():
     L.p3_decode_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3ParseOpts), C.POINTER(P3ParseState), C.POINTER(P3Parsed),
                                 C.c_void_p, C.c_int64, C.POINTER(P3Taps)]
     L.p3_hop_rounds.argtypes = [C.c_void_p]
+    L.p3_hop_ms.argtypes = [C.c_void_p]
+    L.p3_hop_ms.restype = C.c_float
     L.p3_batch_channels.argtypes = [C.c_void_p]
     L.p3_dist_unique_id.argtypes = [C.c_void_p]
     L.p3_dist_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
@@ -233,7 +235,7 @@ class Context:
         _check(lib().p3_batch_upload_raw(self.h, self._raw.ctypes.data if len(self._raw) else None, len(self._raw), 0, C.byref(o), C.byref(st), C.byref(info)), "p3_batch_upload_raw")
         self._up = None
         return dict(n_frames=info.n_frames, n_pcm_frames=info.n_pcm_frames, consumed=info.consumed, stop=info.stop, rounds=lib().p3_hop_rounds(self.h),
-                    nch=lib().p3_batch_channels(self.h))
+                    nch=lib().p3_batch_channels(self.h), hop_ms=lib().p3_hop_ms(self.h))
 
     def download_raw(self, info):
         """PCM of the batch staged by upload_raw() (after run())"""

@@ -43,6 +43,7 @@ struct pdmp3_handle {
   int in_pinned;
   p3_frame *dfr[3]; p3_gc *dgc[3]; int dnext;       /* page-locked descriptor arrays, rotated over the in-flight batches */
   p3_ctx *ctx; int device; int ctx_failed; int mode; int host_sideinfo; int iso;
+  int host_hop; size_t bpf_est;                     /* hop=host: frame hop on the host (default: on the device); bytes per frame seen so far */
   p3_parse_state ps;
   int new_header;                                   /* 0 none yet, 1 seen, -1 reported (pdmp3.c:1318,2470,2531) */
   int nch, sfreq;
@@ -62,6 +63,7 @@ pdmp3_handle *pdmp3_new(const char *decoder, int *error)
     if ((p = strstr(decoder, "device="))) id->device = atoi(p + 7);
     if (strstr(decoder, "mode=exact")) id->mode = P3_MODE_EXACT;   /* bit-identical PCM; default is FAST (<= 1 LSB) */
     if (strstr(decoder, "sideinfo=host")) id->host_sideinfo = 1;   /* parse the side info on the host instead of on the device */
+    if (strstr(decoder, "hop=host") || id->host_sideinfo) id->host_hop = 1;   /* frame hop of large reads on the host as well (default: on the device, p3_hop.cu) */
     for (p = decoder; (p = strstr(p, "iso")) != NULL; p += 3)     /* "iso" as an option of its own: ISO 11172-3 semantics instead of the reference's quirks (P3_FRAME_ISO) */
       if ((p == decoder || p[-1] == ':' || p[-1] == ',') && (p[3] == 0 || p[3] == ',')) id->iso = 1;
   }
@@ -86,7 +88,7 @@ int pdmp3_open_feed(pdmp3_handle *id)
 {
   if (!id) return PDMP3_ERR;
   id->istart = id->iend = 0; id->processed = 0; id->new_header = 0;
-  id->pend_pos = id->pend_end = 0;
+  id->pend_pos = id->pend_end = 0; id->bpf_est = 0;
   memset(&id->ps, 0, sizeof id->ps); id->ps.nch = id->ps.sfreq = -1;
   if (id->ctx) p3_ctx_reset(id->ctx);               /* hsynth_init / synth_init / g_main_data_top (pdmp3.c:2377-2379) */
   id->opened = 1;
@@ -165,6 +167,37 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
     int direct = outsize >= P3_API_DIRECT * fbytes;
     int64_t want = direct ? (int64_t)(outsize / fbytes) : P3_API_AHEAD;
     if (want > P3_API_CHUNK) want = P3_API_CHUNK;
+    if (direct && want >= 1024 && !id->host_hop) {
+      /* Large reads: nothing is parsed on the host.  A window of the buffered bytes goes to the device, the frame hop
+       * (Search_Header / Read_Header, pdmp3.c:1252-1340) runs there (p3_hop.cu) and tells how many frames it found and
+       * where the next window starts; kernels and the PCM download of that batch are queued behind it while this loop
+       * already uploads the next window. */
+      int nch0 = 2, sf0 = 0;
+      const size_t avail = in_filled(id);
+      const int fh = p3_find_header(id->in + id->istart, avail, &nch0, &sf0);  /* format of the first frame: sizes the PCM slots */
+      if (fh <= 0) { res = fh < 0 ? PDMP3_ERR : PDMP3_NEED_MORE; break; }      /* no header within a frame's length: pdmp3.c:1337 */
+      if (nch0 != (id->nch == 1 ? 1 : 2)) { id->nch = nch0; continue; }       /* re-plan with the right frame size */
+      if (ensure_ctx(id) != PDMP3_OK) { res = PDMP3_ERR; break; }
+      size_t win = (size_t)want * (id->bpf_est ? id->bpf_est + id->bpf_est / 32 + 1 : 1441) + 8192;
+      uint32_t look = 2 * 576;                                                 /* the 1152-byte rule counts from the end of what is buffered (pdmp3.c:2445) */
+      if (win >= avail || avail - win < 8192) win = avail; else look = 0;
+      p3_parse_opts po = {want, look, 0, 0, 1u, (uint32_t)id->iso};
+      p3_parse_state ps = id->ps; ps.pcm_index = 0;                           /* slots restart at 0 for every batch */
+      p3_parsed pb;
+      double t0 = trace ? now_ms() : 0;
+      int rc = p3_decode_raw_async(id->ctx, id->in + id->istart, win, &po, &ps, &pb, (int16_t *)outmemory);
+      if (trace) { t_decode += now_ms() - t0; nb++; }
+      if (rc != P3_OK) { fprintf(stderr, "pdmp3_b200: %s\n", p3_last_error()); res = PDMP3_ERR; break; }
+      if (pb.n_frames == 0) { res = pb.stop == 2 ? PDMP3_ERR : PDMP3_NEED_MORE; break; }
+      inflight = 1;
+      id->ps = ps; id->ps.pcm_index = 0; id->sfreq = ps.sfreq;
+      id->bpf_est = (size_t)((pb.consumed + (uint64_t)pb.n_frames - 1) / (uint64_t)pb.n_frames);
+      if (!id->new_header) id->new_header = 1;                                 /* pdmp3.c:1318 */
+      id->istart += pb.consumed; id->processed += pb.consumed;
+      { size_t n = (size_t)pb.n_frames * fbytes; outmemory += n; outsize -= n; *done += n; }
+      res = PDMP3_OK;
+      continue;
+    }
     p3_parse_opts po = {want, 2 * 576, want >= 8192 ? 4 : 1, 0, id->host_sideinfo ? 0u : 1u, (uint32_t)id->iso};   /* side info: parsed on the device */
     p3_parse_state ps = id->ps;
     p3_parsed pb;

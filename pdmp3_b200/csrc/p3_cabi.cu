@@ -73,6 +73,7 @@ struct p3_ctx {
   /* device-side frame hop (p3_hop.cu): scratch, and the reservoir carry kept on the device for batches staged from raw bytes */
   p3_hop_work hop;
   uint8_t *d_tail_cur, *d_tail_nxt; int tail_on_device, have_next_tail_dev;
+  float hop_ms;
 };
 
 extern "C" void *p3_host_alloc(size_t bytes) { void *p = NULL; return cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess ? p : NULL; }
@@ -618,11 +619,14 @@ static int hop_staged(p3_ctx *c, p3_slot *sl, uint64_t raw_bytes, const p3_parse
   int rc;
   if (c->tail_on_device) CK(cudaMemcpyAsync(sl->d_tail, c->d_tail_cur, 512, cudaMemcpyDeviceToDevice, st));
   else { memcpy(sl->h_tail, c->h_tail, 512); CK(cudaMemcpyAsync(sl->d_tail, sl->h_tail, 512, cudaMemcpyHostToDevice, st)); }
+  CK(cudaEventRecord(c->ev[6], st));
   if ((rc = p3_hop_count(&c->hop, st, sl->raw_dev, raw_bytes, o, st_in, 0))) return fail(rc, "device frame hop failed");
   const p3_hop_result *r = c->hop.h_res;
   c->n_frames = r->n_frames; c->n_pcm_frames = r->n_pcm_frames; c->raw_bytes = raw_bytes; c->nch = (uint32_t)r->nch;
   if ((rc = ensure(&sl->frames, (size_t)(r->n_frames ? r->n_frames : 1) * sizeof(p3_frame)))) return rc;
   if ((rc = p3_hop_emit(&c->hop, st, sl->raw_dev, raw_bytes, o, st_in, (p3_frame *)sl->frames.p, sl->d_tail, c->d_tail_nxt))) return fail(rc, "device frame hop failed");
+  CK(cudaEventRecord(c->ev[7], st)); CK(cudaEventSynchronize(c->ev[7]));
+  CK(cudaEventElapsedTime(&c->hop_ms, c->ev[6], c->ev[7]));            /* device time of the hop: kernels + the two result read-backs */
   c->have_next_tail_dev = 1; c->have_next_tail = 0;
   sl->hop_only = 1; sl->iso = o->iso != 0;
   return P3_OK;
@@ -659,7 +663,43 @@ extern "C" int p3_batch_upload_raw(p3_ctx *c, const uint8_t *raw, uint64_t raw_b
 }
 
 extern "C" int p3_batch_channels(p3_ctx *c) { return c ? (int)c->nch : 0; }
+extern "C" float p3_hop_ms(p3_ctx *c) { return c ? c->hop_ms : 0.0f; }
 extern "C" int p3_hop_rounds(p3_ctx *c) { return c && c->hop.h_res ? c->hop.h_res->changed : 0; }
+
+/* Asynchronous, double-buffered decode from raw bytes (behind pdmp3_read() for large reads): upload of the byte window and the
+ * device hop on the H2D stream -- the call returns once the hop result is known (frames found, bytes consumed), which is
+ * while the PREVIOUS batch is still in its kernels / download --, then kernels and the PCM download of exactly the frames
+ * found are enqueued.  raw and pcm must stay valid until p3_batch_sync().  *st is advanced. */
+extern "C" int p3_decode_raw_async(p3_ctx *c, const uint8_t *raw, uint64_t raw_bytes, const p3_parse_opts *o, p3_parse_state *st, p3_parsed *info, int16_t *pcm)
+{
+  if (!c || !raw || !info) return fail(P3_EINVAL, "null argument");
+  CK(cudaSetDevice(c->device));
+  c->taps = 0;
+  c->cur_slot ^= 1;
+  p3_slot *sl = &c->slot[c->cur_slot];
+  if (g_trace < 0) g_trace = getenv("P3_TRACE") != NULL;
+  double t0 = g_trace ? now_ms() : 0;
+  slot_release(sl);                                        /* wait for the batch that used this slot two calls ago */
+  double t1 = g_trace ? now_ms() : 0;
+  int rc = stage_raw(c, sl, raw, raw_bytes, 0, o, st, info, c->s_h2d);
+  if (rc) return rc;
+  double t2 = g_trace ? now_ms() : 0;
+  if (c->n_frames > 0) {
+    CK(cudaEventRecord(sl->h2d_done, c->s_h2d));
+    CK(cudaStreamWaitEvent(c->stream, sl->h2d_done, 0));
+    if ((rc = run_all(c, sl))) return rc;
+    CK(cudaEventRecord(sl->compute_done, c->stream));
+    CK(cudaStreamWaitEvent(c->s_d2h, sl->compute_done, 0));
+    if (pcm && c->n_pcm_frames)
+      CK(cudaMemcpyAsync(pcm, sl->pcm.p, (size_t)c->n_pcm_frames * 1152 * c->nch * sizeof(int16_t), cudaMemcpyDeviceToHost, c->s_d2h));
+    CK(cudaEventRecord(sl->d2h_done, c->s_d2h));
+    sl->busy = 1;
+    commit_tail(c);
+    if (st) *st = c->hop.h_res->st;
+  } else { c->have_next_tail_dev = 0; }
+  if (g_trace) { g_tr_wait += t1 - t0; g_tr_stage += t2 - t1; g_tr_launch += now_ms() - t2; }
+  return P3_OK;
+}
 
 /* Decode raw[0, raw_bytes) in one call, hop included: the device-side counterpart of p3_parse() + p3_decode_batch().
  * *st is updated to the parser state after the decoded frames; info->consumed tells where the next call continues. */
