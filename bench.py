@@ -240,6 +240,7 @@ def main():
     ctx = pdmp3_b200.Context(local, pdmp3_b200.MODE_FAST if a.mode == "fast" else pdmp3_b200.MODE_EXACT)
     # nothing is parsed on the host: the bytes go to the device and the frame hop runs there (p3_hop.cu), as in pdmp3_read()
     info = ctx.upload_raw(stream, lookahead=0, warmup=warm); ctx.sync()
+    info = ctx.upload_raw(stream, lookahead=0, warmup=warm); ctx.sync()         # (the second staging finds every buffer allocated: its hop time is the steady-state one)
     n_frames = info["n_pcm_frames"]; hop_ms = info["hop_ms"]
     class _P: pass
     parsed = _P(); parsed.n_frames = info["n_frames"]; parsed.n_pcm_frames = n_frames
