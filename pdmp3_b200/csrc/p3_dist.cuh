@@ -440,6 +440,7 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
     memset(res, 0, sizeof *res);
     res->n_frames_total = n_total; res->n_frames_mine = me.last - me.first; res->warmup_mine = me.warmup; res->nch = nch;
     res->stop = (int32_t)hd->stop; res->consumed = hd->consumed; res->chunks = nchunk; res->launches = c->launches;
+    res->pad_ = (d->use_ipc ? 1 : 0) | (pull ? 2 : 0);
     res->bytes_in = R == 0 ? 0 : me.byte_hi - me.byte_lo; res->bytes_out = R == 0 ? 0 : (uint64_t)(me.last - me.first) * fbytes;
     CK(cudaEventElapsedTime(&res->ms, d->ev_t0, d->ev_t1));
     CK(cudaEventElapsedTime(&res->ms_scatter, d->ev_t0, d->ev_s1));
