@@ -306,7 +306,7 @@ def main():
         floor_ms = float(tfl.item())
         tm = torch.tensor([res["ms_staged"], res["ms_decoded"], res["ms"]], dtype=torch.float64, device="cuda")
         tms = [torch.zeros_like(tm) for _ in range(world)]; dist.all_gather(tms, tm)
-        sharded = {"ms_per_step": ms_sh, "gather_transport": dd.gather_transport(), "scatter_transport": "cuda-ipc copy-engine pull, rank order" if (res["pad_"] & 2) else "nccl send/recv, rank order", "per_rank_ms_staged_decoded_total": [[round(float(x), 3) for x in t.tolist()] for t in tms], "frames_total": total, "chunk_frames": a.chunk, "scatter_ms": float(tsc.item()),
+        sharded = {"ms_per_step": ms_sh, "gather_transport": dd.gather_transport(), "scatter_transport": "cuda-ipc copy-engine push out of rank 0, rank order" if (res["pad_"] & 2) else "nccl send/recv, rank order", "per_rank_ms_staged_decoded_total": [[round(float(x), 3) for x in t.tolist()] for t in tms], "frames_total": total, "chunk_frames": a.chunk, "scatter_ms": float(tsc.item()),
                    "bytes_to_rank0": nf * 4608 * (world - 1), "bytes_from_rank0": (big_bytes * (world - 1)) // world if rank == 0 else None,
                    "ingest_floor_ms": floor_ms, "ingest_floor_GBps": nf * 4608 * (world - 1) / floor_ms / 1e6, "time_over_floor": ms_sh / floor_ms,
                    "tiles_identical_on_rank0": tiles_ok, "launches_per_step_rank0": res["launches"],

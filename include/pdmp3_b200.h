@@ -197,7 +197,7 @@ int  p3_kernel_launch_count(p3_ctx *c);               /* kernels launched by the
 typedef struct p3_dist p3_dist;
 typedef struct {
   int64_t  n_frames_total, n_frames_mine, warmup_mine, chunks;
-  int32_t  nch, stop, launches, pad_;        /* pad_: transport flags -- 1: PCM by copy-engine peer copies (else ncclSend/ncclRecv), 2: byte ranges pulled by copy engine (else ncclSend/ncclRecv) */
+  int32_t  nch, stop, launches, pad_;        /* pad_: transport flags -- 1: PCM by copy-engine peer copies (else ncclSend/ncclRecv), 2: byte ranges pushed by rank 0's copy engine (else ncclSend/ncclRecv) */
   uint64_t consumed, bytes_in, bytes_out;    /* bytes_in: compressed bytes this rank received; bytes_out: PCM bytes it sent */
   float    ms, ms_scatter;                   /* device time (CUDA events) of this rank's part of the call / until its scatter traffic was done */
   float    ms_staged, ms_decoded;            /* ... until its bytes were staged and hopped / until its own frames were decoded */

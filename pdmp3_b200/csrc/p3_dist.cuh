@@ -75,20 +75,9 @@ typedef struct {                          /* broadcast in front of the plans */
 
 typedef struct {                          /* rank 0's buffers, for the peers to map (travels with the plan) */
   cudaIpcMemHandle_t h; uint64_t bytes; uint64_t serial;          /* the output buffer (PCM of the whole stream) */
-  cudaIpcMemHandle_t h_raw; uint64_t raw_off; uint64_t raw_serial; /* the allocation holding the byte stream, and where the stream starts in it; serial 0: not mappable, the bytes come by ncclSend */
 } p3_ipc_msg;
 
-/* base of the allocation a device pointer lies in (driver API, taken from the libcuda the runtime has already loaded) */
-static int alloc_base(const void *p, void **base, size_t *size)
-{
-  typedef int (*fn_t)(unsigned long long *, size_t *, unsigned long long);
-  static fn_t fn; static int tried;
-  if (!tried) { tried = 1; void *h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_NOLOAD); if (!h) h = dlopen("libcuda.so.1", RTLD_NOW); if (h) fn = (fn_t)dlsym(h, "cuMemGetAddressRange_v2"); }
-  unsigned long long b = 0; size_t n = 0;
-  if (!fn || fn(&b, &n, (unsigned long long)(uintptr_t)p) != 0) return -1;
-  *base = (void *)(uintptr_t)b; *size = n;
-  return 0;
-}
+typedef struct { cudaIpcMemHandle_t h; uint64_t serial; uint64_t bytes; } p3_ipc_peer;   /* a peer's staging buffer for its byte range, for rank 0 to map */
 
 #define P3_DIST_MAXW 16
 
@@ -104,8 +93,10 @@ struct p3_dist {
   p3_ipc_msg *d_ipc, *h_ipc;             /* message buffer (device for the broadcast, page-locked host copy) */
   void *exp_ptr; uint64_t exp_serial; cudaIpcMemHandle_t exp_handle;   /* rank 0: the buffer the current handle stands for */
   void *map_ptr; uint64_t map_serial;    /* peers: the mapping currently open */
-  void *exp_raw; uint64_t exp_raw_serial; cudaIpcMemHandle_t exp_raw_handle;   /* same for the allocation that holds the byte stream */
-  void *map_raw; uint64_t map_raw_serial;
+  /* copy-engine scatter: rank 0 maps every peer's staging buffer and pushes the byte ranges into them */
+  p3_ipc_peer *d_peer, *h_peer;          /* [world] message buffers */
+  void *peer_map[P3_DIST_MAXW]; uint64_t peer_serial[P3_DIST_MAXW];
+  void *exp_in; uint64_t exp_in_serial; cudaIpcMemHandle_t exp_in_handle;    /* peers: the staging buffer the current handle stands for */
   int *d_tok;                            /* completion tokens */
 };
 
@@ -153,7 +144,8 @@ extern "C" void p3_dist_destroy(p3_dist *d)
   free(d->ev_chunk);
   cudaFree(d->d_plan); if (d->h_plan) cudaFreeHost(d->h_plan);
   if (d->map_ptr) cudaIpcCloseMemHandle(d->map_ptr);
-  if (d->map_raw) cudaIpcCloseMemHandle(d->map_raw);
+  for (int r = 0; r < P3_DIST_MAXW; r++) if (d->peer_map[r]) cudaIpcCloseMemHandle(d->peer_map[r]);
+  cudaFree(d->d_peer); if (d->h_peer) cudaFreeHost(d->h_peer);
   cudaFree(d->d_ipc); if (d->h_ipc) cudaFreeHost(d->h_ipc); cudaFree(d->d_tok);
   free(d);
 }
@@ -179,6 +171,7 @@ extern "C" int p3_dist_init(p3_ctx *c, const uint8_t *ids, int rank, int world, 
   DK(cudaEventCreate(&d->ev_t0)); DK(cudaEventCreate(&d->ev_t1)); DK(cudaEventCreate(&d->ev_s1)); DK(cudaEventCreate(&d->ev_h)); DK(cudaEventCreate(&d->ev_d));
   const size_t pb = sizeof(p3_shard_head) + (size_t)world * sizeof(p3_shard_plan) + sizeof(p3_ipc_msg);
   DK(cudaMalloc(&d->d_plan, pb)); DK(cudaHostAlloc((void **)&d->h_plan, pb, cudaHostAllocPortable));
+  DK(cudaMalloc(&d->d_peer, (size_t)world * sizeof(p3_ipc_peer))); DK(cudaHostAlloc((void **)&d->h_peer, (size_t)world * sizeof(p3_ipc_peer), cudaHostAllocPortable));
   DK(cudaMalloc(&d->d_ipc, sizeof(p3_ipc_msg))); DK(cudaHostAlloc((void **)&d->h_ipc, sizeof(p3_ipc_msg), cudaHostAllocPortable));
   DK(cudaMalloc(&d->d_tok, (size_t)(world + 1) * sizeof(int))); DK(cudaMemset(d->d_tok, 0, (size_t)(world + 1) * sizeof(int)));
 #undef DK
@@ -305,15 +298,6 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
     if (d->use_ipc && W > 1) {
       if (d->exp_ptr != sl->pcm.p) { CK(cudaIpcGetMemHandle(&d->exp_handle, sl->pcm.p)); d->exp_ptr = sl->pcm.p; d->exp_serial++; }
       ipc->h = d->exp_handle; ipc->bytes = sl->pcm.cap; ipc->serial = d->exp_serial;
-      /* the byte stream: the peers pull their ranges with the copy engine if the allocation can be exported */
-      void *base = NULL; size_t asz = 0;
-      if (alloc_base(sl->raw_dev, &base, &asz) == 0) {
-        if (d->exp_raw != base) {
-          if (cudaIpcGetMemHandle(&d->exp_raw_handle, base) == cudaSuccess) { d->exp_raw = base; d->exp_raw_serial = ++d->exp_serial; }
-          else { cudaGetLastError(); d->exp_raw = NULL; }
-        }
-        if (d->exp_raw == base) { ipc->h_raw = d->exp_raw_handle; ipc->raw_off = (uint64_t)(sl->raw_dev - (const uint8_t *)base); ipc->raw_serial = d->exp_raw_serial; }
-      }
     }
     CK(cudaMemcpyAsync(d->d_plan + pb - sizeof(p3_ipc_msg), ipc, sizeof *ipc, cudaMemcpyHostToDevice, c->stream));
     CK(cudaEventRecord(d->ev_a, c->stream));
@@ -328,23 +312,36 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
       CK(cudaIpcOpenMemHandle(&d->map_ptr, ipc->h, cudaIpcMemLazyEnablePeerAccess));
       d->map_serial = ipc->serial;
     }
-    if (d->use_ipc && ipc->raw_serial && (!d->map_raw || d->map_raw_serial != ipc->raw_serial)) {
-      if (d->map_raw) { cudaIpcCloseMemHandle(d->map_raw); d->map_raw = NULL; }
-      CK(cudaIpcOpenMemHandle(&d->map_raw, ipc->h_raw, cudaIpcMemLazyEnablePeerAccess));
-      d->map_raw_serial = ipc->raw_serial;
-    }
   }
-  const int pull = d->use_ipc && ipc->raw_serial != 0;      /* scatter by copy-engine pulls (every rank knows: the flag travelled with the plan) */
+  const int push = d->use_ipc && W > 1;                     /* scatter by copy-engine pushes out of rank 0 (agreed at init) */
   const p3_shard_plan me = pl[R];
   const int64_t n_total = hd->n_frames; const int nch = hd->nch;
   o.iso = (uint32_t)hd->iso;
   const size_t fbytes = (size_t)1152 * sizeof(int16_t) * (size_t)nch;
 
   /* ---- scatter: the byte ranges leave rank 0 in rank order (rank 1 can start decoding while rank 7 still waits).
-   *      Copy-engine variant: rank r pulls its range out of rank 0's buffer, and passes a token to rank r+1 when it has it;
-   *      NCCL variant: rank 0 sends the ranges one after the other. ---- */
+   *      Copy-engine variant: every peer exports its staging buffer, rank 0 maps them and pushes each range with a peer copy
+   *      (writes travel on rank 0's egress, which nothing else uses; reads pulled by the peers would have to get their requests
+   *      through rank 0's ingress, where the PCM arrives: measured, the last ranks got their bytes after 24-40 ms), followed
+   *      by a token; NCCL variant: rank 0 sends the ranges one after the other. ---- */
   if (R == 0) {
-    if (!pull)
+    if (push) {
+      NK(g_nccl.GroupStart());
+      for (int r = 1; r < W; r++) NK(g_nccl.Recv(d->d_peer + r, sizeof(p3_ipc_peer), ncclUint8, r, d->comm_s, d->s_scatter));
+      NK(g_nccl.GroupEnd());
+      CK(cudaMemcpyAsync(d->h_peer, d->d_peer, (size_t)W * sizeof(p3_ipc_peer), cudaMemcpyDeviceToHost, d->s_scatter));
+      CK(cudaStreamSynchronize(d->s_scatter));
+      for (int r = 1; r < W; r++) {
+        if (!d->peer_map[r] || d->peer_serial[r] != d->h_peer[r].serial) {
+          if (d->peer_map[r]) { cudaIpcCloseMemHandle(d->peer_map[r]); d->peer_map[r] = NULL; }
+          CK(cudaIpcOpenMemHandle(&d->peer_map[r], d->h_peer[r].h, cudaIpcMemLazyEnablePeerAccess));
+          d->peer_serial[r] = d->h_peer[r].serial;
+        }
+        const uint64_t len = pl[r].byte_hi - pl[r].byte_lo;
+        if (len) CK(cudaMemcpyAsync(d->peer_map[r], sl->raw_dev + pl[r].byte_lo, len, cudaMemcpyDeviceToDevice, d->s_scatter));
+        NK(g_nccl.Send(d->d_tok, sizeof(int), ncclUint8, r, d->comm_s, d->s_scatter));
+      }
+    } else
       for (int r = 1; r < W; r++)
         if (pl[r].byte_hi > pl[r].byte_lo) NK(g_nccl.Send(sl->raw_dev + pl[r].byte_lo, pl[r].byte_hi - pl[r].byte_lo, ncclUint8, r, d->comm_s, d->s_scatter));
     CK(cudaEventRecord(d->ev_s1, d->s_scatter));
@@ -352,10 +349,12 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
     const uint64_t len = me.byte_hi - me.byte_lo;
     if ((rc = ensure(&sl->raw, len + 64))) return rc;
     sl->raw_dev = (const uint8_t *)sl->raw.p;
-    if (pull) {
-      if (R > 1) NK(g_nccl.Recv(d->d_tok, sizeof(int), ncclUint8, R - 1, d->comm_s, d->s_scatter));
-      if (len) CK(cudaMemcpyAsync(sl->raw.p, (const uint8_t *)d->map_raw + ipc->raw_off + me.byte_lo, len, cudaMemcpyDeviceToDevice, d->s_scatter));
-      if (R + 1 < W) NK(g_nccl.Send(d->d_tok, sizeof(int), ncclUint8, R + 1, d->comm_s, d->s_scatter));
+    if (push) {
+      if (d->exp_in != sl->raw.p) { CK(cudaIpcGetMemHandle(&d->exp_in_handle, sl->raw.p)); d->exp_in = sl->raw.p; d->exp_in_serial++; }
+      d->h_peer[R].h = d->exp_in_handle; d->h_peer[R].serial = d->exp_in_serial; d->h_peer[R].bytes = sl->raw.cap;
+      CK(cudaMemcpyAsync(d->d_peer + R, d->h_peer + R, sizeof(p3_ipc_peer), cudaMemcpyHostToDevice, d->s_scatter));
+      NK(g_nccl.Send(d->d_peer + R, sizeof(p3_ipc_peer), ncclUint8, 0, d->comm_s, d->s_scatter));
+      NK(g_nccl.Recv(d->d_tok, sizeof(int), ncclUint8, 0, d->comm_s, d->s_scatter));      /* rank 0's push has landed */
     } else if (len) NK(g_nccl.Recv(sl->raw.p, len, ncclUint8, 0, d->comm_s, d->s_scatter));
     CK(cudaMemsetAsync((uint8_t *)sl->raw.p + len, 0, 64, d->s_scatter));
     CK(cudaEventRecord(d->ev_s1, d->s_scatter));
@@ -440,7 +439,7 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
     memset(res, 0, sizeof *res);
     res->n_frames_total = n_total; res->n_frames_mine = me.last - me.first; res->warmup_mine = me.warmup; res->nch = nch;
     res->stop = (int32_t)hd->stop; res->consumed = hd->consumed; res->chunks = nchunk; res->launches = c->launches;
-    res->pad_ = (d->use_ipc ? 1 : 0) | (pull ? 2 : 0);
+    res->pad_ = (d->use_ipc ? 1 : 0) | (push ? 2 : 0);
     res->bytes_in = R == 0 ? 0 : me.byte_hi - me.byte_lo; res->bytes_out = R == 0 ? 0 : (uint64_t)(me.last - me.first) * fbytes;
     CK(cudaEventElapsedTime(&res->ms, d->ev_t0, d->ev_t1));
     CK(cudaEventElapsedTime(&res->ms_scatter, d->ev_t0, d->ev_s1));

@@ -174,88 +174,115 @@ __device__ __forceinline__ uint64_t hop_frame_pos(const hop_seg &s, const uint16
 
 #define HOP_A_INF 0x3fffffff
 
-/* ---- per-segment aggregates over the true frames ---- */
+/* ---- per-segment aggregates over the true frames, their exclusive prefix inside the block of 128 segments, the block's total ---- */
 extern "C" __global__ void __launch_bounds__(128)
-k_hop_agg(const uint8_t *__restrict__ raw, int64_t nseg, hop_seg *__restrict__ seg, const uint16_t *__restrict__ lists)
+k_hop_agg(const uint8_t *__restrict__ raw, int64_t nseg, hop_seg *__restrict__ seg, const uint16_t *__restrict__ lists, hop_part *__restrict__ part)
 {
+  __shared__ int32_t s_cnt[128], s_ms[128], s_a[128], s_b[128];
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nseg) return;
-  hop_seg s = seg[k];
-  const uint64_t b = (uint64_t)k * HOP_SEG;
-  const uint16_t *L = lists + (size_t)k * HOP_LCAP;
-  const uint32_t cnt = (uint32_t)s.nP + (s.nL - s.j0);
-  uint32_t sum = 0, mx = 0, fmt0 = 0, chg = 0xffff; int64_t fa = HOP_A_INF, fb = 0;
-  for (uint32_t i = 0; i < cnt; i++) {
-    const uint8_t *h = raw + hop_frame_pos(s, L, b, i);
-    const hop_hdr hh = hop_parse_header(h);
-    const uint32_t ms = hh.fsize - hh.hdr - hh.silen, mb = ((uint32_t)h[hh.hdr] << 1) | (h[hh.hdr + 1] >> 7);
-    const uint32_t fmt = hh.nch | (uint32_t)hh.sf << 2;
-    if (i == 0) fmt0 = fmt; else if (fmt != fmt0 && chg == 0xffff) chg = i;
-    sum += ms; mx = max(mx, ms);
-    fa = min(fa, (int64_t)mb - fb); fb += ms;                         /* then top' = min(top, mb) + ms */
+  uint32_t cnt = 0, sum = 0, mx = 0, fmt0 = 0, chg = 0xffff; int64_t fa = HOP_A_INF, fb = 0;
+  if (k < nseg) {
+    const hop_seg s = seg[k];
+    const uint64_t b = (uint64_t)k * HOP_SEG;
+    const uint16_t *L = lists + (size_t)k * HOP_LCAP;
+    cnt = (uint32_t)s.nP + (s.nL - s.j0);
+    for (uint32_t i = 0; i < cnt; i++) {
+      const uint8_t *h = raw + hop_frame_pos(s, L, b, i);
+      const hop_hdr hh = hop_parse_header(h);
+      const uint32_t ms = hh.fsize - hh.hdr - hh.silen, mb = ((uint32_t)h[hh.hdr] << 1) | (h[hh.hdr + 1] >> 7);
+      const uint32_t fmt = hh.nch | (uint32_t)hh.sf << 2;
+      if (i == 0) fmt0 = fmt; else if (fmt != fmt0 && chg == 0xffff) chg = i;
+      sum += ms; mx = max(mx, ms);
+      fa = min(fa, (int64_t)mb - fb); fb += ms;                       /* then top' = min(top, mb) + ms */
+    }
   }
-  seg[k].cnt = (uint16_t)cnt; seg[k].sum_ms = sum; seg[k].fa = (int32_t)fa; seg[k].fb = (uint32_t)fb;
-  seg[k].chg = (uint16_t)chg; seg[k].max_ms = (uint16_t)mx; seg[k].fmt = (uint8_t)fmt0;
+  s_cnt[threadIdx.x] = (int32_t)cnt; s_ms[threadIdx.x] = (int32_t)sum; s_a[threadIdx.x] = (int32_t)fa; s_b[threadIdx.x] = (int32_t)fb;
+  __syncthreads();
+  if (threadIdx.x == 0) {                                            /* exclusive scan over the block's 128 segments (serial: 128 steps) */
+    int64_t rc = 0, rm = 0, ra = HOP_A_INF, rb = 0;
+    for (int i = 0; i < 128; i++) {
+      const int64_t c = s_cnt[i], m = s_ms[i], aa = s_a[i], bb = s_b[i];
+      s_cnt[i] = (int32_t)rc; s_ms[i] = (int32_t)rm; s_a[i] = (int32_t)ra; s_b[i] = (int32_t)rb;
+      rc += c; rm += m; ra = min(ra, aa - rb); rb += bb;
+    }
+    hop_part p; p.cnt = rc; p.ms = rm; p.a = ra; p.b = rb;
+    part[blockIdx.x] = p;
+  }
+  __syncthreads();
+  if (k < nseg) {
+    hop_seg &o = seg[k];
+    o.cnt = (uint16_t)cnt; o.sum_ms = sum; o.fa = (int32_t)fa; o.fb = (uint32_t)fb;
+    o.chg = (uint16_t)chg; o.max_ms = (uint16_t)mx; o.fmt = (uint8_t)fmt0;
+    o.base_idx = (uint64_t)s_cnt[threadIdx.x]; o.base_pos = (uint64_t)s_ms[threadIdx.x]; o.la = s_a[threadIdx.x]; o.lb = (uint32_t)s_b[threadIdx.x];
+  }
 }
 
-/* ---- exclusive scan over the segments + the truncation rules; ONE CTA of 1024 threads ---- */
+/* ---- exclusive scan over the blocks' totals; ONE CTA of 1024 threads (128 x fewer items than segments) ---- */
 extern "C" __global__ void __launch_bounds__(1024)
-k_hop_scan(int64_t nseg, hop_seg *__restrict__ seg, const uint64_t *__restrict__ exits, p3_parse_state st0, int64_t max_frames, uint32_t warmup,
-           p3_hop_result *__restrict__ res)
+k_hop_scan(int64_t nblk, hop_part *__restrict__ part, p3_hop_result *__restrict__ res)
 {
   __shared__ int64_t s_cnt[1024], s_ms[1024], s_a[1024], s_b[1024];
-  __shared__ unsigned long long s_mismatch; __shared__ unsigned int s_maxms; __shared__ int s_stop; __shared__ unsigned long long s_term;
   const int t = threadIdx.x;
-  const int64_t per = (nseg + 1023) / 1024, lo = (int64_t)t * per, hi = min(lo + per, nseg);
-  if (t == 0) { s_mismatch = ~0ull; s_maxms = 0; s_stop = 0; s_term = 0; }
-  int64_t cnt = 0, ms = 0, a = HOP_A_INF, b = 0; uint32_t mx = 0;
-  for (int64_t k = lo; k < hi; k++) {
-    const hop_seg &s = seg[k];
-    cnt += s.cnt; ms += s.sum_ms; mx = max(mx, (uint32_t)s.max_ms);
-    a = min(a, (int64_t)s.fa - b); b += s.fb;
-  }
+  const int64_t per = (nblk + 1023) / 1024, lo = (int64_t)t * per, hi = min(lo + per, nblk);
+  int64_t cnt = 0, ms = 0, a = HOP_A_INF, b = 0;
+  for (int64_t k = lo; k < hi; k++) { const hop_part p = part[k]; cnt += p.cnt; ms += p.ms; a = min(a, p.a - b); b += p.b; }
   s_cnt[t] = cnt; s_ms[t] = ms; s_a[t] = a; s_b[t] = b;
   __syncthreads();
-  if (mx) atomicMax(&s_maxms, mx);
-  if (t == 0) {                                                      /* exclusive scan of the 1024 partials (serial: 1024 steps) */
+  if (t == 0) {
     int64_t rc = 0, rm = 0, ra = HOP_A_INF, rb = 0;
     for (int i = 0; i < 1024; i++) {
       const int64_t c = s_cnt[i], m = s_ms[i], aa = s_a[i], bb = s_b[i];
       s_cnt[i] = rc; s_ms[i] = rm; s_a[i] = ra; s_b[i] = rb;
       rc += c; rm += m; ra = min(ra, aa - rb); rb += bb;
     }
+    res->n_total = rc; res->total_ms = (uint64_t)rm; res->tot_a = ra; res->tot_b = rb;
+    res->mismatch = ~0ull; res->term_stop = 0; res->term_pos = 0; res->max_main = 0;
   }
   __syncthreads();
-  const uint32_t fmt0 = seg[0].cnt ? seg[0].fmt : 0u;
   cnt = s_cnt[t]; ms = s_ms[t]; a = s_a[t]; b = s_b[t];
   for (int64_t k = lo; k < hi; k++) {
-    hop_seg &s = seg[k];
-    s.base_idx = (uint64_t)cnt; s.base_pos = st0.main_pos + (uint64_t)ms;
-    s.top_in = (uint32_t)(min((int64_t)st0.top, a) + b);
-    if (s.cnt) {
-      if (s.fmt != fmt0) atomicMin(&s_mismatch, (unsigned long long)cnt);
-      else if (s.chg != 0xffff) atomicMin(&s_mismatch, (unsigned long long)(cnt + s.chg));
-    }
-    if (s.entry != HOP_TERM && exits[k] == HOP_TERM) { s_stop = s.stop; s_term = s.term_pos; }    /* the one segment in which the chain ends */
-    cnt += s.cnt; ms += s.sum_ms; a = min(a, (int64_t)s.fa - b); b += s.fb;
+    const hop_part p = part[k];
+    hop_part e; e.cnt = cnt; e.ms = ms; e.a = a; e.b = b;
+    part[k] = e;
+    cnt += p.cnt; ms += p.ms; a = min(a, p.a - b); b += p.b;
   }
-  __syncthreads();
-  if (t == 1023 || (hi == nseg && lo < hi)) { s_cnt[0] = cnt; s_ms[0] = ms; s_a[0] = a; s_b[0] = b; }   /* totals: the thread holding the last segment */
-  __syncthreads();
-  if (t == 0) {
-    const int64_t n_total = s_cnt[0];
-    const int64_t lim = max_frames > 0 ? max_frames : INT64_MAX;
-    const int64_t mis = s_mismatch == ~0ull ? INT64_MAX : (int64_t)s_mismatch;
-    res->n_total = n_total;
-    res->nch = fmt0 ? (int)(fmt0 & 3) : 2; res->sfreq = (int)(fmt0 >> 2);
-    res->max_main = s_maxms; res->maxg = 0;
-    if (mis < n_total && mis < lim) { res->n_frames = mis; res->stop = 3; res->consumed = 0; }          /* consumed: k_hop_write (header of frame n_frames) */
-    else if (n_total >= lim) { res->n_frames = lim; res->stop = 1; res->consumed = 0; }                  /* consumed: k_hop_write (end of frame n_frames-1) */
-    else { res->n_frames = n_total; res->stop = s_stop == 3 ? 2 : 0; res->consumed = s_term; }
-    res->n_pcm_frames = res->n_frames > (int64_t)warmup ? res->n_frames - warmup : 0;
-    res->total_ms = (uint64_t)s_ms[0];                               /* (truncated: k_hop_write overwrites) */
-    res->st = st0;                                                   /* (n_frames > 0: k_hop_write overwrites) */
+}
+
+/* ---- per segment: the global prefix (block prefix, then the prefix inside the block), first format change, end of the chain ---- */
+extern "C" __global__ void __launch_bounds__(128)
+k_hop_apply(int64_t nseg, hop_seg *__restrict__ seg, const hop_part *__restrict__ part, const uint64_t *__restrict__ exits, p3_parse_state st0, p3_hop_result *res)
+{
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nseg) return;
+  hop_seg &s = seg[k];
+  const hop_part p = part[blockIdx.x];
+  const int64_t idx = p.cnt + (int64_t)s.base_idx, ms = p.ms + (int64_t)s.base_pos;
+  const int64_t a = min(p.a, (int64_t)s.la - p.b), b = p.b + (int64_t)s.lb;     /* block prefix, then the block's segments in front of this one */
+  s.base_idx = (uint64_t)idx; s.base_pos = st0.main_pos + (uint64_t)ms;
+  s.top_in = (uint32_t)(min((int64_t)st0.top, a) + b);
+  const uint32_t fmt0 = seg[0].cnt ? seg[0].fmt : 0u;
+  if (s.cnt) {
+    if (s.fmt != fmt0) atomicMin(&res->mismatch, (unsigned long long)idx);
+    else if (s.chg != 0xffff) atomicMin(&res->mismatch, (unsigned long long)(idx + s.chg));
+    atomicMax(&res->max_main, (uint32_t)s.max_ms);
   }
+  if (s.entry != HOP_TERM && exits[k] == HOP_TERM) { res->term_stop = s.stop; res->term_pos = s.term_pos; }    /* the one segment in which the chain ends */
+}
+
+/* ---- the truncation rules (p3_parse.c loop head: frame limit first, then the format change) ---- */
+extern "C" __global__ void k_hop_final(const hop_seg *__restrict__ seg, p3_parse_state st0, int64_t max_frames, uint32_t warmup, p3_hop_result *__restrict__ res)
+{
+  const uint32_t fmt0 = seg[0].cnt ? seg[0].fmt : 0u;
+  const int64_t n_total = res->n_total;
+  const int64_t lim = max_frames > 0 ? max_frames : INT64_MAX;
+  const int64_t mis = res->mismatch == ~0ull ? INT64_MAX : (int64_t)res->mismatch;
+  res->nch = fmt0 ? (int)(fmt0 & 3) : 2; res->sfreq = (int)(fmt0 >> 2);
+  res->maxg = 0;
+  if (mis < n_total && mis < lim) { res->n_frames = mis; res->stop = 3; res->consumed = 0; }          /* consumed: k_hop_write (header of frame n_frames) */
+  else if (n_total >= lim) { res->n_frames = lim; res->stop = 1; res->consumed = 0; }                  /* consumed: k_hop_write (end of frame n_frames-1) */
+  else { res->n_frames = n_total; res->stop = res->term_stop == 3 ? 2 : 0; res->consumed = res->term_pos; }
+  res->n_pcm_frames = res->n_frames > (int64_t)warmup ? res->n_frames - warmup : 0;
+  res->st = st0;                                                     /* (n_frames > 0: k_hop_write overwrites, total_ms too) */
 }
 
 /* ---- the records ---- */
@@ -339,20 +366,21 @@ int p3_hop_work_ensure(p3_hop_work *w, int64_t nseg)
 {
   if (!w->d_res) { HCK(cudaMalloc(&w->d_res, sizeof(p3_hop_result))); HCK(cudaHostAlloc((void **)&w->h_res, sizeof(p3_hop_result), cudaHostAllocPortable)); }
   if (nseg <= w->cap_seg) return P3_OK;
-  cudaFree(w->seg); cudaFree(w->lists); cudaFree(w->exit[0]); cudaFree(w->exit[1]);
-  w->seg = NULL; w->lists = NULL; w->exit[0] = w->exit[1] = NULL; w->cap_seg = 0;
+  cudaFree(w->seg); cudaFree(w->lists); cudaFree(w->exit[0]); cudaFree(w->exit[1]); cudaFree(w->part);
+  w->seg = NULL; w->lists = NULL; w->exit[0] = w->exit[1] = NULL; w->part = NULL; w->cap_seg = 0;
   const int64_t cap = nseg + nseg / 8 + 16;
   HCK(cudaMalloc(&w->seg, (size_t)cap * sizeof(hop_seg)));
   HCK(cudaMalloc(&w->lists, (size_t)cap * HOP_LCAP * sizeof(uint16_t)));
   HCK(cudaMalloc(&w->exit[0], (size_t)cap * sizeof(uint64_t)));
   HCK(cudaMalloc(&w->exit[1], (size_t)cap * sizeof(uint64_t)));
+  HCK(cudaMalloc(&w->part, (size_t)(cap / 128 + 2) * sizeof(hop_part)));
   w->cap_seg = cap;
   return P3_OK;
 }
 
 void p3_hop_work_free(p3_hop_work *w)
 {
-  cudaFree(w->seg); cudaFree(w->lists); cudaFree(w->exit[0]); cudaFree(w->exit[1]); cudaFree(w->d_res);
+  cudaFree(w->seg); cudaFree(w->lists); cudaFree(w->exit[0]); cudaFree(w->exit[1]); cudaFree(w->part); cudaFree(w->d_res);
   if (w->h_res) cudaFreeHost(w->h_res);
   memset(w, 0, sizeof *w);
 }
@@ -372,8 +400,10 @@ int p3_hop_count(p3_hop_work *w, cudaStream_t st, const uint8_t *d_raw, uint64_t
     const uint64_t *ep = w->exit[(round - 1) & 1]; uint64_t *ec = w->exit[round & 1];
     HCK(cudaMemsetAsync(&w->d_res->changed, 0, sizeof(int), st));
     k_hop_resolve<<<grid, 128, 0, st>>>(d_raw, n, o->lookahead, nseg, w->seg, w->lists, ep, ec, &w->d_res->changed);
-    k_hop_agg<<<grid, 128, 0, st>>>(d_raw, nseg, w->seg, w->lists);
-    k_hop_scan<<<1, 1024, 0, st>>>(nseg, w->seg, ec, *ps, maxf, o->warmup_frames, w->d_res);
+    k_hop_agg<<<grid, 128, 0, st>>>(d_raw, nseg, w->seg, w->lists, w->part);
+    k_hop_scan<<<1, 1024, 0, st>>>((int64_t)grid, w->part, w->d_res);
+    k_hop_apply<<<grid, 128, 0, st>>>(nseg, w->seg, w->part, ec, *ps, w->d_res);
+    k_hop_final<<<1, 1, 0, st>>>(w->seg, *ps, maxf, o->warmup_frames, w->d_res);
     HCK(cudaGetLastError());
     HCK(cudaMemcpyAsync(w->h_res, w->d_res, sizeof(p3_hop_result), cudaMemcpyDeviceToHost, st));
     HCK(cudaStreamSynchronize(st));

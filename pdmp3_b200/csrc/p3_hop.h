@@ -19,9 +19,12 @@ typedef struct {
   uint32_t sum_ms; int32_t fa; uint32_t fb;      /* main-data bytes; reservoir function top' = min(top, fa) + fb */
   uint16_t cnt, chg, max_ms;                     /* frames; index of the first frame whose format differs from the segment's first (0xffff: none); largest main_size */
   uint8_t  fmt, pad;                             /* nch | sfreq << 2 of the first frame */
-  /* exclusive prefix over the segments (k_hop_scan) */
+  /* exclusive prefix: first within the segment's block of 128 (k_hop_agg), then over the whole stream (k_hop_apply) */
   uint64_t base_idx, base_pos; uint32_t top_in, pad2;
+  int32_t  la; uint32_t lb;                      /* reservoir function of the block's segments in front of this one */
 } hop_seg;
+
+typedef struct { int64_t cnt, ms, a, b; } hop_part;   /* aggregate of a block of 128 segments; after k_hop_scan: the exclusive prefix over the blocks */
 
 typedef struct {
   int64_t  n_total;                    /* frames on the chain before truncation */
@@ -31,11 +34,15 @@ typedef struct {
   uint32_t max_main, maxg;             /* largest main_size; largest main-data span of a group of 32 frames (K1's window) */
   uint64_t total_ms;                   /* main-data bytes of the kept frames */
   p3_parse_state st;                   /* parser state after the kept frames */
+  /* scratch of the scan kernels */
+  unsigned long long mismatch;         /* index of the first frame whose format differs from frame 0's (~0: none) */
+  unsigned long long term_pos; int32_t term_stop, pad_;
+  int64_t tot_a, tot_b;
 } p3_hop_result;
 
 #ifdef __CUDACC__
 struct p3_hop_work {                   /* device scratch, grown on demand */
-  hop_seg *seg; uint16_t *lists; uint64_t *exit[2]; int64_t cap_seg;
+  hop_seg *seg; uint16_t *lists; uint64_t *exit[2]; int64_t cap_seg; hop_part *part;
   p3_hop_result *d_res; p3_hop_result *h_res;     /* h_res: page-locked */
 };
 int p3_hop_work_ensure(p3_hop_work *w, int64_t nseg);
