@@ -114,7 +114,11 @@ k_huffman(const uint32_t *__restrict__ ms /* compact main-data stream */, const 
   {
     const int64_t fk = F0 + (threadIdx.x >> 2);
     uint32_t bv = 0;
+#ifdef K1_SORT_P23L
+    if (fk < F1) bv = P3_GC_P23L(gcs[4 * fk + (threadIdx.x & 3)]) >> 3;     /* experiment: total bits of the part (pairs + quads) instead of the pair count */
+#else
     if (fk < F1) bv = P3_GC_BIGV(gcs[4 * fk + (threadIdx.x & 3)]);
+#endif
     s_key[threadIdx.x] = ((511u - bv) << 8) | threadIdx.x;          /* descending big_values, part index in the low byte */
     __syncthreads();
     for (uint32_t k = 2; k <= K1_THREADS; k <<= 1)

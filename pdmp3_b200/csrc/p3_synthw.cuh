@@ -29,6 +29,11 @@
 #ifndef SW_MINB
 #define SW_MINB   3                 /* CTAs per SM the register allocation aims at */
 #endif
+#ifndef SW_MS_EXACT
+#define SW_MS_EXACT 0               /* 1: MS stereo reproduces the reference's float-sum x DOUBLE-constant product bit for bit (4 packed instructions per line);
+                                       0: one packed multiply by the nearest float to 1/sqrt 2 -- at most 1 ulp away on a fifth of the values, far below the
+                                       1-LSB budget of FAST mode; saves 54 of the 842 packed instructions per granule (k_synth_fast and EXACT mode stay bit-exact) */
+#endif
 #define SW_PITCH  33                /* f2 elements per DCT row: 66 words -> conflict-free for row-per-lane and column-per-lane access */
 #define SW_LUT_BYTES (1728 + 1440 + 656)  /* CTA-shared: reorder_src u16[576] | line_sfbw_s u8[576] | t1h f32[40] | t2 f32[320] | line_sfb_l u8[576] | sfb_l u16[24] | sfb_s u16[16] */
 
@@ -101,6 +106,11 @@ __device__ __forceinline__ uint32_t sw_pcm2(f2 sum)
 #define SW_CA_LIST {-0.514496f, -0.471732f, -0.313377f, -0.181913f, -0.094574f, -0.040966f, -0.014199f, -0.003700f}
 __device__ __forceinline__ float sw_cs(int i) { constexpr float t[8] = SW_CS_LIST; return t[i]; }
 __device__ __forceinline__ float sw_ca(int i) { constexpr float t[8] = SW_CA_LIST; return t[i]; }
+/* x = v under a predicate */
+__device__ __forceinline__ void sw_mov_if(f2 &x, f2 v, bool on)
+{
+  asm("{\n .reg .pred p;\n setp.ne.s32 p, %2, 0;\n @p mov.b64 %0, %1;\n}" : "+l"(x.v) : "l"(v.v), "r"((int)on));
+}
 /* x = c - a under a predicate, as fma(a, -1, c) */
 __device__ __forceinline__ void sw_fnma_if(f2 &x, f2 a, f2 c, bool on)
 {
@@ -347,9 +357,14 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
           const float l = f2_x(in[m]), r = f2_y(in[m]);
           const f2 ad = f2_make(__fadd_rn(l, r), __fsub_rn(l, r));
           const f2 p = vmul(ad, Ch);
+#if SW_MS_EXACT
           const f2 ne = vfma(ad, -Ch, p);                          /* -(a*Ch - p), exact */
           const f2 nt = vfma(ad, -Cl, ne);                         /* -(a*Cl + e) */
           sw_fnma_if(in[m], nt, p, m < msrem);                     /* p + t, written as an fma so that nothing can be contracted into it; in place, lines below msn only */
+#else
+          (void)Cl;
+          sw_mov_if(in[m], p, m < msrem);                          /* lines below msn only */
+#endif
         }
       }
       if constexpr (!LEAN)
