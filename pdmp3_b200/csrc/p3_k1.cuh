@@ -211,3 +211,114 @@ __device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw /* the CTA's
   }
   return c1;
 }
+
+
+#ifdef K1_COOP_TRIAL
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * TRIAL (never built into the product; tools/build_variant.sh coop -DK1_COOP_TRIAL): north_star's "one warp per granule,
+ * __ballot/__shfl to walk the code words" -- the 32 lanes of a warp decode ONE part together: every lane decodes a pair
+ * speculatively at one of 32 consecutive bit offsets, the true chain is then followed through the lanes with shuffles
+ * (lane 0 -> lane 0 + its length -> ...), typically 3-4 symbols per window of 32 bits; the window then moves on.  Same LUTs, same
+ * bit reader, same outputs as the thread-per-part decoder above, so the GPU parity tests run on it unchanged.  Measured
+ * against it in profiles/ (DESIGN.md 4.6). */
+__device__ __forceinline__ uint32_t k1_decode_gc_coop(const uint32_t *sw, const uint16_t *lut, const p3_tables *__restrict__ T,
+                                                      const p3_gc *__restrict__ gcs, const p3_frame &fr, const p3_gc &g, int64_t f,
+                                                      uint32_t gr, uint32_t ch, int64_t win0, uint32_t *dstw /* the part's 288-word row */, uint8_t *scf)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t c1 = 0;
+  const bool ok = ch < fr.nch && !(fr.flags & (P3_FRAME_NODATA | P3_FRAME_BAD));
+  const uint32_t p23l = ok ? P3_GC_P23L(g) : 0u;
+  const uint32_t fstart = (uint32_t)((int64_t)fr.main_pos - fr.main_begin - win0) * 8u;
+  uint32_t pos = fstart + P3_GC_START(g);
+  const uint32_t part2_start = pos;
+  const bool is_short = P3_GC_WINSW(g) && P3_GC_BTYPE(g) == 2;
+  if (ok) {                                                  /* part 2: every lane runs the same (short, uniform) code; lane 0 stores */
+    uint8_t tmp[64];
+    #pragma unroll
+    for (int i = 0; i < 64; i++) tmp[i] = 0;
+    const bool has2 = p23l != 0 || !(fr.flags & P3_FRAME_ISO);
+    const uint32_t slen1 = has2 ? T->slen[P3_GC_SFCOMP(g)][0] : 0u, slen2 = has2 ? T->slen[P3_GC_SFCOMP(g)][1] : 0u;
+    if (is_short) {
+      uint32_t first = 0;
+      if (P3_GC_MIXED(g)) { for (int sfb = 0; sfb < 8; sfb++) tmp[sfb] = (uint8_t)p3_getbits(sw, pos, slen1); first = 3; }
+      for (uint32_t sfb = first; sfb < 12; sfb++)
+        for (int win = 0; win < 3; win++) tmp[P3_SCF_S_OFF + 3 * sfb + win] = (uint8_t)p3_getbits(sw, pos, sfb < 6 ? slen1 : slen2);
+    } else {
+      const uint32_t scfsi = gr == 1 ? (fr.scfsi >> (4 * ch)) & 15u : 0u;
+      const p3_gc g0 = gcs[4 * f + ch];
+      const bool g0_ok = !(P3_GC_WINSW(g0) && P3_GC_BTYPE(g0) == 2) && (P3_GC_P23L(g0) != 0 || !(fr.flags & P3_FRAME_ISO)) && has2;
+      const uint32_t a1 = T->slen[P3_GC_SFCOMP(g0)][0], a2 = T->slen[P3_GC_SFCOMP(g0)][1];
+      const uint32_t g0pos = fstart + P3_GC_START(g0);
+      for (int band = 0; band < 4; band++) {
+        const int lo = band == 0 ? 0 : band == 1 ? 6 : band == 2 ? 11 : 16, hi = band == 0 ? 6 : band == 1 ? 11 : band == 2 ? 16 : 21;
+        if ((scfsi >> band) & 1) {
+          uint32_t p = g0pos + (band == 0 ? 0u : band == 1 ? 6 * a1 : band == 2 ? 11 * a1 : 11 * a1 + 5 * a2), nb = band < 2 ? a1 : a2;
+          for (int sfb = lo; sfb < hi; sfb++) tmp[sfb] = g0_ok ? (uint8_t)p3_getbits(sw, p, nb) : 0;
+        } else
+          for (int sfb = lo; sfb < hi; sfb++) tmp[sfb] = (uint8_t)p3_getbits(sw, pos, band < 2 ? slen1 : slen2);
+      }
+    }
+    if (lane == 0) for (int i = 0; i < 64; i++) scf[i] = tmp[i];
+  }
+  uint32_t nw = 0;                                           /* words (pairs) of the row written so far */
+  if (p23l) {
+    const uint32_t bit_pos_end = part2_start + p23l - 1;
+    uint32_t r1s, r2s;
+    if (is_short) { r1s = 36; r2s = 576; }
+    else { r1s = T->sfb_l[fr.sfreq][P3_GC_REG0(g) + 1]; r2s = T->sfb_l[fr.sfreq][P3_GC_REG0(g) + P3_GC_REG1(g) + 2]; }
+    const uint32_t bv2 = 2 * P3_GC_BIGV(g);
+    uint32_t i = 0;
+    for (int r = 0; r < 3; r++) {
+      const uint32_t t = P3_GC_TSEL(g, r);
+      const int book = T->table_book[t];
+      const uint16_t *tl = lut + (book < 0 ? T->hlut_zero : T->book_base[book]);
+      const uint32_t sh = 32u - (book < 0 ? 1u : T->book_pbits[book]), lb = book < 0 ? 0u : T->table_linbits[t];
+      const uint32_t iend = min(bv2, r == 0 ? r1s : r == 1 ? r2s : 576u);
+      while (i < iend) {
+        k1_bits bb; bb.init(sw, pos + lane);                 /* speculation: a pair that starts at bit pos + lane */
+        const uint32_t v = k1_pair(bb, tl, sh, lb);
+        const uint32_t len = bb.pos() - (pos + lane);
+        uint32_t cur = 0, cnt = 0, mine = 0;
+        while (cur < 32 && cnt < 32 && i < iend) {           /* the true chain through the lanes (cnt: the empty tables' code words have length 0) */
+          const uint32_t pv = __shfl_sync(0xffffffffu, v, cur), pl = __shfl_sync(0xffffffffu, len, cur);
+          if (lane == cnt) mine = pv;
+          cnt++; i += 2; cur += pl;
+        }
+        if (lane < cnt) dstw[nw + lane] = mine;              /* the window's pairs, one coalesced store */
+        nw += cnt; pos += cur;
+      }
+    }
+    /* count1 quads, same scheme (pdmp3.c:2091-2106) */
+    uint32_t is_pos = bv2;
+    const bool tabB = P3_GC_C1TAB(g), isoB = tabB && (fr.flags & P3_FRAME_ISO);
+    const uint32_t qbase = T->book_base[T->table_book[32]], qbits = T->book_pbits[T->table_book[32]];
+    while (is_pos <= 572 && pos <= bit_pos_end) {
+      const uint32_t p0 = pos + lane;
+      uint32_t w = p3_peek32(sw, p0), used = 0, leaf = 3;
+      if (!tabB) { const uint32_t e = lut[qbase + (w >> (32 - qbits))]; used = (e >> 8) & 31; leaf = e & 15; w <<= used; }
+      else if (isoB) { leaf = (~w) >> 28; used = 4; w <<= 4; }
+      int v = (leaf >> 3) & 1, ww = (leaf >> 2) & 1, x = (leaf >> 1) & 1, y = leaf & 1;
+      if (v) { if (w >> 31) v = -1; w <<= 1; used++; }
+      if (ww) { if (w >> 31) ww = -1; w <<= 1; used++; }
+      if (x) { if (w >> 31) x = -1; w <<= 1; used++; }
+      if (y) { if (w >> 31) y = -1; used++; }
+      const uint32_t q0 = (uint32_t)(v & 0xffff) | ((uint32_t)ww << 16), q1 = (uint32_t)(x & 0xffff) | ((uint32_t)y << 16);
+      uint32_t cur = 0, cnt = 0, m0 = 0, m1 = 0;
+      while (cur < 32 && cnt < 32 && is_pos <= 572 && pos + cur <= bit_pos_end) {
+        const uint32_t a = __shfl_sync(0xffffffffu, q0, cur), b = __shfl_sync(0xffffffffu, q1, cur), pl = __shfl_sync(0xffffffffu, used, cur);
+        if (lane == cnt) { m0 = a; m1 = b; }
+        cnt++; is_pos += 4; cur += pl;
+        if (pl == 0) break;                                  /* table B in compat mode with no sign bits: cannot happen (leaf 0011 has two), guard anyway */
+      }
+      if (lane < cnt) { dstw[nw + 2 * lane] = m0; dstw[nw + 2 * lane + 1] = m1; }
+      nw += 2 * cnt; pos += cur;
+    }
+    if (pos > bit_pos_end + 1) is_pos = is_pos >= 4 ? is_pos - 4 : 0;
+    c1 = is_pos;
+  }
+  __syncwarp();
+  for (uint32_t k = (c1 >> 1) + lane; k < 288; k += 32) dstw[k] = 0;        /* rzero region (and whatever a rolled-back quad left) */
+  return c1;
+}
+#endif

@@ -139,6 +139,26 @@ k_huffman(const uint32_t *__restrict__ ms /* compact main-data stream */, const 
       if (!ok && ++spins > (1u << 24)) __trap();
     } while (!ok);
   }
+#ifdef K1_COOP_TRIAL
+  {                                                        /* trial: one WARP per part, the warp's 32 parts one after the other (p3_k1.cuh) */
+    const uint32_t warp = threadIdx.x >> 5;
+    const int64_t o_cta0 = (F0 - f_first) * 4;
+    for (uint32_t k = 0; k < 32; k++) {
+      const uint32_t gi0 = warp * 32 + k;
+      const int64_t f0 = F0 + (gi0 >> 2);
+      if (f0 >= F1) break;
+      const uint32_t gr0 = (gi0 >> 1) & 1, ch0 = gi0 & 1;
+      const int64_t o0 = o_cta0 + gi0;
+      const p3_frame fr0 = frames[f0]; const p3_gc g0 = gcs[4 * f0 + 2 * gr0 + ch0];
+      uint8_t *scf0 = scf_out + o0 * P3_SCF_STRIDE;
+      if ((threadIdx.x & 31) < 4) reinterpret_cast<uint4 *>(scf0)[threadIdx.x & 31] = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+      const uint32_t c1v = k1_decode_gc_coop(sw, lut, T, gcs, fr0, g0, f0, gr0, ch0, win0 - 512 + (int64_t)base0, reinterpret_cast<uint32_t *>(is_out + o0 * 576), scf0);
+      if ((threadIdx.x & 31) == 0) count1_out[o0] = (int32_t)c1v;
+    }
+    return;
+  }
+#endif
   const uint32_t gi = s_key[threadIdx.x] & 0xffu;         /* granule-channel within the group handled by this thread */
   const int64_t f = F0 + (gi >> 2);
   const int64_t o_cta = (F0 - f_first) * 4;
