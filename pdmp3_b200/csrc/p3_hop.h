@@ -3,8 +3,10 @@
 #include <stdint.h>
 #include "../../include/pdmp3_b200.h"
 
-#define HOP_SEG   16384u               /* bytes of the raw stream per segment (one thread each) */
-#define HOP_LCAP  176                  /* headers a segment's chain can visit: frames are >= 96 bytes (32 kbps at 48 kHz) */
+#ifndef HOP_SEG
+#define HOP_SEG   16384u               /* bytes of the raw stream per segment (one thread each); must exceed the longest frame + the resync window (2594) */
+#endif
+#define HOP_LCAP  (HOP_SEG / 96 + 6)   /* headers a segment's chain can visit: frames are >= 96 bytes (32 kbps at 48 kHz) */
 #define HOP_PCAP  8                    /* headers kept in front of the meeting point before the list is rewritten instead */
 
 typedef struct {

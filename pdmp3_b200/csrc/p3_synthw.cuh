@@ -187,19 +187,6 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
 
   const int64_t gw = (int64_t)blockIdx.x * SW_WPB + warp;
   const int64_t c0 = f_first + gw * frames_per_warp;
-#ifdef SW_CTA_SYNC
-  /* experiment (classes with the rare paths only): the warps of a CTA pass the top of the granule loop together for as many
-   * granules as ALL of them have, so that they walk the 43 KB body in the same place (instruction-cache footprint) */
-  __shared__ int s_sync_iters;
-  if (!LEAN) {
-    if (threadIdx.x == 0) s_sync_iters = 0x7fffffff;
-    __syncthreads();
-    const int64_t c1x = min(c0 + (int64_t)frames_per_warp, f_end);
-    const int mine = c0 >= f_end ? 0 : 2 * (int)(c1x - c0 + (gw > 0 ? 1 : 0));
-    if (lane == 0) atomicMin(&s_sync_iters, mine);
-    __syncthreads();
-  }
-#endif
   if (c0 >= f_end) return;
   const int64_t c1 = min(c0 + (int64_t)frames_per_warp, f_end);
   const int warm = gw > 0 ? 1 : 0;
@@ -248,9 +235,6 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
 
   #pragma unroll 1
   for (int32_t q = 0; q < 2 * nfr; q++) {                  /* q: granules done by this warp */
-#ifdef SW_CTA_SYNC
-    if (!LEAN && q < s_sync_iters) __syncthreads();
-#endif
     {
       const int32_t gr = q & 1, fi = q >> 1, rel = rel0 + fi; /* frame index within the warp's run / relative to the launch */
       const uint32_t b = SW_NBUF == 2 ? (q & 1) : 0;
