@@ -214,6 +214,7 @@ int  p3_dist_gather_transport(p3_dist *d);   /* 1: PCM blocks go to rank 0 as co
 int  p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_bytes, int raw_on_device, const p3_parse_opts *opts,
                        int64_t chunk_frames, p3_shard_result *res);
 /* the floor of the gather on this box: every rank > 0 sends bytes_per_rank to rank 0, nothing else running */
+int64_t p3_dist_chunk_start(int64_t j, int64_t chunk_frames, int64_t n_frames);   /* first frame of chunk j of a shard's schedule (== n_frames past the end) */
 int  p3_dist_measure_ingest(p3_dist *d, uint64_t bytes_per_rank, int iters, float *ms_per_iter);
 
 #ifdef __cplusplus

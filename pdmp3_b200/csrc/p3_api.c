@@ -41,6 +41,8 @@ struct pdmp3_handle {
   int16_t *pcm; size_t pcm_cap;                     /* PCM queue: frames decoded ahead of small reads (pcm_cap frames of room) */
   size_t pend_pos, pend_end;                        /* undelivered PCM bytes of the queue: [pend_pos,pend_end) */
   int in_pinned;
+  unsigned char *own;                               /* the handle's own input buffer (`in` points at it unless a fed buffer is borrowed) */
+  int borrow, borrowed;                             /* feed=borrow: pdmp3_feed into an empty handle keeps the caller's pointer instead of copying */
   p3_frame *dfr[3]; p3_gc *dgc[3]; int dnext;       /* page-locked descriptor arrays, rotated over the in-flight batches */
   p3_ctx *ctx; int device; int ctx_failed; int mode; int host_sideinfo; int iso;
   int host_hop; size_t bpf_est;                     /* hop=host: frame hop on the host (default: on the device); bytes per frame seen so far */
@@ -62,6 +64,7 @@ pdmp3_handle *pdmp3_new(const char *decoder, int *error)
     if ((p = strstr(decoder, "ring="))) { unsigned long long v = strtoull(p + 5, NULL, 10); if (v >= 4096) id->cap = (size_t)v; }
     if ((p = strstr(decoder, "device="))) id->device = atoi(p + 7);
     if (strstr(decoder, "mode=exact")) id->mode = P3_MODE_EXACT;   /* bit-identical PCM; default is FAST (<= 1 LSB) */
+    if (strstr(decoder, "feed=borrow")) id->borrow = 1;             /* no copy in pdmp3_feed: the caller keeps its buffer alive and unchanged until it is consumed */
     if (strstr(decoder, "sideinfo=host")) id->host_sideinfo = 1;   /* parse the side info on the host instead of on the device */
     if (strstr(decoder, "hop=host") || id->host_sideinfo) id->host_hop = 1;   /* frame hop of large reads on the host as well (default: on the device, p3_hop.cu) */
     for (p = decoder; (p = strstr(p, "iso")) != NULL; p += 3)     /* "iso" as an option of its own: ISO 11172-3 semantics instead of the reference's quirks (P3_FRAME_ISO) */
@@ -70,6 +73,7 @@ pdmp3_handle *pdmp3_new(const char *decoder, int *error)
   if (id->cap > (1u << 20)) { id->in = (unsigned char *)p3_host_alloc_dev(id->device, id->cap); id->in_pinned = id->in != NULL; }   /* page-locked: full-speed H2D */
   if (!id->in) id->in = (unsigned char *)malloc(id->cap);
   if (!id->in) { free(id); if (error) *error = PDMP3_ERR; return NULL; }
+  id->own = id->in;
   id->ps.nch = id->ps.sfreq = -1; id->nch = 2; id->sfreq = 0;
   if (error) *error = PDMP3_OK;
   return id;
@@ -79,7 +83,7 @@ void pdmp3_delete(pdmp3_handle *id)
 {
   if (!id) return;
   if (id->ctx) p3_ctx_destroy(id->ctx);
-  if (id->in_pinned) p3_host_free(id->in); else free(id->in);
+  if (id->in_pinned) p3_host_free(id->own); else free(id->own);
   for (int k = 0; k < 3; k++) { p3_host_free(id->dfr[k]); p3_host_free(id->dgc[k]); }
   free(id->pcm); free(id);
 }
@@ -88,6 +92,7 @@ int pdmp3_open_feed(pdmp3_handle *id)
 {
   if (!id) return PDMP3_ERR;
   id->istart = id->iend = 0; id->processed = 0; id->new_header = 0;
+  id->in = id->own; id->borrowed = 0;
   id->pend_pos = id->pend_end = 0; id->bpf_est = 0;
   memset(&id->ps, 0, sizeof id->ps); id->ps.nch = id->ps.sfreq = -1;
   if (id->ctx) p3_ctx_reset(id->ctx);               /* hsynth_init / synth_init / g_main_data_top (pdmp3.c:2377-2379) */
@@ -120,6 +125,16 @@ static void big_memcpy(unsigned char *d, const unsigned char *s, size_t n)
 int pdmp3_feed(pdmp3_handle *id, const unsigned char *in, size_t size)
 {
   if (!(id && in && size)) return PDMP3_ERR;
+  if (id->borrow && in_filled(id) == 0) {             /* feed=borrow: decode straight out of the caller's buffer (page-locked for full-speed uploads) */
+    id->in = (unsigned char *)(uintptr_t)in; id->istart = 0; id->iend = size; id->borrowed = 1;
+    return PDMP3_OK;
+  }
+  if (id->borrowed) {                                 /* more data while a borrowed buffer is not used up: its rest moves into the handle's own buffer */
+    const size_t rest = in_filled(id);
+    if (rest + size > id->cap) return PDMP3_NO_SPACE;
+    memmove(id->own, id->in + id->istart, rest);
+    id->in = id->own; id->istart = 0; id->iend = rest; id->borrowed = 0;
+  }
   if (size > in_free(id)) return PDMP3_NO_SPACE;
   if (id->iend + size > id->cap) {                  /* compact */
     memmove(id->in, id->in + id->istart, in_filled(id));
@@ -260,7 +275,7 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
   { double t0 = trace ? now_ms() : 0;
     if (inflight && p3_batch_sync(id->ctx) != P3_OK) { fprintf(stderr, "pdmp3_b200: %s\n", p3_last_error()); res = PDMP3_ERR; }
     if (trace) { t_sync = now_ms() - t0; fprintf(stderr, "pdmp3_read: %d batches, parse %.1f ms, enqueue (incl. waiting for a slot) %.1f ms, final sync %.1f ms\n", nb, t_parse, t_decode, t_sync); } }
-  if (id->istart == id->iend) id->istart = id->iend = 0;
+  if (id->istart == id->iend) { id->istart = id->iend = 0; id->in = id->own; id->borrowed = 0; }
   if (id->new_header == 1 && res == PDMP3_OK) res = PDMP3_NEW_FORMAT;       /* pdmp3.c:2470-2472 */
   return res;
 }

@@ -91,12 +91,12 @@ struct p3_dist {
   /* copy-engine gather through a CUDA IPC mapping of rank 0's output buffer */
   int use_ipc;                           /* 1: agreed by all ranks at init */
   p3_ipc_msg *d_ipc, *h_ipc;             /* message buffer (device for the broadcast, page-locked host copy) */
-  void *exp_ptr; uint64_t exp_serial; cudaIpcMemHandle_t exp_handle;   /* rank 0: the buffer the current handle stands for */
+  void *exp_ptr; size_t exp_cap; uint64_t exp_serial; cudaIpcMemHandle_t exp_handle;   /* rank 0: the allocation the current handle stands for */
   void *map_ptr; uint64_t map_serial;    /* peers: the mapping currently open */
   /* copy-engine scatter: rank 0 maps every peer's staging buffer and pushes the byte ranges into them */
   p3_ipc_peer *d_peer, *h_peer;          /* [world] message buffers */
   void *peer_map[P3_DIST_MAXW]; uint64_t peer_serial[P3_DIST_MAXW];
-  void *exp_in; uint64_t exp_in_serial; cudaIpcMemHandle_t exp_in_handle;    /* peers: the staging buffer the current handle stands for */
+  void *exp_in; size_t exp_in_cap; uint64_t exp_in_serial; cudaIpcMemHandle_t exp_in_handle;    /* peers: the staging allocation the current handle stands for */
   int *d_tok;                            /* completion tokens */
 };
 
@@ -233,6 +233,7 @@ static inline int64_t chunk_start(int64_t j, int64_t C, int64_t nf)
   else f = nf;
   return f < nf ? f : nf;
 }
+extern "C" int64_t p3_dist_chunk_start(int64_t j, int64_t chunk_frames, int64_t n_frames) { return chunk_start(j, chunk_frames, n_frames); }   /* (the schedule, for tests) */
 static inline int64_t chunk_count(int64_t C, int64_t nf) { int64_t j = 0; while (chunk_start(j, C, nf) < nf) j++; return j; }
 /* PCM slots [lo, hi) (in frames of the rank's shard) that chunk j of a shard with `wu` warm-up frames and `cnt` own frames produces */
 static inline void chunk_slots(int64_t j, int64_t C, int64_t wu, int64_t cnt, int64_t *lo, int64_t *hi)
@@ -296,7 +297,9 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
     if ((rc = size_batch(c, sl, r->n_frames, r->n_frames, r->maxg, pl[0].ms_bytes, c->stream))) return rc;
     memset(ipc, 0, sizeof *ipc);
     if (d->use_ipc && W > 1) {
-      if (d->exp_ptr != sl->pcm.p) { CK(cudaIpcGetMemHandle(&d->exp_handle, sl->pcm.p)); d->exp_ptr = sl->pcm.p; d->exp_serial++; }
+      if (d->exp_ptr != sl->pcm.p || d->exp_cap != sl->pcm.cap) {      /* (a new allocation may come back at the old address: the size tells) */
+        CK(cudaIpcGetMemHandle(&d->exp_handle, sl->pcm.p)); d->exp_ptr = sl->pcm.p; d->exp_cap = sl->pcm.cap; d->exp_serial++;
+      }
       ipc->h = d->exp_handle; ipc->bytes = sl->pcm.cap; ipc->serial = d->exp_serial;
     }
     CK(cudaMemcpyAsync(d->d_plan + pb - sizeof(p3_ipc_msg), ipc, sizeof *ipc, cudaMemcpyHostToDevice, c->stream));
@@ -350,7 +353,9 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
     if ((rc = ensure(&sl->raw, len + 64))) return rc;
     sl->raw_dev = (const uint8_t *)sl->raw.p;
     if (push) {
-      if (d->exp_in != sl->raw.p) { CK(cudaIpcGetMemHandle(&d->exp_in_handle, sl->raw.p)); d->exp_in = sl->raw.p; d->exp_in_serial++; }
+      if (d->exp_in != sl->raw.p || d->exp_in_cap != sl->raw.cap) {
+        CK(cudaIpcGetMemHandle(&d->exp_in_handle, sl->raw.p)); d->exp_in = sl->raw.p; d->exp_in_cap = sl->raw.cap; d->exp_in_serial++;
+      }
       d->h_peer[R].h = d->exp_in_handle; d->h_peer[R].serial = d->exp_in_serial; d->h_peer[R].bytes = sl->raw.cap;
       CK(cudaMemcpyAsync(d->d_peer + R, d->h_peer + R, sizeof(p3_ipc_peer), cudaMemcpyHostToDevice, d->s_scatter));
       NK(g_nccl.Send(d->d_peer + R, sizeof(p3_ipc_peer), ncclUint8, 0, d->comm_s, d->s_scatter));

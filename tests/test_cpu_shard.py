@@ -46,3 +46,27 @@ def test_plan_covers_reservoir():
             sub = s[p["byte_lo"]:p["byte_hi"]]
             o = H.oracle_decode(sub, lookahead=0, taps=False, warmup=p["warmup"])["pcm"]
             assert np.array_equal(o, whole[p["first"]:p["last"]]), (world, p)
+
+
+def test_chunk_schedule_of_the_sharded_decode():
+    """p3_sharded_decode cuts a shard into launch sequences (C/4, C/4, C/2, C ... C, C/2, C/4, C/4; uniform for short shards).
+    Every rank derives the schedule from the plan alone, so it must be a partition of [0, n) into chunks of at most C frames that
+    start on multiples of 32 (K1's frame groups), for any shard length."""
+    import ctypes as C, pdmp3_b200
+    L = pdmp3_b200.lib()
+    L.p3_dist_chunk_start.restype = C.c_int64; L.p3_dist_chunk_start.argtypes = [C.c_int64] * 3
+    import random
+    rng = random.Random(5)
+    cases = [(c, n) for c in (32, 64, 96, 256, 4096, 227328, 262144) for n in (1, 31, 32, 33, 700, 3 * c - 1, 3 * c, 3 * c + 1, 8 * c + 17, 1000002)]
+    cases += [(32 * rng.randint(1, 9000), rng.randint(1, 3000000)) for _ in range(300)]
+    for c, n in cases:
+        prev, j, sizes = 0, 1, []
+        while True:
+            f = L.p3_dist_chunk_start(j, c, n)
+            assert prev < f <= n, (c, n, j, prev, f)
+            assert prev % 32 == 0 and f - prev <= c, (c, n, j, prev, f)
+            sizes.append(f - prev); prev = f; j += 1
+            if f == n: break
+            assert j < 200000
+        assert L.p3_dist_chunk_start(0, c, n) == 0 and L.p3_dist_chunk_start(j + 3, c, n) == n
+        if n >= 3 * c and c >= 128: assert sizes[0] <= c // 4 and sizes[-1] <= c // 4 + 64, (c, n, sizes[:4], sizes[-4:])

@@ -120,3 +120,36 @@ def test_cli_entry_writes_raw_file(tmp_path):
     o = H.oracle_decode(s, lookahead=1152, taps=False)["pcm"]
     assert raw.size == o.size
     assert np.abs(raw.astype(np.int32) - o.reshape(-1).astype(np.int32)).max() <= 1      # default FAST mode
+
+
+@pytest.mark.parametrize("opts", ["b200:ring=4000000", "b200:ring=4000000,hop=host"])
+def test_feed_borrow_equals_copying_feed(opts):
+    """feed=borrow (no copy in pdmp3_feed: the handle decodes out of the caller's buffer) delivers the same bytes and return codes
+    as the copying feed: one big feed + one big read, a second feed while a rest of the borrowed buffer is pending (the rest moves
+    into the handle's own buffer), and small reads in the reference's CLI pattern."""
+    import pdmp3_b200
+    s, _ = H.synth(700, seed=71, **H.CONFIGS["cfg4_vbr_mixed"])
+    half = len(s) // 2
+    got = {}
+    for mode in ("", ",feed=borrow"):
+        d = pdmp3_b200.Decoder(opts + mode); d.open_feed()
+        a, b = np.ascontiguousarray(s[:half]), np.ascontiguousarray(s[half:])     # kept alive below: borrowed buffers belong to the caller
+        trace = [d.feed(a)]
+        rc, p1 = d.read(700 * 4608); trace.append((rc, len(p1)))
+        trace.append(d.feed(b))
+        rc, p2 = d.read(700 * 4608); trace.append((rc, len(p2)))
+        rc, p3 = d.read(700 * 4608); trace.append((rc, len(p3)))
+        got[mode] = (np.concatenate([p1, p2, p3]), trace)
+        d.close()
+    assert got[""][1] == got[",feed=borrow"][1], (got[""][1], got[",feed=borrow"][1])
+    assert np.array_equal(got[""][0], got[",feed=borrow"][0]) and len(got[""][0]) >= 690 * 4608
+    # the CLI pattern on a borrowed whole-stream feed: small reads out of the caller's buffer
+    d = pdmp3_b200.Decoder("b200:ring=65536,feed=borrow"); d.open_feed()
+    whole = np.ascontiguousarray(s); assert d.feed(whole) == 0
+    parts = []
+    while True:
+        rc, out = d.read(16384)
+        parts.append(out.copy())
+        if rc in (-1, -10): break
+    d.close()
+    assert np.array_equal(np.concatenate(parts), got[""][0])
