@@ -2,6 +2,7 @@
 
   pdmp3_b200/libpdmp3_b200.so   the product: plain-C host side + sm_100a kernels (nvcc, sm_100a only)
   tools/libp3synth.so           synthetic stream generator (test/bench infrastructure)
+  tools/tc_trial/tc_matrix      the tcgen05 trial of the matrixing stage (measurement tool)
   oracle/libp3_oracle.so        CPU restatement of the reference (checker)
   oracle/_ref/*                 the compiled reference + tap harness (only where /root/reference exists)
 """
@@ -62,6 +63,15 @@ def build_tools(force=False):
     return out
 
 
+def build_trials(force=False):
+    """tools/tc_trial/tc_matrix: the stand-alone tcgen05 trial of the matrixing stage (measurement tool, not product)"""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    src = os.path.join(ROOT, "tools", "tc_trial", "tc_matrix.cu"); out = os.path.join(ROOT, "tools", "tc_trial", "tc_matrix")
+    if force or _newer(out, [src, os.path.join(CSRC, "p3_xform.cuh"), os.path.join(CSRC, "p3_lee.inc")]):
+        _run([nvcc] + NVCC_ARCH + ["-O3", "-lineinfo", "-std=c++17", "-diag-suppress", "550", "-I", CSRC, "-o", out, src])
+    return out
+
+
 def build_oracle():
     _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"])
 
@@ -69,6 +79,7 @@ def build_oracle():
 def build_all(force=False, verbose=False):
     build_product(force, verbose)
     build_tools(force)
+    build_trials(force)
     build_oracle()
 
 
