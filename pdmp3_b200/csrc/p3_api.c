@@ -45,6 +45,7 @@ struct pdmp3_handle {
   int borrow, borrowed;                             /* feed=borrow: pdmp3_feed into an empty handle keeps the caller's pointer instead of copying */
   p3_frame *dfr[3]; p3_gc *dgc[3]; int dnext;       /* page-locked descriptor arrays, rotated over the in-flight batches */
   p3_ctx *ctx; int device; int ctx_failed; int mode; int host_sideinfo; int iso;
+  int64_t batch;                                    /* frames per GPU batch of a large read (batch=<n>, default P3_API_CHUNK) */
   int host_hop; size_t bpf_est;                     /* hop=host: frame hop on the host (default: on the device); bytes per frame seen so far */
   p3_parse_state ps;
   int new_header;                                   /* 0 none yet, 1 seen, -1 reported (pdmp3.c:1318,2470,2531) */
@@ -58,12 +59,13 @@ pdmp3_handle *pdmp3_new(const char *decoder, int *error)
 {
   pdmp3_handle *id = (pdmp3_handle *)calloc(1, sizeof *id);
   if (!id) { if (error) *error = PDMP3_ERR; return NULL; }
-  id->cap = P3_DEFAULT_RING; id->device = 0; id->mode = P3_MODE_FAST;
+  id->cap = P3_DEFAULT_RING; id->device = 0; id->mode = P3_MODE_FAST; id->batch = P3_API_CHUNK;
   if (decoder) {                                    /* "b200:ring=<bytes>,device=<n>" */
     const char *p;
     if ((p = strstr(decoder, "ring="))) { unsigned long long v = strtoull(p + 5, NULL, 10); if (v >= 4096) id->cap = (size_t)v; }
     if ((p = strstr(decoder, "device="))) id->device = atoi(p + 7);
     if (strstr(decoder, "mode=exact")) id->mode = P3_MODE_EXACT;   /* bit-identical PCM; default is FAST (<= 1 LSB) */
+    if ((p = strstr(decoder, "batch="))) { long long v = atoll(p + 6); if (v >= 1024 && v <= (1 << 20)) id->batch = v; }
     if (strstr(decoder, "feed=borrow")) id->borrow = 1;             /* no copy in pdmp3_feed: the caller keeps its buffer alive and unchanged until it is consumed */
     if (strstr(decoder, "sideinfo=host")) id->host_sideinfo = 1;   /* parse the side info on the host instead of on the device */
     if (strstr(decoder, "hop=host") || id->host_sideinfo) id->host_hop = 1;   /* frame hop of large reads on the host as well (default: on the device, p3_hop.cu) */
@@ -181,7 +183,8 @@ int pdmp3_read(pdmp3_handle *id, unsigned char *outmemory, size_t outsize, size_
      * frames are decoded, the bytes delivered and the return codes are the reference's; only the moment differs. */
     int direct = outsize >= P3_API_DIRECT * fbytes;
     int64_t want = direct ? (int64_t)(outsize / fbytes) : P3_API_AHEAD;
-    if (want > P3_API_CHUNK) want = P3_API_CHUNK;
+    if (direct && !id->host_hop && want > id->batch) want = id->batch;
+    else if (want > P3_API_CHUNK && !(direct && !id->host_hop)) want = P3_API_CHUNK;
     if (direct && want >= 1024 && !id->host_hop) {
       /* Large reads: nothing is parsed on the host.  A window of the buffered bytes goes to the device, the frame hop
        * (Search_Header / Read_Header, pdmp3.c:1252-1340) runs there (p3_hop.cu) and tells how many frames it found and
