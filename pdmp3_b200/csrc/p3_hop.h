@@ -45,7 +45,7 @@ typedef struct {
 #ifdef __CUDACC__
 struct p3_hop_work {                   /* device scratch, grown on demand */
   hop_seg *seg; uint16_t *lists; uint64_t *exit[2]; int64_t cap_seg; hop_part *part;
-  p3_hop_result *d_res; p3_hop_result *h_res;     /* h_res: page-locked */
+  p3_hop_result *d_res; p3_hop_result *h_res, *h_res_dev;     /* h_res: page-locked and mapped (h_res_dev: its device address) */
 };
 int p3_hop_work_ensure(p3_hop_work *w, int64_t nseg);
 void p3_hop_work_free(p3_hop_work *w);
