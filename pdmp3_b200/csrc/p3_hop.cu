@@ -358,7 +358,7 @@ k_hop_tail(const uint8_t *__restrict__ raw, const p3_frame *__restrict__ frames,
 }
 
 /* The result block goes to the host by STORES into mapped page-locked memory, not by a device-to-host copy: in the streaming path
- * the D2H copy engine is busy with the previous batch's PCM (2.9 ms per 32 768 frames), and a 160-byte cudaMemcpyAsync queued
+ * the D2H copy engine is busy with the previous batch's PCM (2.9 ms per 32 768 frames), and a 128-byte cudaMemcpyAsync queued
  * behind it made every hop wait for it -- twice per batch (measured: 99 of 102 ms of pdmp3_read were spent there). */
 extern "C" __global__ void k_hop_publish(const p3_hop_result *__restrict__ d, p3_hop_result *__restrict__ h)
 {
