@@ -125,6 +125,10 @@ void p3_ctx_destroy(p3_ctx *c);
 int  p3_ctx_reset(p3_ctx *c);                 /* zero overlap / FIFO / reservoir state (pdmp3_open_feed, pdmp3.c:2377-2379) */
 int  p3_ctx_set_mode(p3_ctx *c, int mode);
 int  p3_ctx_set_taps(p3_ctx *c, int on);              /* keep stage taps of the next batches on the device */
+int  p3_ctx_set_overlap(p3_ctx *c, int64_t chunk_frames, int prio, int synth_pad_bytes, int k1_pad_bytes);
+                                                  /* FAST mode: K0 + K1 of chunk i+1 run on their own stream under the synthesis of chunk i (0 = off);
+                                                     prio 1: K1's stream above the kernel stream; pads: unused dynamic shared memory that caps the
+                                                     CTAs per SM of the synthesis kernels / of K1 (tuning).  Same PCM bits as the sequential path. */
 int  p3_ctx_set_frames_per_cta(p3_ctx *c, int n);     /* FAST mode: frames each CTA (k_synth_fast) / warp (k_synth_warp) walks (default 32) */
 int  p3_ctx_set_synth_kernel(p3_ctx *c, int which);   /* FAST mode: 0 = k_synth_warp(_lean) for stereo batches (default), 1 = always k_synth_fast,
                                                          2 = k_synth_warp only, no content classes (check: same bits as 0) */

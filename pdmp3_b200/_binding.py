@@ -75,6 +75,7 @@ def lib():
     L.p3_ctx_set_taps.argtypes = [C.c_void_p, C.c_int]
     L.p3_ctx_set_frames_per_cta.argtypes = [C.c_void_p, C.c_int]
     L.p3_ctx_set_synth_kernel.argtypes = [C.c_void_p, C.c_int]
+    L.p3_ctx_set_overlap.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int]
     L.p3_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3Parsed), C.c_void_p, C.POINTER(P3Taps)]
     L.p3_synth_from_xr.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(P3Parsed), C.c_void_p]
     L.p3_batch_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(P3Parsed)]
@@ -178,6 +179,10 @@ class Context:
     def set_synth_kernel(self, which):
         """FAST mode: 0 = k_synth_warp / k_synth_warp_lean by content class (default), 1 = always k_synth_fast, 2 = k_synth_warp only (no classes)."""
         _check(lib().p3_ctx_set_synth_kernel(self.h, which), "p3_ctx_set_synth_kernel")
+
+    def set_overlap(self, chunk_frames, prio=0, synth_pad=0, k1_pad=0):
+        """FAST mode: K0 + K1 of chunk i+1 under the synthesis of chunk i (0 = off); call before upload (sizes the intermediates)."""
+        _check(lib().p3_ctx_set_overlap(self.h, chunk_frames, prio, synth_pad, k1_pad), "p3_ctx_set_overlap")
 
     def reset(self):
         _check(lib().p3_ctx_reset(self.h), "p3_ctx_reset")

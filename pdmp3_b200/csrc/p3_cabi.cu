@@ -74,7 +74,13 @@ struct p3_ctx {
   p3_hop_work hop;
   uint8_t *d_tail_cur, *d_tail_nxt; int tail_on_device, have_next_tail_dev;
   float hop_ms;
+  /* K1 / synthesis overlap (FAST mode, run_all_overlap): the batch goes through in chunks of ov_chunk frames, K0 + K1 of chunk
+   * i+1 on their own stream while the synthesis of chunk i runs on c->stream; OV_NBUF sets of intermediates */
+  cudaStream_t s_k1[2]; cudaEvent_t ov_start, ov_k1_done[3], ov_synth_done[3];
+  int64_t ov_chunk; int ov_prio, ov_synth_pad, ov_k1_pad;
 };
+#define OV_NBUF 3
+#define OV_MAX_PAD (64 * 1024)                              /* largest shared-memory padding p3_ctx_set_overlap accepts (caps the CTAs per SM of a kernel) */
 
 extern "C" void *p3_host_alloc(size_t bytes) { void *p = NULL; return cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess ? p : NULL; }
 /* same, after selecting `device`: the allocation then does not create a primary context on device 0 for a decoder that runs on device N */
@@ -106,6 +112,13 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
 static int ctx_init(p3_ctx *c, int n_sm)
 {
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0; CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));          /* lo: least (what c->stream has), hi: greatest */
+    CK(cudaStreamCreateWithPriority(&c->s_k1[0], cudaStreamNonBlocking, lo));     /* ov_prio 0: K1 and the synthesis at the same priority */
+    CK(cudaStreamCreateWithPriority(&c->s_k1[1], cudaStreamNonBlocking, hi < lo ? lo - 1 : lo));   /* ov_prio 1: K1's CTAs are placed first */
+    CK(cudaEventCreateWithFlags(&c->ov_start, cudaEventDisableTiming));
+    for (int i = 0; i < OV_NBUF; i++) { CK(cudaEventCreateWithFlags(&c->ov_k1_done[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ov_synth_done[i], cudaEventDisableTiming)); }
+  }
   CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
   c->n_sm = n_sm;
@@ -127,12 +140,12 @@ static int ctx_init(p3_ctx *c, int n_sm)
   CK(cudaFuncSetAttribute(k_polyphase, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   c->chunk_frames = 1 << 18; c->fpc = 32;
   { const char *e = getenv("P3_FPC"); if (e && atoi(e) >= 1) c->fpc = atoi(e); }   /* tuning: frames per run (warp of k_synth_warp / CTA of k_synth_fast) */
-  CK(cudaFuncSetAttribute(k_synth_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
-  CK(cudaFuncSetAttribute(k_synth_warp_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
-  CK(cudaFuncSetAttribute(k_synth_warp_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
-  CK(cudaFuncSetAttribute(k_synth_warp_iso_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
-  CK(cudaFuncSetAttribute(k_synth_warp_iso, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
-  CK(cudaFuncSetAttribute(k_synth_warp_iso_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes()));
+  CK(cudaFuncSetAttribute(k_synth_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes() + OV_MAX_PAD));
+  CK(cudaFuncSetAttribute(k_synth_warp_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes() + OV_MAX_PAD));
+  CK(cudaFuncSetAttribute(k_synth_warp_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes() + OV_MAX_PAD));
+  CK(cudaFuncSetAttribute(k_synth_warp_iso_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes() + OV_MAX_PAD));
+  CK(cudaFuncSetAttribute(k_synth_warp_iso, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes() + OV_MAX_PAD));
+  CK(cudaFuncSetAttribute(k_synth_warp_iso_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes() + OV_MAX_PAD));
   {
     /* pow43s[8207 + v] = sign(v) * |v|^(4/3): requantization without abs / sign fix-up (pdmp3.c:2125-2132) */
     static float h[2 * 8207 + 1];
@@ -179,6 +192,9 @@ extern "C" void p3_ctx_destroy(p3_ctx *c)
   cudaFree(c->d_tail_cur); cudaFree(c->d_tail_nxt); p3_hop_work_free(&c->hop);
   for (int i = 0; i < 10; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   if (c->stream) cudaStreamDestroy(c->stream);
+  for (int i = 0; i < 2; i++) if (c->s_k1[i]) cudaStreamDestroy(c->s_k1[i]);
+  if (c->ov_start) cudaEventDestroy(c->ov_start);
+  for (int i = 0; i < OV_NBUF; i++) { if (c->ov_k1_done[i]) cudaEventDestroy(c->ov_k1_done[i]); if (c->ov_synth_done[i]) cudaEventDestroy(c->ov_synth_done[i]); }
   if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
   if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   cudaGetLastError();
@@ -196,6 +212,7 @@ extern "C" int p3_ctx_reset(p3_ctx *c)
   return P3_OK;
 }
 
+extern "C" int p3_ctx_set_overlap(p3_ctx *c, int64_t chunk_frames, int prio, int synth_pad_bytes, int k1_pad_bytes);
 extern "C" int p3_ctx_set_mode(p3_ctx *c, int mode)
 {
   if (!c || (mode != P3_MODE_EXACT && mode != P3_MODE_FAST)) return fail(P3_EINVAL, "bad mode");
@@ -206,6 +223,19 @@ extern "C" int p3_ctx_set_mode(p3_ctx *c, int mode)
   /* K1's shared-memory window is sized over groups of K1_FPB frames aligned to the batch start (stage_batch); a launch
    * sequence must start on such a boundary, or a group could span more bytes than the window */
   c->chunk_frames -= c->chunk_frames % K1_FPB;
+  { const char *e = getenv("P3_OVERLAP");                  /* "chunk[,prio[,synth_pad[,k1_pad]]]" */
+    if (e) { long long ch = 0; int pr = 0, sp = 0, kp = 0; sscanf(e, "%lld,%d,%d,%d", &ch, &pr, &sp, &kp); int rc = p3_ctx_set_overlap(c, ch, pr, sp, kp); if (rc) return rc; } }
+  return P3_OK;
+}
+/* K1 / synthesis overlap of FAST mode (run_all_overlap): chunk_frames = 0 turns it off; prio 1 puts K1's stream above the kernel
+ * stream; the pads add unused dynamic shared memory to the synthesis kernels / to K1, which caps their CTAs per SM (tuning). */
+extern "C" int p3_ctx_set_overlap(p3_ctx *c, int64_t chunk_frames, int prio, int synth_pad_bytes, int k1_pad_bytes)
+{
+  if (!c || chunk_frames < 0 || prio < 0 || prio > 1 || synth_pad_bytes < 0 || synth_pad_bytes > OV_MAX_PAD || k1_pad_bytes < 0 || k1_pad_bytes > OV_MAX_PAD)
+    return fail(P3_EINVAL, "bad overlap parameters");
+  if (chunk_frames && chunk_frames < 4 * K1_FPB) chunk_frames = 4 * K1_FPB;
+  c->ov_chunk = chunk_frames - chunk_frames % K1_FPB;      /* a launch sequence starts on a K1 group boundary (see p3_ctx_set_mode) */
+  c->ov_prio = prio; c->ov_synth_pad = synth_pad_bytes; c->ov_k1_pad = k1_pad_bytes;
   return P3_OK;
 }
 extern "C" int p3_ctx_set_taps(p3_ctx *c, int on) { if (!c) return P3_EINVAL; c->taps = on; return P3_OK; }
@@ -241,7 +271,8 @@ static int size_batch(p3_ctx *c, p3_slot *sl, int64_t nf, int64_t npcm, uint64_t
   if ((rc = ensure(&sl->frames, (size_t)(nf ? nf : 1) * sizeof(p3_frame)))) return rc;
   if ((rc = ensure(&sl->gcs, (size_t)(nf ? nf : 1) * 4 * sizeof(p3_gc)))) return rc;
   if ((rc = ensure(&sl->pcm, (size_t)(npcm ? npcm : 1) * 1152 * c->nch * sizeof(int16_t)))) return rc;
-  const int64_t cf = nf < c->chunk_frames ? nf : c->chunk_frames;
+  int64_t cf = nf < c->chunk_frames ? nf : c->chunk_frames;
+  if (c->ov_chunk > 0 && OV_NBUF * c->ov_chunk > cf) cf = OV_NBUF * c->ov_chunk;   /* the overlapped pipeline keeps OV_NBUF chunks of intermediates */
   if (cf) {
     if ((rc = ensure(&c->is16, (size_t)cf * 4 * 576 * 2))) return rc;
     if ((rc = ensure(&c->count1, (size_t)cf * 4 * 4))) return rc;
@@ -252,6 +283,7 @@ static int size_batch(p3_ctx *c, p3_slot *sl, int64_t nf, int64_t npcm, uint64_t
     }
   }
   /* K1 shared-memory window: 512 reservoir bytes + the largest group of K1_FPB frames (+ alignment and read-ahead slack) */
+  maxg *= (K1_FPB + 31) / 32;                              /* (maxg is measured over groups of 32 frames; K1_FPB is 32 unless an experiment build says otherwise) */
   c->k1_smem_words = (uint32_t)(((512 + maxg + 64 + 15) & ~(uint64_t)15) / 4);
   if ((size_t)c->k1_smem_words * 4 + sizeof(((p3_tables *)0)->hlut) + 4 * K1_THREADS * 4 > 200 * 1024) return fail(P3_EINVAL, "frame group too large for shared memory");
   /* compact main-data stream: 512 reservoir bytes + all main data of the batch, zero padded (the bit readers run a few words ahead) */
@@ -277,8 +309,8 @@ static int stage_batch(p3_ctx *c, p3_slot *sl, const uint8_t *raw, uint64_t raw_
   }
   if ((rc = ensure(&sl->raw, raw_bytes + 64))) return rc;
   uint64_t maxg = 0;
-  for (int64_t f0 = 0; f0 < nf; f0 += K1_FPB) {
-    int64_t f1 = f0 + K1_FPB < nf ? f0 + K1_FPB : nf;
+  for (int64_t f0 = 0; f0 < nf; f0 += 32) {                /* groups of 32 frames, like k_hop_groups */
+    int64_t f1 = f0 + 32 < nf ? f0 + 32 : nf;
     uint64_t span = b->frames[f1 - 1].main_pos + b->frames[f1 - 1].main_size - b->frames[f0].main_pos;
     if (span > maxg) maxg = span;
   }
@@ -317,11 +349,11 @@ static void launch_synth(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, const i
     const int64_t warps = (nf + c->fpc - 1) / c->fpc;
     /* the same grid three times: every CTA classifies its frames and only the kernel of that class decodes them (p3_synthw.cuh) */
     const unsigned grid = (unsigned)((warps + wpb - 1) / wpb);
-    (sl->iso ? k_synth_warp_iso_lean : k_synth_warp_lean)<<<grid, wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
+    (sl->iso ? k_synth_warp_iso_lean : k_synth_warp_lean)<<<grid, wpb * 32, p3_synthw_smem_bytes() + (size_t)c->ov_synth_pad, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
         is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207, classify);
-    (sl->iso ? k_synth_warp_iso_same : k_synth_warp_same)<<<grid, wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
+    (sl->iso ? k_synth_warp_iso_same : k_synth_warp_same)<<<grid, wpb * 32, p3_synthw_smem_bytes() + (size_t)c->ov_synth_pad, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
         is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207, classify);
-    (sl->iso ? k_synth_warp_iso : k_synth_warp)<<<grid, wpb * 32, p3_synthw_smem_bytes(), c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
+    (sl->iso ? k_synth_warp_iso : k_synth_warp)<<<grid, wpb * 32, p3_synthw_smem_bytes() + (size_t)c->ov_synth_pad, c->stream>>>(fr, gc, c->d_tables, f0, f1, c->fpc,
         is16, c1, scf, si, so, (int16_t *)sl->pcm.p, c->d_pow43s + 8207, classify);
     c->launches += 2;
   } else
@@ -339,7 +371,7 @@ static int run_chunk(p3_ctx *c, p3_slot *sl, int64_t f0, int64_t f1, cudaEvent_t
   if (ev) CK(cudaEventRecord(ev[0], c->stream));
   k_compact<<<(unsigned)((nf + 3) / 4), 128, 0, c->stream>>>(sl->raw_dev, fr, sl->d_tail, f0, f1, (uint32_t *)sl->ms.p);
   if (ev) CK(cudaEventRecord(ev[1], c->stream));
-  size_t smem1 = (size_t)c->k1_smem_words * 4 + 4 * K1_THREADS * 4 + (size_t)p3_tables_get()->hlut_used * 2 + 16;
+  size_t smem1 = (size_t)c->k1_smem_words * 4 + 4 * K1_THREADS * 4 + K1_LUT_SMEM(p3_tables_get()->hlut_used) + 16;
   k_huffman<<<(unsigned)((nf + K1_FPB - 1) / K1_FPB), K1_THREADS, smem1, c->stream>>>((const uint32_t *)sl->ms.p, fr, gc, c->d_tables, f0, f1,
       c->k1_smem_words, (int16_t *)c->is16.p, (int32_t *)c->count1.p, (uint8_t *)c->scf.p);
   if (ev) CK(cudaEventRecord(ev[2], c->stream));
@@ -387,10 +419,51 @@ static int run_sideinfo(p3_ctx *c, p3_slot *sl)
   return rc;
 }
 
+/* FAST mode, K1 and the synthesis overlapped.  K1 is integer / shared-memory work that leaves the FMA pipe idle (16 % busy), the
+ * synthesis is packed-fp32 work bound by that pipe and by issue slots at 57 % each: run one after the other, each leaves half of
+ * the SM's issue slots empty.  Here the batch goes through in chunks: K0 + K1 of chunk i+1 on their own stream while the
+ * synthesis kernels of chunk i run on c->stream, chained by events, OV_NBUF sets of intermediates; a chunk is small enough that
+ * neither kernel fills the machine on its own, so CTAs of both are resident on an SM together.  Same kernels, same launch
+ * arithmetic per chunk as run_chunk: the PCM is bit-identical to the sequential path (tests/test_gpu_fast.py). */
+static int overlap_on(const p3_ctx *c)
+{
+  return c->mode == P3_MODE_FAST && c->ov_chunk > 0 && !c->taps && c->n_frames > c->ov_chunk;
+}
+
+static int run_all_overlap(p3_ctx *c, p3_slot *sl)
+{
+  const p3_frame *fr = (const p3_frame *)sl->frames.p; const p3_gc *gc = (const p3_gc *)sl->gcs.p;
+  const int64_t C = c->ov_chunk;
+  if (c->is16.cap < (size_t)OV_NBUF * C * 4 * 576 * 2) return fail(P3_EINVAL, "batch was staged without room for the overlapped pipeline");
+  cudaStream_t sk = c->s_k1[c->ov_prio];
+  const size_t smem1 = (size_t)c->k1_smem_words * 4 + 4 * K1_THREADS * 4 + K1_LUT_SMEM(p3_tables_get()->hlut_used) + 16 + (size_t)c->ov_k1_pad;
+  CK(cudaEventRecord(c->ov_start, c->stream)); CK(cudaStreamWaitEvent(sk, c->ov_start, 0));   /* K1 starts behind whatever the kernel stream holds (side info, the previous batch) */
+  int i = 0;
+  for (int64_t f0 = 0; f0 < c->n_frames; f0 += C, i++) {
+    const int64_t f1 = f0 + C < c->n_frames ? f0 + C : c->n_frames, nf = f1 - f0;
+    const int b = i % OV_NBUF;
+    int16_t *is16 = (int16_t *)c->is16.p + (size_t)b * C * 4 * 576; int32_t *c1 = (int32_t *)c->count1.p + (size_t)b * C * 4;
+    uint8_t *scf = (uint8_t *)c->scf.p + (size_t)b * C * 4 * P3_SCF_STRIDE;
+    if (i >= OV_NBUF) CK(cudaStreamWaitEvent(sk, c->ov_synth_done[b], 0));          /* the synthesis of chunk i - OV_NBUF has read this set */
+    k_compact<<<(unsigned)((nf + 3) / 4), 128, 0, sk>>>(sl->raw_dev, fr, sl->d_tail, f0, f1, (uint32_t *)sl->ms.p);
+    k_huffman<<<(unsigned)((nf + K1_FPB - 1) / K1_FPB), K1_THREADS, smem1, sk>>>((const uint32_t *)sl->ms.p, fr, gc, c->d_tables, f0, f1, c->k1_smem_words, is16, c1, scf);
+    CK(cudaEventRecord(c->ov_k1_done[b], sk));
+    CK(cudaStreamWaitEvent(c->stream, c->ov_k1_done[b], 0));
+    p3_state *si = c->d_state[c->cur], *so = c->d_state[c->cur ^ 1];
+    CK(cudaMemcpyAsync(so, si, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
+    launch_synth(c, sl, f0, f1, is16, c1, scf, si, so);
+    CK(cudaEventRecord(c->ov_synth_done[b], c->stream));
+    CK(cudaGetLastError());
+    c->cur ^= 1; c->launches += 3;
+  }
+  return P3_OK;
+}
+
 static int run_all(p3_ctx *c, p3_slot *sl)
 {
   c->launches = 0;
   { int rc = run_sideinfo(c, sl); if (rc) return rc; }
+  if (overlap_on(c)) return run_all_overlap(c, sl);
   for (int64_t f0 = 0; f0 < c->n_frames; f0 += c->chunk_frames) {
     int64_t f1 = f0 + c->chunk_frames < c->n_frames ? f0 + c->chunk_frames : c->n_frames;
     int rc = run_chunk(c, sl, f0, f1, NULL);
@@ -554,12 +627,13 @@ extern "C" int p3_batch_time(p3_ctx *c, int iters, float *ms_total, float *ms_st
     CK(cudaMemcpyAsync(c->d_state[c->cur], save, sizeof(p3_state), cudaMemcpyDeviceToDevice, c->stream));
     c->launches = 0;
     CK(cudaEventRecord(c->ev[8], c->stream));
-    if (c->n_frames <= c->chunk_frames) { int rc = run_chunk(c, &c->slot[c->cur_slot], 0, c->n_frames, c->ev); if (rc) { cudaFree(save); return rc; } }
+    const bool one = c->n_frames <= c->chunk_frames && !overlap_on(c);       /* one launch sequence: per-kernel times exist */
+    if (one) { int rc = run_chunk(c, &c->slot[c->cur_slot], 0, c->n_frames, c->ev); if (rc) { cudaFree(save); return rc; } }
     else { int rc = run_all(c, &c->slot[c->cur_slot]); if (rc) { cudaFree(save); return rc; } }
     CK(cudaEventRecord(c->ev[9], c->stream));
     CK(cudaStreamSynchronize(c->stream));
     float ms; CK(cudaEventElapsedTime(&ms, c->ev[8], c->ev[9])); tot += ms;
-    if (c->n_frames <= c->chunk_frames)
+    if (one)
       for (int k = 0; k < 5; k++) { CK(cudaEventElapsedTime(&ms, c->ev[k], c->ev[k + 1])); st[k] += ms; }
   }
   cudaFree(save);

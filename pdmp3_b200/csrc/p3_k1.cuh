@@ -3,6 +3,14 @@
 #pragma once
 #include "p3_device.cuh"
 
+/* K1_LUT_GLOBAL (experiment, tools/build_variant.sh lutg -DK1_LUT_GLOBAL): the Huffman LUT is read through L1 from global memory
+ * instead of a per-CTA copy in shared memory -- 9 KB less per CTA, six resident CTAs per SM instead of five. */
+#ifdef K1_LUT_GLOBAL
+#define K1_LD(p) __ldg(p)
+#else
+#define K1_LD(p) (*(p))
+#endif
+
 /* MSB-first bit reader over the big-endian words of the CTA's window of the compact main-data stream in shared
  * memory: two consecutive words in registers plus a bit offset, so a 32-bit look-ahead is ONE funnel shift;
  * advancing adds to the offset and, when it crosses a word, shifts the pair and loads the next word under a
@@ -31,10 +39,10 @@ struct k1_bits {
 __device__ __forceinline__ uint32_t k1_pair(k1_bits &bb, const uint16_t *tl, uint32_t sh, uint32_t linbits)
 {
   const uint32_t w0 = bb.peek();
-  uint32_t e = tl[w0 >> sh], used = 0;
+  uint32_t e = K1_LD(tl + (w0 >> sh)), used = 0;
   if (e & 0x8000u) {                                      /* codes longer than the first level: walk the next levels */
     uint32_t cw = 32 - sh;
-    do { used += cw; cw = (e >> 10) & 7; e = tl[(e & 1023u) + ((w0 << used) >> (32 - cw))]; } while (e & 0x8000u);
+    do { used += cw; cw = (e >> 10) & 7; e = K1_LD(tl + (e & 1023u) + ((w0 << used) >> (32 - cw))); } while (e & 0x8000u);
   }
   used += (e >> 8) & 31;
   int x = (e >> 4) & 15, y = e & 15;
@@ -175,7 +183,7 @@ __device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw /* the CTA's
       pos = bb.pos();
       while (is_pos <= 572 && pos <= bit_pos_end) {
         uint32_t w = bb.peek(), used = 0, leaf = 3;
-        if (!tabB) { uint32_t e = lut[qbase + (w >> (32 - qbits))]; used = (e >> 8) & 31; leaf = e & 15; w <<= used; }
+        if (!tabB) { uint32_t e = K1_LD(lut + qbase + (w >> (32 - qbits))); used = (e >> 8) & 31; leaf = e & 15; w <<= used; }
         else if (isoB) { leaf = (~w) >> 28; used = 4; w <<= 4; }
         int v = (leaf >> 3) & 1, ww = (leaf >> 2) & 1, x = (leaf >> 1) & 1, y = leaf & 1;
         if (v) { if (w >> 31) v = -1; w <<= 1; used++; }
@@ -296,7 +304,7 @@ __device__ __forceinline__ uint32_t k1_decode_gc_coop(const uint32_t *sw, const 
     while (is_pos <= 572 && pos <= bit_pos_end) {
       const uint32_t p0 = pos + lane;
       uint32_t w = p3_peek32(sw, p0), used = 0, leaf = 3;
-      if (!tabB) { const uint32_t e = lut[qbase + (w >> (32 - qbits))]; used = (e >> 8) & 31; leaf = e & 15; w <<= used; }
+      if (!tabB) { const uint32_t e = K1_LD(lut + qbase + (w >> (32 - qbits))); used = (e >> 8) & 31; leaf = e & 15; w <<= used; }
       else if (isoB) { leaf = (~w) >> 28; used = 4; w <<= 4; }
       int v = (leaf >> 3) & 1, ww = (leaf >> 2) & 1, x = (leaf >> 1) & 1, y = leaf & 1;
       if (v) { if (w >> 31) v = -1; w <<= 1; used++; }

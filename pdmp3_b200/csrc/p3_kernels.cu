@@ -84,7 +84,11 @@ k_huffman(const uint32_t *__restrict__ ms /* compact main-data stream */, const 
   extern __shared__ __align__(16) uint32_t sm[];
   uint32_t *sw = sm;                                     /* window of the main-data stream, big-endian words */
   uint32_t *ring = sm + smem_words;                      /* [4][K1_THREADS] output staging */
+#ifdef K1_LUT_GLOBAL
+  const uint16_t *lut = T->hlut;
+#else
   uint16_t *lut = reinterpret_cast<uint16_t *>(ring + 4 * K1_THREADS);
+#endif
   __shared__ __align__(8) unsigned long long s_bar;
 
   const int64_t F0 = f_first + (int64_t)blockIdx.x * K1_FPB;
@@ -104,8 +108,10 @@ k_huffman(const uint32_t *__restrict__ ms /* compact main-data stream */, const 
                  :: "r"((uint32_t)__cvta_generic_to_shared(sw)), "l"(reinterpret_cast<const uint8_t *>(ms) + win0), "r"(bytes), "r"(bar) : "memory");
   }
 
+#ifndef K1_LUT_GLOBAL
   for (uint32_t i = threadIdx.x; i < (T->hlut_used + 1) / 2; i += blockDim.x)
     reinterpret_cast<uint32_t *>(lut)[i] = reinterpret_cast<const uint32_t *>(T->hlut)[i];
+#endif
 
   /* Lanes of a warp run in lock step, so a warp takes as long as its longest part.  Parts are therefore
    * handed out sorted by big_values (bitonic sort of the group's 128 keys in shared memory): each warp

@@ -4,8 +4,15 @@
 #include "p3_tables.h"
 #include "../../include/pdmp3_b200.h"
 
-#define K1_FPB      32                 /* frames per CTA in the Huffman kernel */
+#ifndef K1_FPB
+#define K1_FPB      32                 /* frames per CTA in the Huffman kernel (32 or 64: the sort keys carry the part index in a byte) */
+#endif
 #define K1_THREADS  (K1_FPB * 4)       /* one thread per granule-channel       */
+#ifdef K1_LUT_GLOBAL                    /* experiment (p3_k1.cuh): the LUT stays in global memory */
+#define K1_LUT_SMEM(used) ((size_t)0)
+#else
+#define K1_LUT_SMEM(used) ((size_t)(used) * 2)
+#endif
 #define K2_THREADS  192                /* requantize kernel: one CTA per granule, 3 lines per thread */
 #define K3_THREADS  576                /* IMDCT kernel: one CTA per granule-channel, one thread per output sample */
 #define K4_GRAN     4                  /* polyphase kernel: granules per CTA   */

@@ -200,3 +200,36 @@ def test_content_classes_give_the_same_bits(fast_ctx, name):
         got = fast_ctx.decode(s, lookahead=0)
         assert np.array_equal(got, full), "content classes change the result (run length %d)" % fpw
     fast_ctx.set_frames_per_cta(32)
+
+
+@pytest.mark.parametrize("name", ["cfg3", "cfg4", "garbage", "nores", "c1b"])
+def test_overlapped_pipeline_same_bits(fast_ctx, name):
+    """p3_ctx_set_overlap: K0 + K1 of chunk i+1 on their own stream under the synthesis of chunk i, three sets of intermediates.
+    Same kernels and the same launch boundaries as a chunked sequential run, so the PCM must be bit-identical to the one-launch
+    decode -- for chunk sizes that give 2 chunks (fewer than the buffer sets), a ragged last chunk, and many chunks that cycle
+    through the buffer sets several times; with and without K1's stream at the higher priority; host-parsed and device-hopped
+    batches; and again on the next batch with carried state."""
+    s, _ = H.synth(1500, seed=41, **VARIANTS[name])
+    fast_ctx.reset(); fast_ctx.set_overlap(0)
+    ref = fast_ctx.decode(s, lookahead=0)
+    try:
+        for chunk, prio in ((1024, 0), (640, 1), (128, 0), (128, 1), (352, 1)):
+            fast_ctx.set_overlap(chunk, prio)
+            fast_ctx.reset(); got = fast_ctx.decode(s, lookahead=0)
+            assert np.array_equal(got, ref), "overlap chunk %d prio %d" % (chunk, prio)
+            fast_ctx.reset(); got, info = fast_ctx.decode_raw(s, lookahead=0)
+            assert np.array_equal(got, ref), "overlap chunk %d prio %d (device hop)" % (chunk, prio)
+        # two batches through the overlapped pipeline with the reservoir and the filter state carried between them
+        import pdmp3_b200
+        fast_ctx.set_overlap(128, 1, 24 * 1024, 30 * 1024)          # with the shared-memory pads of the tuning sweep
+        fast_ctx.reset()
+        st = pdmp3_b200._binding.P3ParseState(0, 0, 0, -1, -1)
+        pos, parts = 0, []
+        while True:
+            p = pdmp3_b200.parse_stream(s[pos:], lookahead=0, max_frames=700, state=st)
+            if p.n_frames == 0: break
+            for f in range(p.n_frames): p.c.frames[f].pcm_index = f
+            parts.append(fast_ctx.decode_parsed(p)); pos += p.consumed
+        assert len(parts) >= 2 and np.array_equal(np.concatenate(parts), ref)
+    finally:
+        fast_ctx.set_overlap(0)
