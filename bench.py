@@ -94,13 +94,15 @@ def _port_worker(args):
     return o["n_frames"], dt
 
 
-def ref_cpu_throughput(stream_block_frames, nprocs, frames_per_proc):
+def ref_cpu_throughput(stream_block_frames, nprocs, frames_per_proc, exe_name="ref_bench"):
     """CPU arm: the unmodified reference (oracle/_ref/ref_bench, kind 'reference') on `nprocs` forked processes;
     if it did not travel with the repo, the oracle restatement (kind 'port') in a process pool.
     -> (sample-frames/s, frames, seconds, kind)"""
     import p3synth
-    exe = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
+    exe = os.path.join(ROOT, "oracle", "_ref", exe_name)
     if not os.path.exists(exe):
+        if exe_name != "ref_bench":
+            return None
         import multiprocessing as mp
         with mp.get_context("fork").Pool(nprocs) as pool:
             t0 = time.perf_counter(); res = pool.map(_port_worker, [(3, min(frames_per_proc, 1024))] * nprocs); wall = time.perf_counter() - t0
@@ -206,12 +208,17 @@ def main():
             if i >= a.warmup:
                 vals.append(r)
         v = float(np.median([x[0] for x in vals])); fr = vals[0][1]
+        # the other CPU baselines SURVEY 8d asks for, once each (bounded samples): one core, and the reference Makefile's own flags (-Os -ffast-math ...)
+        variants = {}
+        for key, exe, npr in (("O2_ieee_1core", "ref_bench", 1), ("stock_makefile_flags_allcores", "ref_bench_stock", ncores), ("stock_makefile_flags_1core", "ref_bench_stock", 1)):
+            r = ref_cpu_throughput(BLOCK, npr, per, exe)
+            if r: variants[key] = {"value": r[0], "cores": npr, "frames": r[1]}
         sample = "%d forked processes x %d frames of the same 320 kbps joint-stereo stream, pdmp3_read() 16 KiB / pdmp3_feed() 4096 B loop (pdmp3.c:2564-2584), -O2 IEEE build" % (ncores, per)
         print(json.dumps({"impl": "reference", "metric": "decoded_pcm_sample_frames_per_sec", "value": v, "unit": "sample-frames/s",
                           "x_realtime_44k1": v / 44100.0, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": 1e3 * fr * 1152 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "frames_per_step": fr},
-                          "cpu_baseline": {"value": v, "unit": "sample-frames/s", "cores": ncores, "kind": vals[0][3], "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": "sample-frames/s", "cores": ncores, "kind": vals[0][3], "sample": sample, "variants": variants},
                           "e2e": {"value": v, "unit": "sample-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}))
         return 0

@@ -16,6 +16,29 @@
  * advancing adds to the offset and, when it crosses a word, shifts the pair and loads the next word under a
  * predicate -- no branch, one shared-memory load per 32 bits.  The reference does a byte access per BIT
  * (pdmp3.c:1489-1527). */
+#ifdef K1_PAIR2
+/* (experiment build: the same reader with ONE 32-bit shared-memory address instead of a generic pointer, so that a refill
+ *  advances one register) */
+struct k1_bits {
+  uint32_t wa, base, hi, lo, off;                          /* wa: shared-memory address of the next word; hi:lo = the two words before it */
+  __device__ __forceinline__ void init(const uint32_t *s, uint32_t bitpos)
+  {
+    const uint32_t i = bitpos >> 5;
+    base = (uint32_t)__cvta_generic_to_shared(s); wa = base + (i + 2) * 4; off = bitpos & 31; hi = s[i]; lo = s[i + 1];
+  }
+  __device__ __forceinline__ uint32_t pos() const { return (wa - base - 8) * 8 + off; }
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_l(lo, hi, off); }
+  __device__ __forceinline__ void skip(uint32_t n)
+  {
+    off += n;
+    /* crossing a word: hi <- lo, lo <- next word, in place under one predicate (no copies; the in/out operands also keep the load
+     * behind the loads that produced hi / lo, i.e. behind the mbarrier wait) */
+    asm("{\n .reg .pred p;\n setp.ge.u32 p, %3, 32;\n @p mov.b32 %0, %1;\n @p ld.shared.b32 %1, [%2];\n @p add.u32 %2, %2, 4;\n}"
+        : "+r"(hi), "+r"(lo), "+r"(wa) : "r"(off));
+    off &= 31u;
+  }
+};
+#else
 struct k1_bits {
   const uint32_t *wp; uint32_t hi, lo, off;               /* hi:lo = words at wp[-2], wp[-1]; off in 0..31 */
   const uint32_t *base;
@@ -32,6 +55,7 @@ struct k1_bits {
     off &= 31u;
   }
 };
+#endif
 
 /* One Huffman-coded pair (pdmp3.c:1593-1643) as a packed int16 pair.  tl: the code book's LUT, sh = 32 - width of
  * its first level.  Fast path (no escape): the LUT leaf gives x, y and the code length; the sign bits follow the
@@ -64,6 +88,45 @@ __device__ __forceinline__ uint32_t k1_pair(k1_bits &bb, const uint16_t *tl, uin
   bb.skip(used + nx + ny);
   return __byte_perm((uint32_t)x, (uint32_t)y, 0x5410);    /* (x & 0xffff) | y << 16 */
 }
+
+#ifdef K1_PAIR2
+/* EXPERIMENT (tools/build_variant.sh pair2 -DK1_PAIR2): the same pair decode with ONE test in front of the fast path --
+ * `slow` = 0x8000 (entry is a link to the next LUT level) | 0x4000 if the table has linbits (x or y is 15: escape) -- instead of
+ * two reconvergence regions, and the sign / length arithmetic written as min / shift / xor-sub chains. */
+__device__ __forceinline__ uint32_t k1_pair2(k1_bits &bb, const uint16_t *tl, uint32_t sh, uint32_t linbits, uint32_t slow)
+{
+  const uint32_t w0 = bb.peek();
+  uint32_t e = tl[w0 >> sh], used = 0;
+  if (e & slow) {
+    if (e & 0x8000u) {
+      uint32_t cw = 32 - sh;
+      do { used += cw; cw = (e >> 10) & 7; e = tl[(e & 1023u) + ((w0 << used) >> (32 - cw))]; } while (e & 0x8000u);
+    }
+    if (e & slow) {                                        /* a leaf now: only the escape bit can still match */
+      used += (e >> 8) & 31;
+      int x = (e >> 4) & 15, y = e & 15;
+      bb.skip(used);
+      uint32_t w = bb.peek(), n = 0;
+      if (x == 15) { x += (int)(w >> (32 - linbits)); w <<= linbits; n += linbits; }
+      if (x) { if ((int)w < 0) x = -x; w <<= 1; n++; }
+      if (y == 15) { y += (int)(w >> (32 - linbits)); w <<= linbits; n += linbits; }
+      if (y) { if ((int)w < 0) y = -y; n++; }
+      bb.skip(n);
+      return __byte_perm((uint32_t)x, (uint32_t)y, 0x5410);
+    }
+  }
+  const uint32_t len = used + ((e >> 8) & 31u);
+  uint32_t x = (e >> 4) & 15u, y = e & 15u, nx, ny;
+  asm("min.u32 %0, %1, 1;" : "=r"(nx) : "r"(x));
+  asm("min.u32 %0, %1, 1;" : "=r"(ny) : "r"(y));
+  uint32_t w = w0 << len;
+  uint32_t m = (uint32_t)((int)w >> 31); x = (x ^ m) - m;
+  w <<= nx;
+  m = (uint32_t)((int)w >> 31); y = (y ^ m) - m;
+  bb.skip(len + nx + ny);
+  return __byte_perm(x, y, 0x5410);
+}
+#endif
 
 /* Per-thread output staging: 8 words (16 spectral values = half a 32-byte sector) are collected in
  * shared memory, transposed [word][thread] so that neither the word writes nor the flush conflict,
@@ -144,6 +207,9 @@ __device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw /* the CTA's
       else { r1s = T->sfb_l[fr.sfreq][P3_GC_REG0(g) + 1]; r2s = T->sfb_l[fr.sfreq][P3_GC_REG0(g) + P3_GC_REG1(g) + 2]; }
       const uint32_t bv2 = 2 * P3_GC_BIGV(g);
       const uint16_t *tls[3]; uint32_t shs[3], lbs[3];
+#ifdef K1_PAIR2
+      uint32_t sms[3];
+#endif
       #pragma unroll
       for (int r = 0; r < 3; r++) {
         const uint32_t t = P3_GC_TSEL(g, r);
@@ -152,6 +218,9 @@ __device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw /* the CTA's
         tls[r] = lut + (book < 0 ? T->hlut_zero : T->book_base[book]);
         shs[r] = 32u - (book < 0 ? 1u : T->book_pbits[book]);
         lbs[r] = book < 0 ? 0u : T->table_linbits[t];
+#ifdef K1_PAIR2
+        sms[r] = lbs[r] ? 0xc000u : 0x8000u;
+#endif
       }
       /* one loop over all big_values pairs; the table changes at the region boundaries, so every lane of the warp
        * stays in the same loop whatever its region split.  Four pairs (half a sector) per iteration leave straight
@@ -160,6 +229,17 @@ __device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw /* the CTA's
       uint32_t nsw = r1s;                                   /* next value index at which the table changes */
       k1_bits bb; bb.init(sw, pos);
       uint32_t i = 0;
+#ifdef K1_PAIR2
+      uint32_t sm = sms[0];
+      auto pair_at = [&](uint32_t at) -> uint32_t {
+        if (at == nsw) {
+          if (at == r1s) { tl = tls[1]; sh = shs[1]; lb = lbs[1]; sm = sms[1]; }
+          if (at == r2s) { tl = tls[2]; sh = shs[2]; lb = lbs[2]; sm = sms[2]; }
+          nsw = r2s > at ? r2s : 0xffffffffu;
+        }
+        return k1_pair2(bb, tl, sh, lb, sm);
+      };
+#else
       auto pair_at = [&](uint32_t at) -> uint32_t {
         if (at == nsw) {
           if (at == r1s) { tl = tls[1]; sh = shs[1]; lb = lbs[1]; }
@@ -168,6 +248,7 @@ __device__ __forceinline__ uint32_t k1_decode_gc(const uint32_t *sw /* the CTA's
         }
         return k1_pair(bb, tl, sh, lb);
       };
+#endif
       for (; i + 8 <= bv2; i += 8) {
         uint4 o;
         o.x = pair_at(i); o.y = pair_at(i + 2); o.z = pair_at(i + 4); o.w = pair_at(i + 6);
