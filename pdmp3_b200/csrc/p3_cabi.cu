@@ -13,6 +13,7 @@
 extern "C" int p3_fused_upload_consts(const p3_tables *T, const float *dct4);
 extern "C" size_t p3_synthw_smem_bytes(void);
 extern "C" int p3_synthw_warps_per_cta(void);
+extern "C" int p3_synthw_warps_per_sm(void);
 #define SW_DECL(NAME) extern "C" __global__ void NAME(const p3_frame *frames, const p3_gc *gcs, const p3_tables *T, int64_t f_first, int64_t f_end, int frames_per_warp, \
     const int16_t *is_in, const int32_t *count1, const uint8_t *scf, const p3_state *st_in, p3_state *st_out, int16_t *pcm, const float *pow43s, int classify)
 SW_DECL(k_synth_warp); SW_DECL(k_synth_warp_same); SW_DECL(k_synth_warp_lean); SW_DECL(k_synth_warp_iso); SW_DECL(k_synth_warp_iso_same); SW_DECL(k_synth_warp_iso_lean);
@@ -109,6 +110,9 @@ extern "C" int p3_ctx_create(int device, p3_ctx **out)
   return P3_OK;
 }
 
+/* dynamic shared memory the synthesis kernels may be launched with: their own + the tuning pad of p3_ctx_set_overlap, within the 227 KB a CTA can have */
+static int synthw_smem_cap(void) { const size_t v = p3_synthw_smem_bytes() + OV_MAX_PAD; return (int)(v < 227 * 1024 ? v : 227 * 1024); }
+
 static int ctx_init(p3_ctx *c, int n_sm)
 {
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -140,12 +144,12 @@ static int ctx_init(p3_ctx *c, int n_sm)
   CK(cudaFuncSetAttribute(k_polyphase, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   c->chunk_frames = 1 << 18; c->fpc = 32;
   { const char *e = getenv("P3_FPC"); if (e && atoi(e) >= 1) c->fpc = atoi(e); }   /* tuning: frames per run (warp of k_synth_warp / CTA of k_synth_fast) */
-  CK(cudaFuncSetAttribute(k_synth_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes() + OV_MAX_PAD));
-  CK(cudaFuncSetAttribute(k_synth_warp_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes() + OV_MAX_PAD));
-  CK(cudaFuncSetAttribute(k_synth_warp_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes() + OV_MAX_PAD));
-  CK(cudaFuncSetAttribute(k_synth_warp_iso_same, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes() + OV_MAX_PAD));
-  CK(cudaFuncSetAttribute(k_synth_warp_iso, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes() + OV_MAX_PAD));
-  CK(cudaFuncSetAttribute(k_synth_warp_iso_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p3_synthw_smem_bytes() + OV_MAX_PAD));
+  CK(cudaFuncSetAttribute(k_synth_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, synthw_smem_cap()));
+  CK(cudaFuncSetAttribute(k_synth_warp_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, synthw_smem_cap()));
+  CK(cudaFuncSetAttribute(k_synth_warp_same, cudaFuncAttributeMaxDynamicSharedMemorySize, synthw_smem_cap()));
+  CK(cudaFuncSetAttribute(k_synth_warp_iso_same, cudaFuncAttributeMaxDynamicSharedMemorySize, synthw_smem_cap()));
+  CK(cudaFuncSetAttribute(k_synth_warp_iso, cudaFuncAttributeMaxDynamicSharedMemorySize, synthw_smem_cap()));
+  CK(cudaFuncSetAttribute(k_synth_warp_iso_lean, cudaFuncAttributeMaxDynamicSharedMemorySize, synthw_smem_cap()));
   {
     /* pow43s[8207 + v] = sign(v) * |v|^(4/3): requantization without abs / sign fix-up (pdmp3.c:2125-2132) */
     static float h[2 * 8207 + 1];

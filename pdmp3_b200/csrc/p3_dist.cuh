@@ -261,9 +261,9 @@ extern "C" int p3_sharded_decode(p3_dist *d, const uint8_t *raw, uint64_t raw_by
   if ((rc = p3_ctx_reset(c))) return rc;                   /* every shard starts from zero state + its warm-up (rank 0: like pdmp3_open_feed) */
   p3_parse_opts o; if (o_in) o = *o_in; else memset(&o, 0, sizeof o);
   o.max_frames = 0; o.warmup_frames = 0; o.hop_only = 1;
-  /* default chunk: four waves of the synthesis kernel (n_sm x 3 CTAs x 4 warps x 32 frames = 56 832 frames on a B200), so that the
+  /* default chunk: four waves of the synthesis kernel (n_sm x resident warps per SM x 32 frames = 56 832 frames on a B200), so that the
    * quarter chunks at both ends of the schedule are exactly one wave and no launch ends in a mostly empty wave */
-  int64_t C = chunk_frames > 0 ? chunk_frames : 4 * (int64_t)c->n_sm * 3 * p3_synthw_warps_per_cta() * c->fpc;
+  int64_t C = chunk_frames > 0 ? chunk_frames : 4 * (int64_t)c->n_sm * p3_synthw_warps_per_sm() * c->fpc;
   C -= C % K1_FPB; if (C < K1_FPB) C = K1_FPB;
   c->chunk_frames = C; c->taps = 0;
   p3_slot *sl = &c->slot[c->cur_slot];

@@ -557,8 +557,17 @@ sw_body(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, cons
   }
 }
 
+#ifdef SW_MAXNREG                   /* a register cap instead of a CTA count: SW_WPB warps per CTA, SW_CPS CTAs per SM fit at SW_MAXNREG registers */
+#define SW_BOUNDS __maxnreg__(SW_MAXNREG)
+#ifndef SW_CPS
+#define SW_CPS (65536 / (SW_MAXNREG * SW_WPB * 32))
+#endif
+#else
+#define SW_BOUNDS __launch_bounds__(SW_WPB * 32, SW_MINB)
+#define SW_CPS SW_MINB
+#endif
 #define SW_KERNEL(NAME, ISO, CLS) \
-extern "C" __global__ void __launch_bounds__(SW_WPB * 32, SW_MINB) \
+extern "C" __global__ void SW_BOUNDS \
 NAME(const p3_frame *__restrict__ frames, const p3_gc *__restrict__ gcs, const p3_tables *__restrict__ T, int64_t f_first, int64_t f_end, int frames_per_warp, \
      const int16_t *__restrict__ is_in, const int32_t *__restrict__ count1, const uint8_t *__restrict__ scf, \
      const p3_state *__restrict__ st_in, p3_state *__restrict__ st_out, int16_t *__restrict__ pcm, const float *__restrict__ pow43s, int classify) \
@@ -579,3 +588,4 @@ static int p3_synthw_check_consts(const float *cs, const float *ca)
 
 extern "C" size_t p3_synthw_smem_bytes(void) { return SW_LUT_BYTES + SW_WPB * sizeof(sw_warp_sm); }
 extern "C" int p3_synthw_warps_per_cta(void) { return SW_WPB; }
+extern "C" int p3_synthw_warps_per_sm(void) { return SW_WPB * SW_CPS; }      /* resident warps per SM (one wave = n_sm x this x frames per warp) */
