@@ -142,3 +142,18 @@ def empty_some_parts(s, every=7):
         for b in range(pos, pos + 12):
             t[si + (b >> 3)] &= ~(0x80 >> (b & 7)) & 0xff
     return t
+
+
+def check_against_golden(g, pcm, is_huff, count1, xr_ali, y_hyb):
+    """One decoder's stage outputs against a committed fixture of the UNMODIFIED reference (tests/golden/*.npz, tools/make_golden.py):
+    Huffman output, count1 and PCM equal, the float stages equal bit for bit (+0 == -0).  Used with the oracle's arrays on the CPU
+    (tests/test_cpu_oracle.py) and with the CUDA path's taps on the GPU (tests/test_gpu_parity.py)."""
+    n = int(g["n_frames"]); nch = g["pcm"].shape[2]
+    assert pcm.shape == (n, 1152, nch), (pcm.shape, n, nch)
+    assert np.array_equal(is_huff[:n, :, :nch], g["is_huff"][:, :, :nch]), "Huffman output"
+    assert np.array_equal(count1[:n, :, :nch], g["count1"][:, :, :nch]), "count1"
+    for name, bits, got in (("requantize..antialias", g["xr_ali_bits"], xr_ali), ("hybrid synthesis", g["y_hyb_bits"], y_hyb)):
+        a = bits[:, :, :nch]; b = np.ascontiguousarray(got[:n, :, :nch], dtype=np.float32).view(np.uint32)
+        assert ((a == b) | (((a & 0x7fffffff) == 0) & ((b & 0x7fffffff) == 0))).all(), name
+    assert np.array_equal(pcm, g["pcm"]), "PCM"
+

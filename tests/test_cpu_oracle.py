@@ -37,6 +37,17 @@ def test_oracle_matches_golden(path):
     assert np.array_equal(o["frames"]["main_begin"], g["hdr"][:, 6])
 
 
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_golden_checker_on_the_oracle(path):
+    """the fixture checker the GPU parity test uses (p3harness.check_against_golden), run here on the oracle's arrays"""
+    g = np.load(path)
+    o = H.oracle_decode(g["stream"], lookahead=1152)
+    H.check_against_golden(g, o["pcm"], o["is_huff"], o["count1"], o["xr_ali"], o["y_hyb"])
+    bad = o["pcm"].copy(); bad[0, 5, 0] ^= 1                   # ... and it does notice a single flipped PCM bit
+    with pytest.raises(AssertionError):
+        H.check_against_golden(g, bad, o["is_huff"], o["count1"], o["xr_ali"], o["y_hyb"])
+
+
 def test_oracle_matches_golden_empty_parts():
     """integer stages of a stream with empty parts (part2_3_length == 0, scalefac_compress != 0) as the unmodified
     reference decodes them (tests/golden/int_only/gi_empty.npz, tools/make_golden.py)"""

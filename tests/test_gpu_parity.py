@@ -1,6 +1,7 @@
 """GPU parity tests proper: the CUDA path (through the C-ABI) against the oracle restatement, the
 compiled reference (oracle/_ref, when it travelled with the repo) and the committed fixtures.
 Bit-exact for integer stages; P3_MODE_EXACT is also bit-exact in PCM; P3_MODE_FAST within 1 LSB."""
+import glob, os
 import numpy as np, pytest
 import p3harness as H
 
@@ -45,6 +46,20 @@ def live_scalefactors(gc, nch):
 def feq(a, b):
     """float arrays equal bit for bit, +0 == -0"""
     return ((a.view(np.uint32) == b.view(np.uint32)) | ((a == 0) & (b == 0)))
+
+
+GOLD = sorted(glob.glob(os.path.join(H.ROOT, "tests", "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_exact_mode_matches_the_committed_golden_fixtures(gpu_ctx, path):
+    """The CUDA path (P3_MODE_EXACT, through the C-ABI) against the committed outputs of the UNMODIFIED reference
+    (tests/golden/*.npz: 7 stream types incl. mono, 48 kHz + CRC, count1 table B, near full scale): every stage bit for bit.
+    Needs neither the oracle nor oracle/_ref at run time."""
+    g = np.load(path)
+    gpu_ctx.reset()
+    pcm, t = gpu_ctx.decode(g["stream"], lookahead=1152, taps=True)
+    H.check_against_golden(g, pcm, t["is_huff"], t["count1"], t["xr"], t["y"])
 
 
 @pytest.mark.parametrize("name", list(VARIANTS))
